@@ -1,0 +1,157 @@
+/*
+ * kakveda_b200 -- C ABI of the B200-native GFKB fingerprint-match engine.
+ *
+ * The reference (prateekdevisingh/kakveda) is pure Python and has no FFI for this path;
+ * its one similarity entry point is the method
+ *     SimilarityEngine.score(self, query: str, corpus: List[str]) -> List[float]
+ *                                      (services/shared/similarity.py:14-20)
+ * called from the GFKB match handler (services/gfkb/app.py:86) which then takes a stable
+ * top-5 (services/gfkb/app.py:89-91).  The entry points below are what a ctypes shim
+ * backing that class binds; each one names the reference code it
+ * replaces.  Conventions: every function returns an int status (KV_OK == 0), the caller
+ * owns every buffer it passes in, no callbacks, plain pointers and sizes only.  A handle
+ * may be used from several threads (calls on one handle serialise on an internal mutex;
+ * device work runs on the handle's own CUDA stream).
+ */
+#ifndef KAKVEDA_B200_H
+#define KAKVEDA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KV_OK 0
+#define KV_ERR_INVALID 1     /* bad argument / size limit exceeded              */
+#define KV_ERR_CUDA 2        /* CUDA runtime error or no usable device          */
+#define KV_ERR_EMPTY_VOCAB 3 /* sklearn's "empty vocabulary" ValueError         */
+#define KV_ERR_NOMEM 4
+#define KV_ERR_NONASCII 5    /* raw-text featurizer met a non-ASCII byte: the   */
+                             /* caller must pre-tokenise that document itself   */
+#define KV_ERR_STATE 6       /* call order violated (e.g. query before finalize)*/
+
+/* Thread-local text of the last error raised on the calling thread ("" if none). */
+const char *kv_last_error(void);
+/* Library version string, and compile-time facts for the loader test. */
+const char *kv_version(void);
+/* Number of visible CUDA devices (0 when there is no driver/GPU); never fails. */
+int kv_device_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Host featuriser: replaces TfidfVectorizer's analyzer + vocabulary
+ * (sklearn/feature_extraction/text.py:1257 _count_vocab, :248 _word_ngrams, token
+ * pattern (?u)\b\w\w+\b :1969, lowercase=True) as used by similarity.py:17-18.
+ * Features are word 1-grams and 2-grams; a vocabulary maps feature -> dense uint32 id
+ * (identity by a 128-bit hash of the feature bytes).
+ * ---------------------------------------------------------------------------------- */
+typedef struct kv_vocab kv_vocab;
+typedef struct kv_csr kv_csr;
+
+int kv_vocab_create(kv_vocab **out);
+void kv_vocab_destroy(kv_vocab *v);
+int64_t kv_vocab_size(const kv_vocab *v);
+
+#define KV_TEXT_RAW_ASCII 0 /* docs are raw ASCII text: lower-cased + tokenised here       */
+#define KV_TEXT_TOKENS 1    /* docs are tokens already lower-cased, separated by 0x1F (any  */
+                            /* UTF-8): used by the Python shim for non-ASCII documents      */
+#define KV_TEXT_MIXED 2     /* per document: a leading 0x1F byte marks a KV_TEXT_TOKENS     */
+                            /* document (the marker is skipped), anything else is raw ASCII */
+
+/* Featurise n_docs documents stored back to back in `bytes`; document i occupies
+ * bytes[offsets[i] .. offsets[i+1]).  grow != 0 adds unseen features to the vocabulary
+ * (corpus rows); grow == 0 leaves it untouched and reports, per document, the sum of
+ * tf^2 over out-of-vocabulary features (needed for the query norm: such features have
+ * corpus df == 0).  n_threads <= 0 picks hardware concurrency.  On KV_ERR_NONASCII
+ * *bad_doc (if non-NULL) is the index of the first offending document. */
+int kv_featurize(kv_vocab *v, const char *bytes, const int64_t *offsets, int64_t n_docs,
+                 int mode, int grow, int n_threads, kv_csr **out, int64_t *bad_doc);
+
+/* Borrow the arrays of a featurised batch (valid until kv_csr_destroy):
+ * indptr[n_docs+1], ids[nnz], tf[nnz], oov_tf2[n_docs]. */
+int kv_csr_view(const kv_csr *c, int64_t *n_docs, const int64_t **indptr, const uint32_t **ids,
+                const uint32_t **tf, const double **oov_tf2);
+void kv_csr_destroy(kv_csr *c);
+
+/* ------------------------------------------------------------------------------------
+ * TF-IDF cosine index (kernels K1a/K1b/K5): replaces the arithmetic of
+ * SimilarityEngine.score -- TfidfTransformer.fit/transform (sklearn text.py:1650-1739),
+ * cosine_similarity (sklearn/metrics/pairwise.py:1742-1752) -- with a resident, row-
+ * sharded device index.  Rows are appended as CSR over vocabulary ids (append-only like
+ * data/failures.jsonl, services/gfkb/app.py:49-51,132,146), then finalize() rebuilds the
+ * query-independent statistics (df, idf tables, row norms) and the scan layout.
+ * ---------------------------------------------------------------------------------- */
+typedef struct kv_index kv_index;
+
+/* device: CUDA ordinal.  row_base: global index of this shard's first row (row ids
+ * reported by top-k are row_base + local row). */
+int kv_index_create(int device, int64_t row_base, kv_index **out);
+void kv_index_destroy(kv_index *ix);
+
+int kv_index_append(kv_index *ix, const int64_t *indptr, const uint32_t *ids, const uint32_t *tf,
+                    int64_t n_rows);
+
+/* Optional, before finalize, for a corpus sharded over several GPUs: the GLOBAL document
+ * frequency per feature id and the GLOBAL row count (else both come from the local rows). */
+int kv_index_set_global_df(kv_index *ix, const uint32_t *df, int64_t vocab_size, int64_t n_rows_global);
+
+/* Copy out the LOCAL document frequencies (length vocab_size) -- what a rank contributes
+ * to the df all-reduce of a sharded corpus.  Valid after append, before or after finalize. */
+int kv_index_local_df(kv_index *ix, uint32_t *df_out, int64_t vocab_size);
+
+int kv_index_finalize(kv_index *ix, int64_t vocab_size);
+
+int64_t kv_index_rows(const kv_index *ix);
+
+/* Drop-in path (similarity.py:14-20): float64 cosine of one query against every local
+ * row, in row order.  q_ids/q_tf: the query's in-vocabulary features; q_oov_tf2: sum of
+ * tf^2 of its out-of-vocabulary features.  out_scores: host, length kv_index_rows().
+ * Returns KV_ERR_EMPTY_VOCAB when neither the query nor any row has a feature. */
+int kv_score(kv_index *ix, const uint32_t *q_ids, const uint32_t *q_tf, int64_t q_nnz,
+             double q_oov_tf2, double *out_scores);
+
+/* Batched scan with fused top-k (services/gfkb/app.py:88-89 generalised from 5 to k<=32):
+ * for each query the k best rows ordered by (score desc, row asc) -- Python's stable
+ * sort(reverse=True).  Outputs (host): out_scores[n_q*k] float32, out_rows[n_q*k] int64
+ * (global row ids; unused tail slots: score -inf, row -1). */
+int kv_topk(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
+            const double *q_oov_tf2, int64_t n_q, int k, float *out_scores, int64_t *out_rows);
+
+/* Same, results left on the device (d_scores float32[n_q*k], d_rows int64[n_q*k], device
+ * pointers owned by the caller, e.g. torch tensors feeding the NCCL all-gather); the call
+ * returns after the work is enqueued AND completed on the handle's stream. */
+int kv_topk_device(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
+                   const double *q_oov_tf2, int64_t n_q, int k, void *d_scores, void *d_rows);
+
+/* K5: merge n_lists partial top-k lists per query (device pointers; list l of query q at
+ * [l*n_q*k + q*k], each sorted by (score desc,row asc)) into one [n_q*k] result with the
+ * same ordering.  Used after the cross-GPU all-gather. */
+int kv_merge_topk_device(int device, const void *d_scores_in, const void *d_rows_in, int n_lists,
+                         int64_t n_q, int k, void *d_scores_out, void *d_rows_out);
+
+/* Timing of the last kv_topk / kv_topk_device call on this handle, CUDA-event
+ * milliseconds on its stream:
+ * ms[0] = H2D of query structures, ms[1] = scan kernel, ms[2] = merge kernel, ms[3] = D2H. */
+int kv_index_last_timing(const kv_index *ix, float ms[4]);
+
+/* Scan-layout facts for roofline accounting: bytes[0] = stream bytes, bytes[1] = row-norm
+ * bytes, bytes[2] = chunk-pointer bytes; counts[0] = stored entries, counts[1] = folded
+ * (universal) features, counts[2] = rows, counts[3] = CTAs of the last scan launch,
+ * counts[4] = query tiles of the last scan, counts[5] = row splits of the last scan. */
+int kv_index_layout(const kv_index *ix, int64_t bytes[3], int64_t counts[6]);
+
+/* ------------------------------------------------------------------------------------
+ * Synthetic failures.jsonl-shaped signature_text generator (test / bench support; the
+ * strings have the shape services/shared/fingerprint.py:51-66 produces).  Row i of a
+ * stream is a pure function of (seed, i).  Writes rows [first, first+count) back to back
+ * into `bytes` (capacity cap) with offsets[count+1]; returns KV_ERR_NOMEM if cap is too
+ * small (needed size in offsets[count]).  dup_of_seed/dup_rows != 0 makes about half the
+ * rows exact copies of rows of another stream (queries that hit stored failures). */
+int kv_synth_signatures(uint64_t seed, int64_t first, int64_t count, uint64_t dup_of_seed,
+                        int64_t dup_rows, char *bytes, int64_t cap, int64_t *offsets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KAKVEDA_B200_H */

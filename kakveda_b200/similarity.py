@@ -1,0 +1,296 @@
+"""Host-side mirror of the reference's similarity interface, backed by the CUDA library.
+
+``SimilarityEngine`` keeps the reference's class name, constructor (no arguments) and method
+signature -- ``score(self, query: str, corpus: List[str]) -> List[float]``
+(services/shared/similarity.py:10-20) -- so ``services.gfkb.app.engine`` can be replaced by
+assignment (services/gfkb/app.py:31,86).  ``GfkbIndex`` is the resident device index the
+engine caches between calls, and the batched entry point (``topk``) the GFKB match handler's
+sort/top-5 (services/gfkb/app.py:88-91) maps onto.
+
+All arithmetic runs in libkakveda_b200.so (hand-written sm_100a kernels).  Nothing here falls
+back to scikit-learn or NumPy math: without the library or without a GPU the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+import threading
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+
+_TOKEN = re.compile(r"(?u)\b\w\w+\b")  # sklearn text.py:1969; used only for non-ASCII documents
+
+
+def _ptr(a: np.ndarray, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def pack_texts(texts: Sequence[str]) -> Tuple[bytes, np.ndarray, int]:
+    """Concatenate documents for kv_featurize.  Returns (bytes, offsets[int64 n+1], text mode).
+
+    ASCII-only batches go through as raw text (tokenised in C++).  A batch containing any
+    non-ASCII document is sent in KV_TEXT_MIXED mode: those documents are tokenised here with
+    Python's own ``str.lower`` + ``re`` (exactly what sklearn's analyzer runs, so Unicode
+    case-folding and ``\\w`` semantics cannot diverge) and passed as 0x1F-separated tokens.
+    """
+    n = len(texts)
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    joined = "".join(texts)
+    if joined.isascii() and "\x1f" not in joined:
+        if n:
+            np.cumsum(np.fromiter((len(t) for t in texts), dtype=np.int64, count=n), out=offsets[1:])
+        return joined.encode("ascii"), offsets, _capi.KV_TEXT_RAW_ASCII
+    parts: List[bytes] = []
+    for i, t in enumerate(texts):
+        if t.isascii() and not t.startswith("\x1f"):
+            b = t.encode("ascii")
+        else:
+            b = b"\x1f" + "\x1f".join(_TOKEN.findall(t.lower())).encode("utf-8")
+        parts.append(b)
+        offsets[i + 1] = offsets[i] + len(b)
+    return b"".join(parts), offsets, _capi.KV_TEXT_MIXED
+
+
+class FeatureBatch:
+    """CSR of a featurised batch; owns the native kv_csr and exposes zero-copy NumPy views."""
+
+    def __init__(self, handle: C.c_void_p):
+        lib = _capi.load()
+        self._h = handle
+        n = C.c_int64()
+        indptr = _capi.c_i64p()
+        ids = _capi.c_u32p()
+        tf = _capi.c_u32p()
+        oov = _capi.c_f64p()
+        _capi.check(lib.kv_csr_view(handle, C.byref(n), C.byref(indptr), C.byref(ids), C.byref(tf), C.byref(oov)))
+        self.n = n.value
+        self.indptr = np.ctypeslib.as_array(indptr, shape=(self.n + 1,))
+        nnz = int(self.indptr[-1])
+        if nnz:
+            self.ids = np.ctypeslib.as_array(ids, shape=(nnz,))
+            self.tf = np.ctypeslib.as_array(tf, shape=(nnz,))
+        else:
+            self.ids = np.zeros(0, dtype=np.uint32)
+            self.tf = np.zeros(0, dtype=np.uint32)
+        self.oov = np.ctypeslib.as_array(oov, shape=(self.n,)) if self.n else np.zeros(0)
+
+    def close(self) -> None:
+        if self._h is not None:
+            self.indptr = self.ids = self.tf = self.oov = None
+            _capi.load().kv_csr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Vocabulary:
+    """Word 1,2-gram vocabulary (feature -> uint32 id) shared by corpus rows and queries."""
+
+    def __init__(self):
+        lib = _capi.load()
+        h = C.c_void_p()
+        _capi.check(lib.kv_vocab_create(C.byref(h)))
+        self._h = h
+
+    def __len__(self) -> int:
+        return int(_capi.load().kv_vocab_size(self._h))
+
+    def featurize_packed(self, data, offsets: np.ndarray, mode: int, grow: bool, n_threads: int = 0) -> FeatureBatch:
+        lib = _capi.load()
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        out = C.c_void_p()
+        bad = C.c_int64(-1)
+        if isinstance(data, np.ndarray):
+            buf = data.ctypes.data_as(C.c_char_p)
+        else:
+            buf = C.c_char_p(data)
+        rc = lib.kv_featurize(self._h, buf, _ptr(offsets, C.c_int64), len(offsets) - 1, mode, 1 if grow else 0,
+                              n_threads, C.byref(out), C.byref(bad))
+        _capi.check(rc)
+        return FeatureBatch(out)
+
+    def featurize(self, texts: Sequence[str], grow: bool, n_threads: int = 0) -> FeatureBatch:
+        data, offsets, mode = pack_texts(texts)
+        return self.featurize_packed(data, offsets, mode, grow, n_threads)
+
+    def close(self) -> None:
+        if self._h is not None:
+            _capi.load().kv_vocab_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GfkbIndex:
+    """Resident TF-IDF index of one row shard of the GFKB on one B200.
+
+    ``row_base`` is the global index of the shard's first row; ``vocab`` may be shared between
+    shards living in one process.  Usage: ``add_texts`` / ``add_features`` (append-only, like
+    failures.jsonl), ``finalize`` (after every append epoch), then ``score`` / ``topk``.
+    """
+
+    def __init__(self, device: int = 0, row_base: int = 0, vocab: Optional[Vocabulary] = None):
+        lib = _capi.load()
+        self.vocab = vocab if vocab is not None else Vocabulary()
+        h = C.c_void_p()
+        _capi.check(lib.kv_index_create(device, row_base, C.byref(h)))
+        self._h = h
+        self.device = device
+        self.row_base = row_base
+
+    # -- build ---------------------------------------------------------------------------
+    def add_features(self, fb: FeatureBatch, lo: int = 0, hi: Optional[int] = None) -> None:
+        hi = fb.n if hi is None else hi
+        if hi <= lo:
+            return
+        ip = np.ascontiguousarray(fb.indptr[lo:hi + 1])
+        _capi.check(_capi.load().kv_index_append(self._h, _ptr(ip, C.c_int64), _ptr(fb.ids, C.c_uint32),
+                                                 _ptr(fb.tf, C.c_uint32), hi - lo))
+
+    def add_texts(self, texts: Sequence[str]) -> None:
+        fb = self.vocab.featurize(texts, grow=True)
+        try:
+            self.add_features(fb)
+        finally:
+            fb.close()
+
+    def local_df(self) -> np.ndarray:
+        v = len(self.vocab)
+        df = np.zeros(max(v, 1), dtype=np.uint32)
+        _capi.check(_capi.load().kv_index_local_df(self._h, _ptr(df, C.c_uint32), v))
+        return df[:v]
+
+    def set_global_df(self, df: np.ndarray, n_rows_global: int) -> None:
+        df = np.ascontiguousarray(df, dtype=np.uint32)
+        _capi.check(_capi.load().kv_index_set_global_df(self._h, _ptr(df, C.c_uint32), len(df), n_rows_global))
+
+    def finalize(self) -> None:
+        _capi.check(_capi.load().kv_index_finalize(self._h, len(self.vocab)))
+
+    @property
+    def n_rows(self) -> int:
+        return int(_capi.load().kv_index_rows(self._h))
+
+    # -- query ---------------------------------------------------------------------------
+    def score_features(self, ids: np.ndarray, tf: np.ndarray, oov_tf2: float) -> np.ndarray:
+        out = np.empty(self.n_rows, dtype=np.float64)
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        tf = np.ascontiguousarray(tf, dtype=np.uint32)
+        _capi.check(_capi.load().kv_score(self._h, _ptr(ids, C.c_uint32), _ptr(tf, C.c_uint32), len(ids),
+                                          float(oov_tf2), _ptr(out, C.c_double)))
+        return out
+
+    def score(self, query: str) -> np.ndarray:
+        """float64 cosine of ``query`` against every local row (K1a)."""
+        fb = self.vocab.featurize([query], grow=False)
+        try:
+            return self.score_features(fb.ids, fb.tf, float(fb.oov[0]))
+        finally:
+            fb.close()
+
+    def topk_features(self, fb: FeatureBatch, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        scores = np.empty((fb.n, k), dtype=np.float32)
+        rows = np.empty((fb.n, k), dtype=np.int64)
+        _capi.check(_capi.load().kv_topk(self._h, _ptr(fb.indptr, C.c_int64), _ptr(fb.ids, C.c_uint32),
+                                         _ptr(fb.tf, C.c_uint32), _ptr(fb.oov, C.c_double), fb.n, k,
+                                         _ptr(scores, C.c_float), _ptr(rows, C.c_int64)))
+        return scores, rows
+
+    def topk_features_device(self, fb: FeatureBatch, k: int, d_scores_ptr: int, d_rows_ptr: int) -> None:
+        """Results stay on the device: float32[n,k] / int64[n,k] buffers owned by the caller."""
+        _capi.check(_capi.load().kv_topk_device(self._h, _ptr(fb.indptr, C.c_int64), _ptr(fb.ids, C.c_uint32),
+                                                _ptr(fb.tf, C.c_uint32), _ptr(fb.oov, C.c_double), fb.n, k,
+                                                C.c_void_p(d_scores_ptr), C.c_void_p(d_rows_ptr)))
+
+    def topk(self, queries: Sequence[str], k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """(scores float32 [Q,k], rows int64 [Q,k]) ordered by (score desc, row asc) (K1b+K5)."""
+        fb = self.vocab.featurize(queries, grow=False)
+        try:
+            return self.topk_features(fb, k)
+        finally:
+            fb.close()
+
+    def last_timing_ms(self) -> Tuple[float, float, float, float]:
+        ms = (C.c_float * 4)()
+        _capi.check(_capi.load().kv_index_last_timing(self._h, ms))
+        return tuple(ms)
+
+    def layout(self) -> dict:
+        b = (C.c_int64 * 3)()
+        c = (C.c_int64 * 6)()
+        _capi.check(_capi.load().kv_index_layout(self._h, b, c))
+        return {"stream_bytes": b[0], "norm_bytes": b[1], "chunkptr_bytes": b[2], "entries": c[0],
+                "universal_features": c[1], "rows": c[2], "last_ctas": c[3], "last_tiles": c[4],
+                "last_splits": c[5]}
+
+    def close(self) -> None:
+        if self._h is not None:
+            _capi.load().kv_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class SimilarityEngine:
+    """Drop-in for services.shared.similarity.SimilarityEngine (similarity.py:10-20).
+
+    Same contract: ``score(query, corpus)`` returns ``len(corpus)`` Python floats (float64
+    TF-IDF(1,2-gram) cosine, refit semantics included) in corpus order; ``[]`` for an empty
+    corpus; ``ValueError`` when no document has a token.  The engine caches the device index of
+    the last corpus it saw (GFKB re-reads failures.jsonl per request, app.py:81, but the rows
+    only ever grow by appends, app.py:132,146): an unchanged corpus is reused, a corpus that
+    extends the cached one is appended, anything else is rebuilt.  Thread-safe (match() runs on
+    a worker pool).
+    """
+
+    device: int = 0
+    _lock: threading.Lock = field(default_factory=threading.Lock, repr=False, compare=False)
+    _index: Optional[GfkbIndex] = field(default=None, repr=False, compare=False)
+    _sig: Tuple[int, int] = field(default=(0, 0), repr=False, compare=False)
+
+    def _sync_index(self, corpus: Sequence[str]) -> GfkbIndex:
+        n = len(corpus)
+        sig = (n, hash(tuple(corpus)))
+        if self._index is not None and sig == self._sig:
+            return self._index
+        old_n = self._sig[0]
+        if self._index is not None and 0 < old_n < n and hash(tuple(corpus[:old_n])) == self._sig[1]:
+            self._index.add_texts(corpus[old_n:])
+        else:
+            if self._index is not None:
+                self._index.close()
+            self._index = GfkbIndex(device=self.device)
+            self._index.add_texts(corpus)
+        self._index.finalize()
+        self._sig = sig
+        return self._index
+
+    def score(self, query: str, corpus: List[str]) -> List[float]:
+        if not corpus:
+            return []
+        with self._lock:
+            return self._sync_index(corpus).score(query).tolist()
+
+    def topk(self, queries: Sequence[str], corpus: Sequence[str], k: int = 5) -> Tuple[np.ndarray, np.ndarray]:
+        """Batched form: the k best rows per query, ties to the lower row (gfkb/app.py:89)."""
+        if not corpus:
+            return (np.zeros((len(queries), 0), np.float32), np.zeros((len(queries), 0), np.int64))
+        with self._lock:
+            return self._sync_index(corpus).topk(queries, min(k, 32))
