@@ -124,6 +124,14 @@ int kv_topk(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const 
 int kv_topk_device(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
                    const double *q_oov_tf2, int64_t n_q, int k, void *d_scores, void *d_rows);
 
+/* The two halves of kv_topk_device, for callers that keep a query batch resident:
+ * kv_query_upload does the host-side preparation and the host->device copies of a batch;
+ * kv_topk_resident runs scan + merge for the uploaded batch (device work only) and returns
+ * when it has completed.  The batch stays valid until the next upload or finalize. */
+int kv_query_upload(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
+                    const double *q_oov_tf2, int64_t n_q);
+int kv_topk_resident(kv_index *ix, int k, void *d_scores, void *d_rows);
+
 /* K5: merge n_lists partial top-k lists per query (device pointers; list l of query q at
  * [l*n_q*k + q*k], each sorted by (score desc,row asc)) into one [n_q*k] result with the
  * same ordering.  Used after the cross-GPU all-gather. */
@@ -138,8 +146,9 @@ int kv_index_last_timing(const kv_index *ix, float ms[4]);
 /* Scan-layout facts for roofline accounting: bytes[0] = stream bytes, bytes[1] = row-norm
  * bytes, bytes[2] = chunk-pointer bytes; counts[0] = stored entries, counts[1] = folded
  * (universal) features, counts[2] = rows, counts[3] = CTAs of the last scan launch,
- * counts[4] = query tiles of the last scan, counts[5] = row splits of the last scan. */
-int kv_index_layout(const kv_index *ix, int64_t bytes[3], int64_t counts[6]);
+ * counts[4] = query tiles of the last scan, counts[5] = row splits of the last scan,
+ * counts[6] = host->device bytes of the last query upload, counts[7] = tf-overflow entries. */
+int kv_index_layout(const kv_index *ix, int64_t bytes[3], int64_t counts[8]);
 
 /* ------------------------------------------------------------------------------------
  * Synthetic failures.jsonl-shaped signature_text generator (test / bench support; the

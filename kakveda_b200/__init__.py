@@ -5,11 +5,11 @@ fingerprints against the Global Failure Knowledge Base (``SimilarityEngine.score
 services/shared/similarity.py:14-20, as called by services/gfkb/app.py:86) -- as hand-written
 sm_100a CUDA behind a C ABI (include/kakveda_b200.h).  See DESIGN.md.
 """
-from .fingerprint import fingerprint, fingerprint_text, fingerprint_u64, normalize_prompt, signature_text
+from .fingerprint import fingerprint_text, fingerprint_u64, normalize_prompt, signature_text
 from .similarity import FeatureBatch, GfkbIndex, SimilarityEngine, Vocabulary
 
 __all__ = [
     "SimilarityEngine", "GfkbIndex", "Vocabulary", "FeatureBatch",
-    "signature_text", "fingerprint", "fingerprint_text", "fingerprint_u64", "normalize_prompt",
+    "signature_text", "fingerprint_text", "fingerprint_u64", "normalize_prompt",
 ]
 __version__ = "0.1.0"

@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 KV_OK, KV_ERR_INVALID, KV_ERR_CUDA, KV_ERR_EMPTY_VOCAB, KV_ERR_NOMEM, KV_ERR_NONASCII, KV_ERR_STATE = range(7)
-KV_TEXT_RAW_ASCII, KV_TEXT_TOKENS = 0, 1
+KV_TEXT_RAW_ASCII, KV_TEXT_TOKENS, KV_TEXT_MIXED = 0, 1, 2
 
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libkakveda_b200.so"
 _lib = None
@@ -45,6 +45,8 @@ SIGNATURES = {
     "kv_topk": (C.c_int, [C.c_void_p, c_i64p, c_u32p, c_u32p, c_f64p, C.c_int64, C.c_int, c_f32p, c_i64p]),
     "kv_topk_device": (C.c_int, [C.c_void_p, c_i64p, c_u32p, c_u32p, c_f64p, C.c_int64, C.c_int, C.c_void_p,
                                  C.c_void_p]),
+    "kv_query_upload": (C.c_int, [C.c_void_p, c_i64p, c_u32p, c_u32p, c_f64p, C.c_int64]),
+    "kv_topk_resident": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "kv_merge_topk_device": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
                                        C.c_void_p]),
     "kv_index_last_timing": (C.c_int, [C.c_void_p, c_f32p]),

@@ -204,50 +204,58 @@ __global__ void __launch_bounds__(256) tfidf_score_kernel(ScoreParams P) {
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t c = warp; c < P.n_chunks; c += n_warps) {
     const int64_t p0 = P.chunkptr[c], p1 = P.chunkptr[c + 1];
-    int64_t row = c * CHUNK_ROWS;
-    double cu = 0.0, cv = 0.0;  // partial sums of a row that straddles a 32-entry group
+    const int64_t row0 = c * CHUNK_ROWS;
+    int row_in = 0;
+    // Per-row sums are accumulated strictly in entry order (warp-uniform accumulators), so rows with
+    // identical text get bit-identical scores wherever they sit in the stream -- the GFKB handler's
+    // stable sort (services/gfkb/app.py:89) then orders duplicate rows exactly like the reference.
+    double du = 0.0, dv = 0.0, mine = 0.0;
     for (int64_t p = p0; p < p1; p += 32) {
-      uint32_t e = (p + lane < p1) ? P.stream[p + lane] : ((FID_NONE << 5) | 1u);
-      uint32_t fid = (e >> 5) & FID_MASK, tf = e & 31u;
-      bool last = (e >> 31) != 0;
-      const uint32_t lastmask = __ballot_sync(FULL, last);
-      const uint32_t lower = lastmask & ((1u << lane) - 1u);
-      const int my_row_off = __popc(lower);
+      const uint32_t e = (p + lane < p1) ? P.stream[p + lane] : ((FID_NONE << 5) | 1u);
+      const uint32_t fid = (e >> 5) & FID_MASK;
+      const uint32_t lastmask = __ballot_sync(FULL, (e >> 31) != 0);
+      const int my_row_off = __popc(lastmask & ((1u << lane) - 1u));
       double wu = 0.0, wv = 0.0;
+      bool hit = false;
       if (fid != FID_NONE) {
         uint32_t h = hash_fid(fid, P.log_h);
         for (;;) {
           uint32_t k = keys[h];
           if (k == KEY_EMPTY) break;
           if (k == fid) {
-            if (tf == TF_OVF) tf = ovf_lookup(P.ovf_keys, P.ovf_vals, P.n_ovf, row + my_row_off, fid);
+            uint32_t tf = e & 31u;
+            if (tf == TF_OVF) tf = ovf_lookup(P.ovf_keys, P.ovf_vals, P.n_ovf, row0 + row_in + my_row_off, fid);
             double f = (double)tf;
             wu = f * qw[h];
             wv = f * f * qd[h];
+            hit = true;
             break;
           }
           h = (h + 1) & (H - 1);
         }
       }
-      if (lane == 0) { wu += cu; wv += cv; }
-      const int segstart = lower ? 32 - __clz(lower) : 0;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        double ou = __shfl_up_sync(FULL, wu, d), ov = __shfl_up_sync(FULL, wv, d);
-        if (lane >= segstart + d) { wu += ou; wv += ov; }
+      const uint32_t hitmask = __ballot_sync(FULL, hit);
+      uint32_t ev = hitmask | lastmask;
+      while (ev) {
+        const int j = __ffs(ev) - 1;
+        ev &= ev - 1;
+        if ((hitmask >> j) & 1u) {
+          du += __shfl_sync(FULL, wu, j);
+          dv += __shfl_sync(FULL, wv, j);
+        }
+        if ((lastmask >> j) & 1u) {
+          const int64_t r = row0 + row_in;
+          const double dot = P.dotU + du;
+          const double den = P.nq * (P.B64[r] + P.corrU + dv);
+          const double sc = (den > 0.0 && dot != 0.0) ? dot / sqrt(den) : 0.0;
+          if ((row_in & 31) == lane) mine = sc;
+          row_in++;
+          du = 0.0; dv = 0.0;
+          if ((row_in & 31) == 0) P.out[row0 + row_in - 32 + lane] = mine;  // coalesced store of 32 rows
+        }
       }
-      if (last) {
-        int64_t r = row + my_row_off;
-        double dot = P.dotU + wu;
-        double den = P.nq * (P.B64[r] + P.corrU + wv);
-        P.out[r] = (den > 0.0 && dot != 0.0) ? dot / sqrt(den) : 0.0;
-      }
-      double eu = __shfl_sync(FULL, wu, 31), ev = __shfl_sync(FULL, wv, 31);
-      bool closed = (lastmask >> 31) != 0;
-      cu = closed ? 0.0 : eu;
-      cv = closed ? 0.0 : ev;
-      row += __popc(lastmask);
     }
+    if ((row_in & 31) != 0 && lane < (row_in & 31)) P.out[row0 + (row_in & ~31) + lane] = mine;
   }
 }
 
@@ -657,6 +665,13 @@ struct kv_index {
   DevBuf<unsigned char> d_qtab;
   DevBuf<double> d_scores;
 
+  // query batch currently resident on the device (kv_query_upload / first half of kv_topk)
+  bool batch_valid = false;
+  int64_t batch_q = 0, batch_tiles = 0, batch_h2d_bytes = 0;
+  std::vector<int64_t> irr_q, irr_indptr;
+  std::vector<uint32_t> irr_ids, irr_tf;
+  std::vector<double> irr_oov;
+
   float last_ms[4] = {0, 0, 0, 0};
   int64_t last_ctas = 0, last_tiles = 0, last_splits = 0;
 };
@@ -941,6 +956,7 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
   for (uint8_t u : ix->h_univ) ix->n_univ += u;
   ix->V = V;
   ix->finalized = true;
+  ix->batch_valid = false;
   return KV_OK;
 }
 
@@ -1003,24 +1019,22 @@ int kv_score(kv_index *ix, const uint32_t *q_ids, const uint32_t *q_tf, int64_t 
   return score_impl(ix, q_ids, q_tf, q_nnz, q_oov_tf2, out_scores);
 }
 
-static int topk_impl(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
-                     const double *q_oov, int64_t n_q, int k, float *h_scores, int64_t *h_rows, void *d_scores_out,
-                     void *d_rows_out) {
-  if (!ix || n_q < 0 || k < 1 || k > 32 || (n_q > 0 && !q_indptr))
-    return kv_fail(KV_ERR_INVALID, "kv_topk: bad arguments (k must be 1..32)");
-  std::lock_guard<std::mutex> g(ix->mu);
+// ---- batched top-k, in two halves: prepare_batch (host work + H2D) and run_batch (device only) ----
+static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
+                         const double *q_oov, int64_t n_q) {
   if (!ix->finalized) return kv_fail(KV_ERR_STATE, "kv_topk: index not finalized");
-  if (n_q == 0) return KV_OK;
   if (n_q >= (1LL << 31)) return kv_fail(KV_ERR_INVALID, "kv_topk: too many queries in one call");
   KV_CUDA(cudaSetDevice(ix->device));
   cudaStream_t s = ix->stream;
   const int QT = Tile::QT, H = Tile::H;
+  ix->batch_valid = false;
+  ix->irr_q.clear(); ix->irr_indptr.assign(1, 0); ix->irr_ids.clear(); ix->irr_tf.clear(); ix->irr_oov.clear();
 
-  // ---- host: per-query constants, tile packing, tile tables ----
-  KV_CUDA(ix->h_qconst.ensure(3 * n_q));
-  float *c_nq = ix->h_qconst.p, *c_dotU = c_nq + n_q, *c_corrU = c_dotU + n_q;
+  // host: per-query constants, tile packing, tile tables
+  KV_CUDA(ix->h_qconst.ensure(4 * n_q));
+  float *c_nq = ix->h_qconst.p, *c_dotU = c_nq + n_q, *c_corrU = c_dotU + n_q, *c_ninf = c_corrU + n_q;
   std::vector<QueryPrep> qp((size_t)n_q);
-  std::vector<int64_t> irregular;
+  std::vector<char> is_irr((size_t)n_q, 0);
   std::vector<TileDesc> tiles;
   {
     TileDesc cur{0, 0, 0, 0};
@@ -1032,10 +1046,18 @@ static int topk_impl(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_id
       c_nq[q] = (float)qp[(size_t)q].nq;
       c_dotU[q] = (float)qp[(size_t)q].dotU;
       c_corrU[q] = (float)qp[(size_t)q].corrU;
+      c_ninf[q] = -INFINITY;
       int nf = (int)qp[(size_t)q].fid.size(), nx = 0;
       for (uint32_t f : qp[(size_t)q].tfq) nx += f > 1;
-      bool irr = nf > H / 2 || nx > TXCAP;
-      if (irr) { irregular.push_back(q); nf = 0; nx = 0; }
+      if (nf > H / 2 || nx > TXCAP) {  // too many features for a tile: full float64 scan + selection instead
+        is_irr[(size_t)q] = 1;
+        ix->irr_q.push_back(q);
+        ix->irr_ids.insert(ix->irr_ids.end(), q_ids + a, q_ids + b);
+        ix->irr_tf.insert(ix->irr_tf.end(), q_tf + a, q_tf + b);
+        ix->irr_indptr.push_back((int64_t)ix->irr_ids.size());
+        ix->irr_oov.push_back(q_oov ? q_oov[q] : 0.0);
+        nf = 0; nx = 0;
+      }
       if (cur.q_count == QT || cur_feats + nf > H / 2 || cur.n_extras + nx > TXCAP) {
         tiles.push_back(cur);
         cur = TileDesc{(int)q, 0, 0, 0};
@@ -1050,8 +1072,6 @@ static int topk_impl(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_id
   const int64_t n_tiles = (int64_t)tiles.size();
   KV_CUDA(ix->h_tables.ensure(n_tiles * (int64_t)Tile::table_bytes));
   KV_CUDA(ix->h_tiles.ensure(n_tiles));
-  std::vector<char> is_irr((size_t)n_q, 0);
-  for (int64_t q : irregular) is_irr[(size_t)q] = 1;
   for (int64_t t = 0; t < n_tiles; t++) {
     unsigned char *tb = ix->h_tables.p + (size_t)t * Tile::table_bytes;
     uint32_t *keys = (uint32_t *)(tb + Tile::off_keys);
@@ -1090,41 +1110,45 @@ static int topk_impl(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_id
     td.n_extras = nx;
     ix->h_tiles.p[t] = td;
   }
+  KV_CUDA(ix->d_tables.ensure(n_tiles * (int64_t)Tile::table_bytes));
+  KV_CUDA(ix->d_tiles.ensure(n_tiles));
+  KV_CUDA(ix->d_qconst.ensure(4 * n_q));
+  KV_CUDA(cudaEventRecord(ix->ev[0], s));
+  KV_CUDA(cudaMemcpyAsync(ix->d_tables.p, ix->h_tables.p, (size_t)n_tiles * Tile::table_bytes, cudaMemcpyHostToDevice, s));
+  KV_CUDA(cudaMemcpyAsync(ix->d_tiles.p, ix->h_tiles.p, (size_t)n_tiles * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
+  KV_CUDA(cudaMemcpyAsync(ix->d_qconst.p, ix->h_qconst.p, (size_t)4 * n_q * sizeof(float), cudaMemcpyHostToDevice, s));
+  KV_CUDA(cudaEventRecord(ix->ev[1], s));
+  KV_CUDA(cudaStreamSynchronize(s));  // the pinned staging buffers may be rewritten by the next call
+  ix->batch_q = n_q;
+  ix->batch_tiles = n_tiles;
+  ix->batch_h2d_bytes = n_tiles * (int64_t)(Tile::table_bytes + sizeof(TileDesc)) + 4 * n_q * (int64_t)sizeof(float);
+  ix->batch_valid = true;
+  cudaEventElapsedTime(&ix->last_ms[0], ix->ev[0], ix->ev[1]);
+  return KV_OK;
+}
 
-  // ---- launch geometry: tiles x row-splits; aim at >= 8 waves of resident CTAs ----
+// Device-only half: scan + merge (+ fallback scans for irregular queries) of the uploaded batch.
+static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
+  if (!ix->batch_valid) return kv_fail(KV_ERR_STATE, "kv_topk_resident: no query batch uploaded");
+  if (k < 1 || k > 32) return kv_fail(KV_ERR_INVALID, "kv_topk: k must be 1..32");
+  KV_CUDA(cudaSetDevice(ix->device));
+  cudaStream_t s = ix->stream;
+  const int64_t n_q = ix->batch_q, n_tiles = ix->batch_tiles;
+  // launch geometry: tiles x row-splits; aim at >= 8 waves of resident CTAs
   const int ctas_per_sm = 2;
   int64_t want = (int64_t)ix->sm_count * ctas_per_sm * 8;
   int64_t n_splits = (want + n_tiles - 1) / n_tiles;
   n_splits = std::max<int64_t>(1, std::min<int64_t>(n_splits, std::max<int64_t>(1, ix->n_chunks / 8)));
   n_splits = std::min<int64_t>(n_splits, 2048);
   ix->last_tiles = n_tiles; ix->last_splits = n_splits; ix->last_ctas = n_tiles * n_splits;
-
-  KV_CUDA(ix->d_tables.ensure(n_tiles * (int64_t)Tile::table_bytes));
-  KV_CUDA(ix->d_tiles.ensure(n_tiles));
-  KV_CUDA(ix->d_qconst.ensure(3 * n_q));
   KV_CUDA(ix->d_gthr.ensure(n_q));
   KV_CUDA(ix->d_part_s.ensure(n_splits * n_q * k));
   KV_CUDA(ix->d_part_r.ensure(n_splits * n_q * k));
-  float *d_out_s = (float *)d_scores_out;
-  long long *d_out_r = (long long *)d_rows_out;
-  if (!d_out_s) {
-    KV_CUDA(ix->d_out_s.ensure(n_q * k)); KV_CUDA(ix->d_out_r.ensure(n_q * k));
-    d_out_s = ix->d_out_s.p; d_out_r = ix->d_out_r.p;
-  }
 
-  KV_CUDA(cudaEventRecord(ix->ev[0], s));
-  KV_CUDA(cudaMemcpyAsync(ix->d_tables.p, ix->h_tables.p, (size_t)n_tiles * Tile::table_bytes, cudaMemcpyHostToDevice, s));
-  KV_CUDA(cudaMemcpyAsync(ix->d_tiles.p, ix->h_tiles.p, (size_t)n_tiles * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
-  KV_CUDA(cudaMemcpyAsync(ix->d_qconst.p, ix->h_qconst.p, (size_t)3 * n_q * sizeof(float), cudaMemcpyHostToDevice, s));
-  {
-    // gthr := -inf (as float bits) for every query
-    // 0xFF800000 (-inf) is not a memset byte pattern: stage it through the pinned output buffer
-    KV_CUDA(ix->h_out_s.ensure(std::max<int64_t>(n_q * k, n_q)));
-    for (int64_t q = 0; q < n_q; q++) ix->h_out_s.p[q] = -INFINITY;
-    KV_CUDA(cudaMemcpyAsync(ix->d_gthr.p, ix->h_out_s.p, (size_t)n_q * sizeof(float), cudaMemcpyHostToDevice, s));
-  }
   KV_CUDA(cudaEventRecord(ix->ev[1], s));
   if (ix->n_rows > 0) {
+    // global lower bounds of the k-th score start at -inf (staged as the 4th constants column)
+    KV_CUDA(cudaMemcpyAsync(ix->d_gthr.p, ix->d_qconst.p + 3 * n_q, (size_t)n_q * sizeof(float), cudaMemcpyDeviceToDevice, s));
     TopkParams P;
     P.stream = ix->d_stream.p; P.chunkptr = ix->d_chunkptr.p; P.n_chunks = ix->n_chunks; P.n_rows = ix->n_rows;
     P.row_base = ix->row_base; P.B32 = ix->d_B32.p; P.ovf_keys = ix->d_ovf_keys.p; P.ovf_vals = ix->d_ovf_vals.p;
@@ -1142,31 +1166,48 @@ static int topk_impl(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_id
     dim3 grid((unsigned)n_tiles, (unsigned)n_splits);
     tfidf_topk_kernel<TG, TLOGH, TXCAP><<<grid, 256, smem, s>>>(P);
     KV_CUDA(cudaGetLastError());
-  }
-  KV_CUDA(cudaEventRecord(ix->ev[2], s));
-  if (ix->n_rows > 0) {
-    const float *in_s = ix->d_part_s.p;
-    const long long *in_r = ix->d_part_r.p;
-    merge_topk_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, s>>>(in_s, in_r, (int)n_splits, n_q, k, d_out_s, d_out_r);
+    KV_CUDA(cudaEventRecord(ix->ev[2], s));
+    merge_topk_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, s>>>(ix->d_part_s.p, ix->d_part_r.p, (int)n_splits,
+                                                                         n_q, k, d_out_s, d_out_r);
     KV_CUDA(cudaGetLastError());
+    for (size_t i = 0; i < ix->irr_q.size(); i++) {
+      const int64_t q = ix->irr_q[i], a = ix->irr_indptr[i], b = ix->irr_indptr[i + 1];
+      int rc = score_impl(ix, ix->irr_ids.data() + a, ix->irr_tf.data() + a, b - a, ix->irr_oov[i], nullptr);
+      if (rc != KV_OK) return rc;
+      select_topk_kernel<<<1, 1024, 0, s>>>(ix->d_scores.p, ix->n_rows, ix->row_base, k, d_out_s + q * k, d_out_r + q * k);
+      KV_CUDA(cudaGetLastError());
+    }
   } else {
+    KV_CUDA(cudaEventRecord(ix->ev[2], s));
     std::vector<float> es((size_t)(n_q * k), -INFINITY);
     std::vector<long long> er((size_t)(n_q * k), -1);
     KV_CUDA(cudaMemcpyAsync(d_out_s, es.data(), es.size() * 4, cudaMemcpyHostToDevice, s));
     KV_CUDA(cudaMemcpyAsync(d_out_r, er.data(), er.size() * 8, cudaMemcpyHostToDevice, s));
     KV_CUDA(cudaStreamSynchronize(s));
   }
-  // irregular queries (too many features for a tile): full float64 scan + selection, one by one
-  if (!irregular.empty() && ix->n_rows > 0) {
-    for (int64_t q : irregular) {
-      const int64_t a = q_indptr[q], b = q_indptr[q + 1];
-      int rc = score_impl(ix, q_ids + a, q_tf + a, b - a, q_oov ? q_oov[q] : 0.0, nullptr);
-      if (rc != KV_OK) return rc;
-      select_topk_kernel<<<1, 1024, 0, s>>>(ix->d_scores.p, ix->n_rows, ix->row_base, k, d_out_s + q * k, d_out_r + q * k);
-      KV_CUDA(cudaGetLastError());
-    }
-  }
   KV_CUDA(cudaEventRecord(ix->ev[3], s));
+  return KV_OK;
+}
+
+static int topk_impl(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
+                     const double *q_oov, int64_t n_q, int k, float *h_scores, int64_t *h_rows, void *d_scores_out,
+                     void *d_rows_out) {
+  if (!ix || n_q < 0 || k < 1 || k > 32 || (n_q > 0 && !q_indptr))
+    return kv_fail(KV_ERR_INVALID, "kv_topk: bad arguments (k must be 1..32)");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (!ix->finalized) return kv_fail(KV_ERR_STATE, "kv_topk: index not finalized");
+  if (n_q == 0) return KV_OK;
+  int rc = prepare_batch(ix, q_indptr, q_ids, q_tf, q_oov, n_q);
+  if (rc != KV_OK) return rc;
+  cudaStream_t s = ix->stream;
+  float *d_out_s = (float *)d_scores_out;
+  long long *d_out_r = (long long *)d_rows_out;
+  if (!d_out_s) {
+    KV_CUDA(ix->d_out_s.ensure(n_q * k)); KV_CUDA(ix->d_out_r.ensure(n_q * k));
+    d_out_s = ix->d_out_s.p; d_out_r = ix->d_out_r.p;
+  }
+  rc = run_batch(ix, k, d_out_s, d_out_r);
+  if (rc != KV_OK) return rc;
   if (h_scores) {
     KV_CUDA(ix->h_out_s.ensure(n_q * k)); KV_CUDA(ix->h_out_r.ensure(n_q * k));
     KV_CUDA(cudaMemcpyAsync(ix->h_out_s.p, d_out_s, (size_t)n_q * k * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -1178,7 +1219,25 @@ static int topk_impl(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_id
     memcpy(h_scores, ix->h_out_s.p, (size_t)n_q * k * sizeof(float));
     memcpy(h_rows, ix->h_out_r.p, (size_t)n_q * k * sizeof(int64_t));
   }
-  for (int i = 0; i < 4; i++) cudaEventElapsedTime(&ix->last_ms[i], ix->ev[i], ix->ev[i + 1]);
+  for (int i = 1; i < 4; i++) cudaEventElapsedTime(&ix->last_ms[i], ix->ev[i], ix->ev[i + 1]);
+  return KV_OK;
+}
+
+int kv_query_upload(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
+                    const double *q_oov_tf2, int64_t n_q) {
+  if (!ix || n_q < 1 || !q_indptr) return kv_fail(KV_ERR_INVALID, "kv_query_upload: bad arguments");
+  std::lock_guard<std::mutex> g(ix->mu);
+  return prepare_batch(ix, q_indptr, q_ids, q_tf, q_oov_tf2, n_q);
+}
+
+int kv_topk_resident(kv_index *ix, int k, void *d_scores, void *d_rows) {
+  if (!ix || !d_scores || !d_rows) return kv_fail(KV_ERR_INVALID, "kv_topk_resident: bad arguments");
+  std::lock_guard<std::mutex> g(ix->mu);
+  int rc = run_batch(ix, k, (float *)d_scores, (long long *)d_rows);
+  if (rc != KV_OK) return rc;
+  KV_CUDA(cudaEventRecord(ix->ev[4], ix->stream));
+  KV_CUDA(cudaStreamSynchronize(ix->stream));
+  for (int i = 1; i < 4; i++) cudaEventElapsedTime(&ix->last_ms[i], ix->ev[i], ix->ev[i + 1]);
   return KV_OK;
 }
 
@@ -1214,13 +1273,14 @@ int kv_index_last_timing(const kv_index *ix, float ms[4]) {
   return KV_OK;
 }
 
-int kv_index_layout(const kv_index *ix, int64_t bytes[3], int64_t counts[6]) {
+int kv_index_layout(const kv_index *ix, int64_t bytes[3], int64_t counts[8]) {
   if (!ix || !bytes || !counts) return kv_fail(KV_ERR_INVALID, "kv_index_layout: bad arguments");
   bytes[0] = ix->stream_len * 4;
   bytes[1] = ix->n_rows * 4;
   bytes[2] = (ix->n_chunks + 1) * 8;
   counts[0] = ix->stream_len; counts[1] = ix->n_univ; counts[2] = ix->n_rows;
   counts[3] = ix->last_ctas; counts[4] = ix->last_tiles; counts[5] = ix->last_splits;
+  counts[6] = ix->batch_h2d_bytes; counts[7] = ix->n_ovf;
   return KV_OK;
 }
 

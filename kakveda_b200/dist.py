@@ -1,0 +1,122 @@
+"""Row-sharded GFKB over the GPUs of one box.
+
+One process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch).  Corpus rows are split
+contiguously (rank r owns rows [n*r/W, n*(r+1)/W)); every rank sees the same query batch.  The
+only exchanges are
+
+* once per append epoch: an all-reduce(sum) of the per-feature document-frequency vector, because
+  TF-IDF's idf and row norms use GLOBAL df and N (``allreduce_df``);
+* once per query batch: ONE all-gather of the per-shard partial top-k (scores float32, rows int64),
+  followed by a local merge ordered by (score desc, row asc) -- identical on every rank
+  (``gather_topk`` + ``kv_merge_topk_device``).
+
+Every rank featurises the whole corpus text so that feature ids agree without exchanging the
+vocabulary (ids are deterministic, see csrc/featurizer.cpp); only its own rows go to its GPU.
+The communication helpers take any torch tensors, so the world_size-2 ``gloo`` tests run them on
+CPU; the compute stays in libkakveda_b200 (CUDA only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _capi
+from .similarity import FeatureBatch, GfkbIndex, Vocabulary
+
+
+def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
+    return n_rows * rank // world, n_rows * (rank + 1) // world
+
+
+def allreduce_df(local_df, group=None):
+    """Sum per-feature document frequencies over ranks, in place; returns the tensor."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(local_df, op=dist.ReduceOp.SUM, group=group)
+    return local_df
+
+
+def gather_topk(scores, rows, group=None):
+    """All-gather per-shard partial top-k: [Q,k] -> ([W,Q,k] scores, [W,Q,k] rows) on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        return scores.unsqueeze(0), rows.unsqueeze(0)
+    gs = torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
+    gr = torch.empty((world,) + tuple(rows.shape), dtype=rows.dtype, device=rows.device)
+    dist.all_gather_into_tensor(gs, scores.contiguous(), group=group)
+    dist.all_gather_into_tensor(gr, rows.contiguous(), group=group)
+    return gs, gr
+
+
+def merge_on_device(device: int, gs, gr):
+    """K5 on the gathered lists: ([W,Q,k],[W,Q,k]) -> ([Q,k],[Q,k])."""
+    import torch
+
+    w, q, k = gs.shape
+    out_s = torch.empty((q, k), dtype=torch.float32, device=gs.device)
+    out_r = torch.empty((q, k), dtype=torch.int64, device=gs.device)
+    _capi.check(_capi.load().kv_merge_topk_device(device, C.c_void_p(gs.data_ptr()), C.c_void_p(gr.data_ptr()), w, q, k,
+                                                  C.c_void_p(out_s.data_ptr()), C.c_void_p(out_r.data_ptr())))
+    return out_s, out_r
+
+
+class ShardedGfkb:
+    """This rank's shard of a GFKB spread over ``world`` GPUs."""
+
+    def __init__(self, device: int, rank: int = 0, world: int = 1, group=None):
+        self.device, self.rank, self.world, self.group = device, rank, world, group
+        self.vocab = Vocabulary()
+        self.index: Optional[GfkbIndex] = None
+        self.n_global = 0
+
+    def build_packed(self, data, offsets: np.ndarray, mode: int = 0, n_threads: int = 0) -> None:
+        import torch
+
+        fb = self.vocab.featurize_packed(data, offsets, mode, grow=True, n_threads=n_threads)
+        self.n_global = fb.n
+        lo, hi = shard_bounds(fb.n, self.world, self.rank)
+        self.index = GfkbIndex(device=self.device, row_base=lo, vocab=self.vocab)
+        self.index.add_features(fb, lo, hi)
+        fb.close()
+        if self.world > 1:
+            df = torch.from_numpy(self.index.local_df().astype(np.int32)).to(f"cuda:{self.device}")
+            allreduce_df(df, self.group)
+            self.index.set_global_df(df.cpu().numpy().astype(np.uint32), self.n_global)
+        self.index.finalize()
+
+    def upload(self, qfb: FeatureBatch) -> None:
+        self.index.upload_queries(qfb)
+
+    def topk_resident(self, k: int):
+        """Device-only step on the uploaded batch: local scan+merge, all-gather, global merge."""
+        import torch
+
+        q = self._resident_q
+        dev = f"cuda:{self.device}"
+        s = torch.empty((q, k), dtype=torch.float32, device=dev)
+        r = torch.empty((q, k), dtype=torch.int64, device=dev)
+        self.index.topk_resident(k, s.data_ptr(), r.data_ptr())
+        if self.world == 1:
+            return s, r
+        gs, gr = gather_topk(s, r, self.group)
+        return merge_on_device(self.device, gs, gr)
+
+    def set_resident(self, qfb: FeatureBatch) -> None:
+        self.upload(qfb)
+        self._resident_q = qfb.n
+
+    def topk_packed(self, data, offsets: np.ndarray, k: int, mode: int = 0):
+        """End-to-end step from host text: featurise, upload, scan, exchange, merge, read back."""
+        qfb = self.vocab.featurize_packed(data, offsets, mode, grow=False)
+        try:
+            self.set_resident(qfb)
+            s, r = self.topk_resident(k)
+            return s.cpu().numpy(), r.cpu().numpy()
+        finally:
+            qfb.close()

@@ -214,6 +214,15 @@ class GfkbIndex:
                                                 _ptr(fb.tf, C.c_uint32), _ptr(fb.oov, C.c_double), fb.n, k,
                                                 C.c_void_p(d_scores_ptr), C.c_void_p(d_rows_ptr)))
 
+    def upload_queries(self, fb: FeatureBatch) -> None:
+        """Make a featurised batch resident on the device (host prep + H2D), for topk_resident."""
+        _capi.check(_capi.load().kv_query_upload(self._h, _ptr(fb.indptr, C.c_int64), _ptr(fb.ids, C.c_uint32),
+                                                 _ptr(fb.tf, C.c_uint32), _ptr(fb.oov, C.c_double), fb.n))
+
+    def topk_resident(self, k: int, d_scores_ptr: int, d_rows_ptr: int) -> None:
+        """Device-only scan + merge of the uploaded batch into caller-owned device buffers."""
+        _capi.check(_capi.load().kv_topk_resident(self._h, k, C.c_void_p(d_scores_ptr), C.c_void_p(d_rows_ptr)))
+
     def topk(self, queries: Sequence[str], k: int) -> Tuple[np.ndarray, np.ndarray]:
         """(scores float32 [Q,k], rows int64 [Q,k]) ordered by (score desc, row asc) (K1b+K5)."""
         fb = self.vocab.featurize(queries, grow=False)
@@ -229,11 +238,11 @@ class GfkbIndex:
 
     def layout(self) -> dict:
         b = (C.c_int64 * 3)()
-        c = (C.c_int64 * 6)()
+        c = (C.c_int64 * 8)()
         _capi.check(_capi.load().kv_index_layout(self._h, b, c))
         return {"stream_bytes": b[0], "norm_bytes": b[1], "chunkptr_bytes": b[2], "entries": c[0],
                 "universal_features": c[1], "rows": c[2], "last_ctas": c[3], "last_tiles": c[4],
-                "last_splits": c[5]}
+                "last_splits": c[5], "last_upload_bytes": c[6], "tf_overflow_entries": c[7]}
 
     def close(self) -> None:
         if self._h is not None:

@@ -96,3 +96,17 @@ def test_unpinned_class_oracles_selfconsistent():
     assert O.fingerprint64("abc") == int("ba7816bf8f01cfea", 16)
     idx, val = O.topk_rows(np.array([[0.5, 1.0, 1.0, 0.2]]), 3)
     assert idx.tolist() == [[1, 2, 0]]
+
+
+def test_vectorised_closed_form(golden, built_lib):
+    from kakveda_b200 import synth
+
+    g = golden("edge_cases.json")
+    np.testing.assert_allclose(O.score_matrix_closed_form(g["queries"], g["corpus"]), np.array(g["scores"]),
+                               rtol=1e-12, atol=1e-15)
+    g = golden("synthetic_small.json")
+    corpus, queries = synth.corpus(g["n"]), synth.queries(g["q"], g["n"])
+    np.testing.assert_allclose(O.score_matrix_closed_form(queries, corpus), np.array(g["scores"]), rtol=1e-12, atol=1e-15)
+    g = golden("fixture54.json")
+    corpus = [r["signature_text"] for r in g["records"]]
+    np.testing.assert_allclose(O.score_matrix_closed_form(g["queries"], corpus), np.array(g["scores"]), rtol=1e-12, atol=1e-15)
