@@ -274,6 +274,10 @@ def run_ours(a):
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
         "algorithmic_bytes_per_launch": compulsory, "bytes_per_row": bytes_per_row,
         "query_tile": 128, "query_tiles": tiles, "row_splits": lay["last_splits"],
+        "chunks": lay["chunks"], "chunks_scanned_per_tile": lay["chunks_scanned"] / max(1, tiles),
+        "chunks_pruned_frac": lay["chunks_pruned"] / max(1, lay["chunks_pruned"] + lay["chunks_scanned"]),
+        "active_groups_per_scanned_chunk": lay["groups_active"] / max(1, lay["chunks_scanned"]),
+        "warp_cycles": {kk: lay["cycles_" + kk] for kk in ("bound_pass", "bound_requery", "scan", "barrier")},
         "kernel_ms": scan_s * 1e3, "merge_ms": sum(merge_ms) / len(merge_ms),
         "unbatched_rate_gbs": a.queries * rows_local * bytes_per_row / scan_s / 1e9,
         "note": "compulsory bytes = query_tiles x rows x bytes_per_row (each 128-query tile streams every row once; "

@@ -143,12 +143,16 @@ int kv_merge_topk_device(int device, const void *d_scores_in, const void *d_rows
  * ms[0] = H2D of query structures, ms[1] = scan kernel, ms[2] = merge kernel, ms[3] = D2H. */
 int kv_index_last_timing(const kv_index *ix, float ms[4]);
 
-/* Scan-layout facts for roofline accounting: bytes[0] = stream bytes, bytes[1] = row-norm
- * bytes, bytes[2] = chunk-pointer bytes; counts[0] = stored entries, counts[1] = folded
- * (universal) features, counts[2] = rows, counts[3] = CTAs of the last scan launch,
- * counts[4] = query tiles of the last scan, counts[5] = row splits of the last scan,
- * counts[6] = host->device bytes of the last query upload, counts[7] = tf-overflow entries. */
-int kv_index_layout(const kv_index *ix, int64_t bytes[3], int64_t counts[8]);
+/* Scan-layout facts for roofline accounting.
+ * bytes[0] = row stream, bytes[1] = row norms (float32), bytes[2] = chunk pointers,
+ * bytes[3] = chunk summaries (pseudo-rows + pointers + min norms).
+ * counts[0] = stored entries, [1] = folded (universal) features, [2] = rows, [3] = CTAs of the
+ * last scan launch, [4] = its query tiles, [5] = its row splits, [6] = host->device bytes of the
+ * last query upload, [7] = tf-overflow entries, [8] = chunks (128 rows each), and for the last
+ * scan summed over CTAs: [9] = chunks scanned, [10] = chunks pruned, [11] = summaries evaluated,
+ * [12] = 32-query groups active in the scanned chunks (of 4 per chunk), [13..16] = warp-cycles
+ * spent in: bound pass, per-query bound re-evaluation, chunk scans, barrier waits. */
+int kv_index_layout(const kv_index *ix, int64_t bytes[4], int64_t counts[17]);
 
 /* ------------------------------------------------------------------------------------
  * Synthetic failures.jsonl-shaped signature_text generator (test / bench support; the

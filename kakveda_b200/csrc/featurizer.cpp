@@ -193,23 +193,23 @@ bool tokenize(const char *doc, int64_t len, int mode, std::string &buf,
   return true;
 }
 
-// Distinct features of one document with counts, in order of first appearance
-// (all 1-grams, then all 2-grams: the order sklearn's analyzer emits them).
+// Distinct features of one document with counts, in order of first appearance in the text.
 void doc_features(const std::string &buf, const std::vector<std::pair<uint32_t, uint32_t>> &spans,
                   std::string &scratch, std::vector<Feat> &occ, std::vector<Feat> &out) {
   occ.clear();
-  uint32_t pos = 0;
   uint64_t h[2];
-  for (auto &s : spans) {
-    hash128(buf.data() + s.first, s.second - s.first, 0x6b616b76ULL, h);
-    occ.push_back({h[0], h[1], 1, pos++});
+  // positions interleave 1-grams and 2-grams in token order (t0, t0 t1, t1, t1 t2, ...): rows that share
+  // a text prefix share a prefix of their feature lists, which the device index factors out per chunk
+  for (size_t i = 0; i < spans.size(); i++) {
+    hash128(buf.data() + spans[i].first, spans[i].second - spans[i].first, 0x6b616b76ULL, h);
+    occ.push_back({h[0], h[1], 1, (uint32_t)(2 * i)});
   }
   for (size_t i = 0; i + 1 < spans.size(); i++) {
     scratch.assign(buf, spans[i].first, spans[i].second - spans[i].first);
     scratch.push_back(' ');
     scratch.append(buf, spans[i + 1].first, spans[i + 1].second - spans[i + 1].first);
     hash128(scratch.data(), scratch.size(), 0x6b616b76ULL, h);
-    occ.push_back({h[0], h[1], 1, pos++});
+    occ.push_back({h[0], h[1], 1, (uint32_t)(2 * i + 1)});
   }
   std::sort(occ.begin(), occ.end(), [](const Feat &a, const Feat &b) {
     if (a.h0 != b.h0) return a.h0 < b.h0;

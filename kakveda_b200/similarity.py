@@ -237,12 +237,15 @@ class GfkbIndex:
         return tuple(ms)
 
     def layout(self) -> dict:
-        b = (C.c_int64 * 3)()
-        c = (C.c_int64 * 8)()
+        b = (C.c_int64 * 4)()
+        c = (C.c_int64 * 17)()
         _capi.check(_capi.load().kv_index_layout(self._h, b, c))
-        return {"stream_bytes": b[0], "norm_bytes": b[1], "chunkptr_bytes": b[2], "entries": c[0],
-                "universal_features": c[1], "rows": c[2], "last_ctas": c[3], "last_tiles": c[4],
-                "last_splits": c[5], "last_upload_bytes": c[6], "tf_overflow_entries": c[7]}
+        return {"stream_bytes": b[0], "norm_bytes": b[1], "chunkptr_bytes": b[2], "summary_bytes": b[3],
+                "entries": c[0], "universal_features": c[1], "rows": c[2], "last_ctas": c[3], "last_tiles": c[4],
+                "last_splits": c[5], "last_upload_bytes": c[6], "tf_overflow_entries": c[7], "chunks": c[8],
+                "chunks_scanned": c[9], "chunks_pruned": c[10], "summaries_evaluated": c[11],
+                "groups_active": c[12], "cycles_bound_pass": c[13], "cycles_bound_requery": c[14],
+                "cycles_scan": c[15], "cycles_barrier": c[16]}
 
     def close(self) -> None:
         if self._h is not None:

@@ -53,7 +53,8 @@ def test_featurizer_matches_sklearn_analyzer(built_lib, golden):
     id2s, s2id = {}, {}
     for i, d in enumerate(docs):
         toks = O.tokens(d)
-        order = list(dict.fromkeys(toks + [a + " " + b for a, b in zip(toks, toks[1:])]))
+        inter = [x for i, t in enumerate(toks) for x in ([t] + ([t + " " + toks[i + 1]] if i + 1 < len(toks) else []))]
+        order = list(dict.fromkeys(inter))  # 1-grams and 2-grams interleaved in token order
         counts = O.features(d)
         ids = fb.ids[fb.indptr[i]:fb.indptr[i + 1]]
         tf = fb.tf[fb.indptr[i]:fb.indptr[i + 1]]
