@@ -47,11 +47,12 @@ def gather_topk(scores, rows, group=None):
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     if world == 1:
         return scores.unsqueeze(0), rows.unsqueeze(0)
-    gs = torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
-    gr = torch.empty((world,) + tuple(rows.shape), dtype=rows.dtype, device=rows.device)
-    dist.all_gather_into_tensor(gs, scores.contiguous(), group=group)
+    q = scores.shape[0]
+    gs = torch.empty((world * q,) + tuple(scores.shape[1:]), dtype=scores.dtype, device=scores.device)
+    gr = torch.empty((world * q,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    dist.all_gather_into_tensor(gs, scores.contiguous(), group=group)  # rank-major concatenation
     dist.all_gather_into_tensor(gr, rows.contiguous(), group=group)
-    return gs, gr
+    return gs.view((world,) + tuple(scores.shape)), gr.view((world,) + tuple(rows.shape))
 
 
 def merge_on_device(device: int, gs, gr):
