@@ -142,6 +142,8 @@ int kv_merge_topk_device(int device, const void *d_scores_in, const void *d_rows
  * milliseconds on its stream:
  * ms[0] = H2D of query structures, ms[1] = scan kernel, ms[2] = merge kernel, ms[3] = D2H. */
 int kv_index_last_timing(const kv_index *ix, float ms[4]);
+/* CUDA-event milliseconds of the scan kernel of the last kv_score call (K1a). */
+int kv_index_last_score_ms(const kv_index *ix, float *ms);
 
 /* Scan-layout facts for roofline accounting.
  * bytes[0] = row stream, bytes[1] = row norms (float32), bytes[2] = chunk pointers,
@@ -153,6 +155,24 @@ int kv_index_last_timing(const kv_index *ix, float ms[4]);
  * [12] = 32-query groups active in the scanned chunks (of 4 per chunk), [13..16] = warp-cycles
  * spent in: bound pass, per-query bound re-evaluation, chunk scans, barrier waits. */
 int kv_index_layout(const kv_index *ix, int64_t bytes[4], int64_t counts[17]);
+
+/* ------------------------------------------------------------------------------------
+ * K4: 64-bit fingerprint exact-match index.  One uint64 per row = the leading 64 bits of
+ * sha256(signature_text), i.e. int(fingerprint(), 16) of services/shared/fingerprint.py:69-71
+ * (a function the reference defines but never queries: matching by it is an extension, its
+ * oracle is integer equality).  kv_hash_match reports, per query hash, how many rows carry it
+ * and the first k of them in ascending row order (unused slots -1).  Pure HBM-bound scan.
+ * ---------------------------------------------------------------------------------- */
+typedef struct kv_hash_index kv_hash_index;
+int kv_hash_create(int device, int64_t row_base, kv_hash_index **out);
+void kv_hash_destroy(kv_hash_index *hx);
+int kv_hash_append(kv_hash_index *hx, const uint64_t *hashes, int64_t n);
+int64_t kv_hash_rows(const kv_hash_index *hx);
+int kv_hash_match(kv_hash_index *hx, const uint64_t *q_hashes, int64_t n_q, int k, int64_t *out_rows,
+                  int64_t *out_counts);
+/* CUDA-event milliseconds of the scan kernel launches of the last kv_hash_match, and their number
+ * (one pass over all rows per 4096 queries). */
+int kv_hash_last_timing(const kv_hash_index *hx, float *scan_ms, int *passes);
 
 /* ------------------------------------------------------------------------------------
  * Synthetic failures.jsonl-shaped signature_text generator (test / bench support; the

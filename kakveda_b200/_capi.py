@@ -50,7 +50,14 @@ SIGNATURES = {
     "kv_merge_topk_device": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
                                        C.c_void_p]),
     "kv_index_last_timing": (C.c_int, [C.c_void_p, c_f32p]),
+    "kv_index_last_score_ms": (C.c_int, [C.c_void_p, c_f32p]),
     "kv_index_layout": (C.c_int, [C.c_void_p, c_i64p, c_i64p]),
+    "kv_hash_create": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    "kv_hash_destroy": (None, [C.c_void_p]),
+    "kv_hash_append": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int64]),
+    "kv_hash_rows": (C.c_int64, [C.c_void_p]),
+    "kv_hash_match": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int64, C.c_int, c_i64p, c_i64p]),
+    "kv_hash_last_timing": (C.c_int, [C.c_void_p, c_f32p, C.POINTER(C.c_int)]),
     "kv_synth_signatures": (C.c_int, [C.c_uint64, C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_char_p,
                                       C.c_int64, c_i64p]),
 }

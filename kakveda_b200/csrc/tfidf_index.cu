@@ -18,7 +18,7 @@ using namespace kvk;
 
 namespace {
 // tile shape used by the batched scan: 128 queries, 2048-slot feature table
-constexpr int TG = 4, TLOGH = 11, TXCAP = 256;
+constexpr int TG = 4, TLOGH = 11, TXCAP = 128;
 using Tile = TileLayout<TG, TLOGH, TXCAP>;
 constexpr int TILE_MAX_FEATURES = (Tile::H * 5) / 8;  // load factor cap 0.625 (linear probing)
 
@@ -109,6 +109,7 @@ struct kv_index {
   std::vector<double> irr_oov;
 
   float last_ms[4] = {0, 0, 0, 0};
+  float last_score_ms = 0;
   int64_t last_ctas = 0, last_tiles = 0, last_splits = 0;
   unsigned long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -564,11 +565,14 @@ static int score_impl(kv_index *ix, const uint32_t *q_ids, const uint32_t *q_tf,
   P.nq = qp.nq; P.dotU = qp.dotU; P.corrU = qp.corrU; P.out = ix->d_scores.p;
   int blocks = (int)std::min<int64_t>((ix->n_chunks + 7) / 8, (int64_t)ix->sm_count * 8);
   if (blocks < 1) blocks = 1;
+  KV_CUDA(cudaEventRecord(ix->ev[1], s));
   tfidf_score_kernel<<<blocks, 256, P.table_in_smem ? tab_bytes : 0, s>>>(P);
   KV_CUDA(cudaGetLastError());
+  KV_CUDA(cudaEventRecord(ix->ev[2], s));
   if (out_scores)
     KV_CUDA(cudaMemcpyAsync(out_scores, ix->d_scores.p, (size_t)ix->n_rows * sizeof(double), cudaMemcpyDeviceToHost, s));
   KV_CUDA(cudaStreamSynchronize(s));
+  cudaEventElapsedTime(&ix->last_score_ms, ix->ev[1], ix->ev[2]);
   return KV_OK;
 }
 
@@ -748,7 +752,7 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
   // there are too few tiles to fill the GPU.
   const char *env = getenv("KAKVEDA_B200_NO_PRUNE");
   const int prune = (env && env[0] == '1') ? 0 : (ix->n_chunks >= 64 ? 1 : 0);
-  const int ctas_per_sm = 2;
+  const int ctas_per_sm = 3;
   int64_t want = (int64_t)ix->sm_count * ctas_per_sm * 8;
   int64_t n_splits = (want + n_tiles - 1) / n_tiles;
   n_splits = std::max<int64_t>(1, std::min<int64_t>(n_splits, std::max<int64_t>(1, ix->n_chunks / 8)));
@@ -895,6 +899,12 @@ int kv_merge_topk_device(int device, const void *d_scores_in, const void *d_rows
 int kv_index_last_timing(const kv_index *ix, float ms[4]) {
   if (!ix || !ms) return kv_fail(KV_ERR_INVALID, "kv_index_last_timing: bad arguments");
   for (int i = 0; i < 4; i++) ms[i] = ix->last_ms[i];
+  return KV_OK;
+}
+
+int kv_index_last_score_ms(const kv_index *ix, float *ms) {
+  if (!ix || !ms) return kv_fail(KV_ERR_INVALID, "kv_index_last_score_ms: bad arguments");
+  *ms = ix->last_score_ms;
   return KV_OK;
 }
 

@@ -417,7 +417,7 @@ __device__ __forceinline__ void scan_entries(const uint32_t *__restrict__ stream
 }
 
 template <int G, int LOGH, int XCAP>
-__global__ void __launch_bounds__(256) tfidf_topk_kernel(TopkParams P) {
+__global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
   using TL = TileLayout<G, LOGH, XCAP>;
   constexpr int QT = TL::QT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -432,6 +432,7 @@ __global__ void __launch_bounds__(256) tfidf_topk_kernel(TopkParams P) {
   int *s_lock = s_cnt + QT;                                 // [QT]
   float *s_thrmin = (float *)(s_lock + QT);                 // [1] min over the tile of the k-th scores
   unsigned int *s_stat = (unsigned int *)(s_thrmin + 1);    // [4]
+  long long *s_next = (long long *)(s_stat + 5);            // [1] (8-byte aligned: s_thrmin sits on a 16-byte boundary)
 
   const int tile = blockIdx.x, split = blockIdx.y;
   const TileDesc td = P.tiles[tile];
@@ -583,12 +584,19 @@ __global__ void __launch_bounds__(256) tfidf_topk_kernel(TopkParams P) {
         for (int g = 0; g < G; g++)
           if (L.valid[g]) m = fminf(m, L.filt[g]);
         for (int o = 16; o; o >>= 1) m = fminf(m, __shfl_xor_sync(FULL, m, o));
-        if (lane == 0) *s_thrmin = m;
+        if (lane == 0) {
+          *s_thrmin = m;
+          *s_next = (long long)c_lo;  // chunk cursor of this level (warps grab 32 chunks at a time)
+        }
       }
       __syncthreads();
       const float thr_min = *s_thrmin;
       if (hi * PRUNE_SLACK < thr_min) break;  // uniform: every remaining bound is below every k-th score
-      for (int64_t base = c_lo + (int64_t)warp * 32; base < c_hi; base += (int64_t)n_warps * 32) {
+      for (;;) {
+        long long nb = 0;
+        if (lane == 0) nb = atomicAdd((unsigned long long *)s_next, 32ULL);
+        const int64_t base = __shfl_sync(FULL, nb, 0);
+        if (base >= c_hi) break;
         const int64_t c = base + lane;
         const float b = c < c_hi ? ub[c] : -INFINITY;
         const bool in_level = c < c_hi && b >= lo && (b < hi || lev == 0);  // level 0 takes +inf bounds too

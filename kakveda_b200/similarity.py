@@ -236,6 +236,11 @@ class GfkbIndex:
         _capi.check(_capi.load().kv_index_last_timing(self._h, ms))
         return tuple(ms)
 
+    def last_score_ms(self) -> float:
+        ms = C.c_float()
+        _capi.check(_capi.load().kv_index_last_score_ms(self._h, C.byref(ms)))
+        return ms.value
+
     def layout(self) -> dict:
         b = (C.c_int64 * 4)()
         c = (C.c_int64 * 17)()

@@ -341,3 +341,35 @@ def test_large_properties(lib):
         for a, b in zip(order, r[i].tolist()):
             assert a == b or full[a] == pytest.approx(full[b], rel=RTOL32)
     assert exact > 30
+
+
+def test_hash_fingerprint_match(lib):
+    """K4 (parity unpinned: the reference never queries fingerprint()): integer equality, bit-exact."""
+    from kakveda_b200 import HashIndex, synth
+    from kakveda_b200.fingerprint import fingerprint_text
+
+    n, q, k = 50_000, 9000, 4
+    corpus, queries = synth.corpus(n), synth.queries(q, n) + ["never stored"]
+    hx = HashIndex()
+    hx.add_signatures(corpus)
+    assert hx.n_rows == n
+    rows, counts = hx.match_signatures(queries, k)
+    where = {}
+    for i, s in enumerate(corpus):
+        where.setdefault(O.fingerprint64(s), []).append(i)
+    for i, s in enumerate(queries):
+        want = where.get(O.fingerprint64(s), [])
+        assert counts[i] == len(want)
+        assert rows[i].tolist() == (want[:k] + [-1] * k)[:k]
+        assert O.fingerprint64(s) == int(fingerprint_text(s), 16)
+    assert counts[-1] == 0 and 0.4 * q < np.count_nonzero(counts) < 0.6 * q + 1
+    # large: 20M random hashes, 4096 planted queries (one pass) -- size-independent properties
+    rng = np.random.default_rng(7)
+    big = rng.integers(0, 2**63, size=20_000_000, dtype=np.uint64)
+    hb = HashIndex(row_base=1000)
+    hb.add_hashes(big)
+    pick = rng.integers(0, len(big), size=4096)
+    r, c = hb.match_hashes(big[pick], 2)
+    assert np.all(c >= 1) and np.all(big[r[:, 0] - 1000] == big[pick]) and np.all(r[:, 0] - 1000 <= pick)
+    ms, passes = hb.last_timing()
+    assert passes == 1 and ms > 0
