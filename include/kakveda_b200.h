@@ -157,6 +157,24 @@ int kv_index_last_score_ms(const kv_index *ix, float *ms);
 int kv_index_layout(const kv_index *ix, int64_t bytes[4], int64_t counts[17]);
 
 /* ------------------------------------------------------------------------------------
+ * K2: dense-embedding cosine index (bf16 rows of `dim` elements, dim a multiple of 64) with the
+ * top-k fused into a tcgen05 GEMM epilogue.  The reference has no embedding path (its docs list
+ * embeddings as a possible extension, docs/failure-intelligence.md:43-46): parity UNPINNED, oracle =
+ * float64 cosine of the same bf16 inputs.  Inputs are bfloat16 bit patterns (uint16), row-major.
+ * kv_dense_topk: per query the k (<=16) best rows by (cosine desc, row asc); host outputs
+ * float32[n_q*k] / int64[n_q*k]; unused slots (-inf, -1).
+ * ---------------------------------------------------------------------------------- */
+typedef struct kv_dense_index kv_dense_index;
+int kv_dense_create(int device, int dim, int64_t row_base, kv_dense_index **out);
+void kv_dense_destroy(kv_dense_index *dx);
+int kv_dense_append(kv_dense_index *dx, const uint16_t *rows_bf16, int64_t n);
+int kv_dense_finalize(kv_dense_index *dx);
+int64_t kv_dense_rows(const kv_dense_index *dx);
+int kv_dense_topk(kv_dense_index *dx, const uint16_t *q_bf16, int64_t n_q, int k, float *out_scores, int64_t *out_rows);
+/* CUDA-event milliseconds of the GEMM+top-k kernel of the last kv_dense_topk and its row splits. */
+int kv_dense_last_timing(const kv_dense_index *dx, float *gemm_ms, int64_t *splits);
+
+/* ------------------------------------------------------------------------------------
  * K4: 64-bit fingerprint exact-match index.  One uint64 per row = the leading 64 bits of
  * sha256(signature_text), i.e. int(fingerprint(), 16) of services/shared/fingerprint.py:69-71
  * (a function the reference defines but never queries: matching by it is an extension, its

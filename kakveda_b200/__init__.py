@@ -6,11 +6,12 @@ services/shared/similarity.py:14-20, as called by services/gfkb/app.py:86) -- as
 sm_100a CUDA behind a C ABI (include/kakveda_b200.h).  See DESIGN.md.
 """
 from .fingerprint import fingerprint_text, fingerprint_u64, normalize_prompt, signature_text
+from .denseindex import DenseIndex
 from .hashindex import HashIndex
 from .similarity import FeatureBatch, GfkbIndex, SimilarityEngine, Vocabulary
 
 __all__ = [
-    "SimilarityEngine", "GfkbIndex", "Vocabulary", "FeatureBatch", "HashIndex",
+    "SimilarityEngine", "GfkbIndex", "Vocabulary", "FeatureBatch", "HashIndex", "DenseIndex",
     "signature_text", "fingerprint_text", "fingerprint_u64", "normalize_prompt",
 ]
 __version__ = "0.1.0"

@@ -52,6 +52,13 @@ SIGNATURES = {
     "kv_index_last_timing": (C.c_int, [C.c_void_p, c_f32p]),
     "kv_index_last_score_ms": (C.c_int, [C.c_void_p, c_f32p]),
     "kv_index_layout": (C.c_int, [C.c_void_p, c_i64p, c_i64p]),
+    "kv_dense_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    "kv_dense_destroy": (None, [C.c_void_p]),
+    "kv_dense_append": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint16), C.c_int64]),
+    "kv_dense_finalize": (C.c_int, [C.c_void_p]),
+    "kv_dense_rows": (C.c_int64, [C.c_void_p]),
+    "kv_dense_topk": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint16), C.c_int64, C.c_int, c_f32p, c_i64p]),
+    "kv_dense_last_timing": (C.c_int, [C.c_void_p, c_f32p, c_i64p]),
     "kv_hash_create": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
     "kv_hash_destroy": (None, [C.c_void_p]),
     "kv_hash_append": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int64]),

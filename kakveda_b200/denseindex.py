@@ -1,0 +1,66 @@
+"""Dense-embedding cosine index (K2): bf16 GEMM on the tcgen05 tensor cores with a fused top-k.
+
+Extension of the reference (which only has TF-IDF; embeddings are listed as a possible upgrade in
+docs/failure-intelligence.md:43-46).  Rows and queries are float arrays rounded to bfloat16 on the way in;
+the cosine is computed on those bf16 values (fp32 accumulation, fp32 norms).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Tuple
+
+import numpy as np
+
+from . import _capi
+
+
+def to_bf16_bits(x: np.ndarray) -> np.ndarray:
+    """float32 -> bfloat16 bit patterns (uint16), round-to-nearest-even."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    return (((u + 0x7FFF + ((u >> 16) & 1)) >> 16) & 0xFFFF).astype(np.uint16)
+
+
+class DenseIndex:
+    def __init__(self, dim: int, device: int = 0, row_base: int = 0):
+        h = C.c_void_p()
+        _capi.check(_capi.load().kv_dense_create(device, dim, row_base, C.byref(h)))
+        self._h, self.dim = h, dim
+
+    def add(self, rows: np.ndarray) -> None:
+        bits = rows if rows.dtype == np.uint16 else to_bf16_bits(rows)
+        bits = np.ascontiguousarray(bits).reshape(-1, self.dim)
+        _capi.check(_capi.load().kv_dense_append(self._h, bits.ctypes.data_as(C.POINTER(C.c_uint16)), bits.shape[0]))
+
+    def finalize(self) -> None:
+        _capi.check(_capi.load().kv_dense_finalize(self._h))
+
+    @property
+    def n_rows(self) -> int:
+        return int(_capi.load().kv_dense_rows(self._h))
+
+    def topk(self, queries: np.ndarray, k: int = 16) -> Tuple[np.ndarray, np.ndarray]:
+        bits = queries if queries.dtype == np.uint16 else to_bf16_bits(queries)
+        bits = np.ascontiguousarray(bits).reshape(-1, self.dim)
+        n = bits.shape[0]
+        scores = np.empty((n, k), dtype=np.float32)
+        rows = np.empty((n, k), dtype=np.int64)
+        _capi.check(_capi.load().kv_dense_topk(self._h, bits.ctypes.data_as(C.POINTER(C.c_uint16)), n, k,
+                                               scores.ctypes.data_as(C.POINTER(C.c_float)),
+                                               rows.ctypes.data_as(C.POINTER(C.c_int64))))
+        return scores, rows
+
+    def last_timing(self) -> Tuple[float, int]:
+        ms, sp = C.c_float(), C.c_int64()
+        _capi.check(_capi.load().kv_dense_last_timing(self._h, C.byref(ms), C.byref(sp)))
+        return ms.value, sp.value
+
+    def close(self) -> None:
+        if self._h is not None:
+            _capi.load().kv_dense_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -373,3 +373,39 @@ def test_hash_fingerprint_match(lib):
     assert np.all(c >= 1) and np.all(big[r[:, 0] - 1000] == big[pick]) and np.all(r[:, 0] - 1000 <= pick)
     ms, passes = hb.last_timing()
     assert passes == 1 and ms > 0
+
+
+@pytest.mark.parametrize("n,d,q", [(3000, 128, 200), (20000, 768, 500), (257, 64, 3)])
+def test_dense_cosine_topk(lib, n, d, q):
+    """K2 (parity unpinned: no embedding path in the reference).  Tolerance from SURVEY 8(c): rtol 1e-5,
+    atol 1e-6 on the returned scores against float64 cosine of the same bf16-rounded inputs."""
+    from kakveda_b200 import DenseIndex
+
+    rng = np.random.default_rng(n + d)
+    C = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((q, d)).astype(np.float32)
+    Q[: min(q, 50)] = C[rng.integers(0, n, size=min(q, 50))] * 1.5   # exact directional matches -> cosine 1
+    C[7] = 0.0                                                        # zero vector scores 0
+    if n > 1000:
+        C[1001] = C[1000]                                             # duplicate rows tie -> lower row first
+        Q[min(q, 50)] = C[1000]
+    dx = DenseIndex(d)
+    dx.add(C[: n // 2])
+    dx.add(C[n // 2:])
+    dx.finalize()
+    k = 16
+    s, r = dx.topk(Q, k)
+    want = O.dense_cosine(Q, C)
+    kk = min(k, n)
+    for i in range(q):
+        assert len(set(r[i, :kk].tolist())) == kk and np.all(r[i, :kk] >= 0)
+        np.testing.assert_allclose(s[i, :kk], want[i, r[i, :kk]], rtol=1e-5, atol=1e-6)
+        rest = np.delete(want[i], r[i, :kk])
+        if rest.size:
+            assert rest.max() <= want[i, r[i, :kk]].min() + 2e-6
+        assert np.all(np.diff(s[i, :kk]) <= 0)
+        ties = np.diff(s[i, :kk]) == 0
+        assert np.all(np.diff(r[i, :kk])[ties] > 0)
+    assert np.allclose(s[:min(q, 50), 0], 1.0, atol=1e-5)
+    if n > 1000:
+        assert r[min(q, 50), :2].tolist() == [1000, 1001]
