@@ -7,20 +7,24 @@
 //
 // scores[q, r] = <Q[q,:], C[r,:]> / (|Q[q]| |C[r]|): a bf16 GEMM Q * C^T with fp32 accumulation, the
 // norms applied as fp32 scales in the epilogue, and the top-k fused into the epilogue so that the
-// [Q, N] score matrix never exists.  One CTA owns a 128-query tile and a range of 256-row tiles:
+// [Q, N] score matrix never exists.  The (query tile, row tile) space is linearised query-tile-major and
+// cut into one contiguous slice per SM (persistent CTAs, no wave tail); a CTA therefore sees long row
+// ranges of at most a few query tiles, which keeps its k-th-score thresholds high.  Per CTA:
 //   warp 0      TMA producer: K-slices (64 elements) of the query tile and of the row tile -> 4-stage
 //               shared-memory ring (128B-swizzled), mbarrier expect_tx / complete_tx
 //   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16, accumulators in TMEM
 //               (2 x 256 columns, double buffered); tcgen05.commit releases ring slots / publishes a tile
 //   warps 2-5   epilogue: tcgen05.ld of the thread's TMEM lane (= its query), scale, threshold test,
 //               insertion into the thread's own top-k list (ties keep the lower row)
-// Partial lists of the row splits are merged by K5 (kv_merge_topk_device).
+// Each (query tile, CTA) pair writes one partial list; K5 (kv_merge_topk_device) merges them.  CTAs
+// working on the same queries exchange k-th-score lower bounds through global memory (gthr).
 #include "kv_cuda.cuh"
 
 #include <cuda.h>
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -34,7 +38,7 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int MAXK = 16;       // per-thread list slots that fit beside the 4-stage ring (k <= 16)
+constexpr int MAXK = 16;       // per-query list slots that fit beside the 4-stage ring (k <= 16)
 constexpr int N_THREADS = 192;  // 6 warps
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -100,20 +104,31 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 
 struct DenseParams {
   int64_t n_rows, row_base, n_q;
-  int dim, k, n_splits;
+  int64_t r_tiles, q_tiles;  // 256-row tiles, 128-query tiles
+  int dim, k, n_lists, dbg;
   const float *inv_norm_c;  // [n_rows]
   const float *inv_norm_q;  // [n_q]
-  float *part_scores;       // [n_splits][n_q][k]
+  unsigned int *gthr;       // [n_q] order-preserving key of a lower bound of the global k-th score (0 = none)
+  float *part_scores;       // [n_lists][n_q][k]
   long long *part_rows;
 };
+
+// order-preserving float <-> unsigned key (cosines may be negative)
+__device__ __forceinline__ unsigned int fkey(float f) {
+  unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
 
 struct __align__(1024) DenseSmem {
   unsigned char stage[STAGES][STAGE_BYTES];
   uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
-  float inv_c[2][BN];
-  float lscore[BM][MAXK];
-  int lrow[BM][MAXK];
+  __align__(16) float inv_c[2][BN];
+  float lscore[MAXK][BM];  // [slot][query]: the 32 lanes of a warp hit 32 different banks
+  int lrow[MAXK][BM];
 };
 
 __global__ void __launch_bounds__(N_THREADS, 1)
@@ -121,9 +136,12 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   extern __shared__ unsigned char smem_raw[];
   DenseSmem &S = *reinterpret_cast<DenseSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qtile = blockIdx.x, split = blockIdx.y;
-  const int64_t n_tiles = (P.n_rows + BN - 1) / BN;
-  const int64_t t_lo = n_tiles * split / P.n_splits, t_hi = n_tiles * (split + 1) / P.n_splits;
+  // work item = (query tile, row split); consecutive CTAs take consecutive query tiles of the same split, so the
+  // CTAs resident at one time stream the same corpus rows (B tiles are shared through L2)
+  const int64_t item = blockIdx.x;
+  const int64_t my_qtile = item % P.q_tiles, my_split = item / P.q_tiles;
+  const int64_t L0 = my_qtile * P.r_tiles + P.r_tiles * my_split / P.n_lists;
+  const int64_t L1 = my_qtile * P.r_tiles + P.r_tiles * (my_split + 1) / P.n_lists;
   const int n_kb = P.dim / BK;
 
   if (warp == 0 && lane == 0) {
@@ -145,7 +163,9 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t t = t_lo; t < t_hi; t++) {
+      for (int64_t L = L0; L < L1; L++) {
+        const int qtile = (int)(L / P.r_tiles);
+        const int64_t t = L % P.r_tiles;
         for (int kb = 0; kb < n_kb; kb++) {
           mbar_wait(&S.empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&S.full_bar[stage], STAGE_BYTES);
@@ -161,7 +181,7 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int64_t it = 0;
-      for (int64_t t = t_lo; t < t_hi; t++, it++) {
+      for (int64_t L = L0; L < L1; L++, it++) {
         const int as = (int)(it & 1);
         const uint32_t aphase = (uint32_t)((it >> 1) & 1);
         mbar_wait(&S.tmem_empty[as], aphase ^ 1);
@@ -186,28 +206,60 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const int lane_base = 32 * (warp & 3);
     const int qi = lane_base + lane;            // TMEM lane = query inside the tile
     const int et = (warp - 2) * 32 + lane;      // 0..127 among the epilogue threads
-    const int64_t q = (int64_t)qtile * BM + qi;
-    const bool q_ok = q < P.n_q;
-    const float inv_q = q_ok ? P.inv_norm_q[q] : 0.f;
     const int k = P.k;
-    float *ls = S.lscore[qi];
-    int *lr = S.lrow[qi];
-    for (int j = 0; j < k; j++) { ls[j] = -INFINITY; lr[j] = 0x7fffffff; }
-    int cnt = 0;
-    float thr = -INFINITY;
+    float *ls = &S.lscore[0][qi];               // element j of this query's list lives at ls[j * BM]
+    int *lr = &S.lrow[0][qi];
+    int cur_qtile = -1, cnt = 0;
+    int64_t q = 0;
+    bool q_ok = false;
+    float inv_q = 0.f;
+    float thr = -INFINITY;  // own k-th score: later rows must beat it strictly (rows ascend inside a CTA)
+    float gth = -INFINITY;  // k-th score another CTA already secured for this query: ties may still win on row id
+    float gth_pred = -INFINITY;  // largest float below gth
+    float lo = INFINITY;         // a row enters the list iff its score > lo
+    auto flush = [&]() {    // publish the list of (cur_qtile, this CTA)
+      if (cur_qtile < 0 || !q_ok) return;
+      const int slot = (int)my_split;
+      for (int j = 0; j < k; j++) {
+        const size_t o = ((size_t)slot * P.n_q + q) * k + j;
+        P.part_scores[o] = j < cnt ? ls[j * BM] : -INFINITY;
+        P.part_rows[o] = j < cnt ? (long long)(P.row_base + lr[j * BM]) : -1LL;
+      }
+    };
     int64_t it = 0;
-    for (int64_t t = t_lo; t < t_hi; t++, it++) {
+    for (int64_t L = L0; L < L1; L++, it++) {
+      const int qtile = (int)(L / P.r_tiles);
+      const int64_t t = L % P.r_tiles;
+      if (qtile != cur_qtile) {  // (warp-uniform) next query tile: publish and restart the lists
+        flush();
+        cur_qtile = qtile;
+        q = (int64_t)qtile * BM + qi;
+        q_ok = q < P.n_q;
+        inv_q = q_ok ? P.inv_norm_q[q] : 0.f;
+        cnt = 0;
+        thr = gth = gth_pred = -INFINITY;
+        lo = q_ok ? -INFINITY : INFINITY;
+        for (int j = 0; j < k; j++) { ls[j * BM] = -INFINITY; lr[j * BM] = 0x7fffffff; }
+      }
       const int as = (int)(it & 1);
       const uint32_t aphase = (uint32_t)((it >> 1) & 1);
-      // inverse norms of this tile's rows (zero for rows past the end -> never inserted)
+      // inverse norms of this tile's rows (0 past the end; such rows are rejected by index below)
       const int64_t row0 = t * BN;
-      for (int c = et; c < BN; c += 128) S.inv_c[as][c] = (row0 + c < P.n_rows) ? P.inv_norm_c[row0 + c] : -1.f;
+      for (int c = et; c < BN; c += 128) S.inv_c[as][c] = (row0 + c < P.n_rows) ? P.inv_norm_c[row0 + c] : -INFINITY;  // 0 * -inf = NaN: never a candidate
+      if (q_ok) {
+        const unsigned int gk = *(volatile unsigned int *)&P.gthr[q];
+        if (gk > fkey(-INFINITY) && fkey_inv(gk) > gth) {
+          gth = fkey_inv(gk);
+          gth_pred = fkey_inv(gk - 1);  // the order-preserving key makes "previous float" a decrement
+          lo = fmaxf(thr, gth_pred);
+        }
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(&S.tmem_full[as], aphase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < ((P.dbg == 1) ? 0 : BN); c0 += 32) {
         uint32_t v[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -220,31 +272,50 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             : "r"(taddr + (uint32_t)c0)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (P.dbg == 2) { if (v[0] == 0x12345678u && v[31] == 0x9abcdef0u) thr = 1.f; continue; }
+        // 32 independent scale ops + a max tree: one (rarely taken) branch per 32 rows instead of 32
+        float tv[32];
+        const float4 *ic4 = reinterpret_cast<const float4 *>(&S.inv_c[as][c0]);
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const float ic = S.inv_c[as][c0 + j];
-          const float s = __uint_as_float(v[j]) * inv_q * ic;
-          if (ic >= 0.f && s > thr && q_ok) {  // strict: on ties the earlier (lower) row stays
-            const int row = (int)(row0 + c0 + j);
-            int pos = cnt < k ? cnt++ : k - 1;
-            while (pos > 0 && ls[pos - 1] < s) { ls[pos] = ls[pos - 1]; lr[pos] = lr[pos - 1]; pos--; }
-            ls[pos] = s;
-            lr[pos] = row;
-            if (cnt == k) thr = ls[k - 1];
+        for (int j4 = 0; j4 < 8; j4++) {
+          const float4 ic = ic4[j4];
+          tv[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * ic.x;
+          tv[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * ic.y;
+          tv[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * ic.z;
+          tv[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * ic.w;
+        }
+        // per 8 columns: max -> one branch; only sub-blocks where some query of the warp has a candidate are
+        // walked element by element (`sc > lo` == `sc > thr && sc >= gth`, lo = max(thr, pred(gth)))
+#pragma unroll
+        for (int sb = 0; sb < 4; sb++) {
+          const float m01 = fmaxf(tv[8 * sb + 0], tv[8 * sb + 1]), m23 = fmaxf(tv[8 * sb + 2], tv[8 * sb + 3]);
+          const float m45 = fmaxf(tv[8 * sb + 4], tv[8 * sb + 5]), m67 = fmaxf(tv[8 * sb + 6], tv[8 * sb + 7]);
+          const float best = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67)) * inv_q;
+          if (best > lo) {
+#pragma unroll  // static indices keep tv[] in registers
+            for (int j = 8 * sb; j < 8 * sb + 8; j++) {
+              const float sc = tv[j] * inv_q;
+              if (sc > lo) {
+                int pos = cnt < k ? cnt++ : k - 1;
+                while (pos > 0 && ls[(pos - 1) * BM] < sc) {
+                  ls[pos * BM] = ls[(pos - 1) * BM];
+                  lr[pos * BM] = lr[(pos - 1) * BM];
+                  pos--;
+                }
+                ls[pos * BM] = sc;
+                lr[pos * BM] = (int)(row0 + c0 + j);
+                if (cnt == k) { thr = ls[(k - 1) * BM]; lo = fmaxf(thr, gth_pred); }
+              }
+            }
           }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.tmem_empty[as]);
+      if (q_ok && cnt == k && thr > gth) atomicMax(&P.gthr[q], fkey(thr));
     }
-    if (q_ok) {
-      for (int j = 0; j < k; j++) {
-        const size_t o = ((size_t)split * P.n_q + q) * k + j;
-        P.part_scores[o] = j < cnt ? ls[j] : -INFINITY;
-        P.part_rows[o] = j < cnt ? (long long)(P.row_base + lr[j]) : -1LL;
-      }
-    }
+    flush();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -306,6 +377,7 @@ struct kv_dense_index {
   DevBuf<float> d_inv_c, d_inv_q, d_part_s, d_out_s;
   DevBuf<long long> d_part_r, d_out_r;
   DevBuf<__nv_bfloat16> d_q;
+  DevBuf<unsigned int> d_gthr;
   bool finalized = false;
   float last_ms = 0;
   int64_t last_splits = 0;
@@ -342,7 +414,7 @@ void kv_dense_destroy(kv_dense_index *dx) {
   cudaSetDevice(dx->device);
   cudaStreamSynchronize(dx->stream);
   dx->rows.release(); dx->d_inv_c.release(); dx->d_inv_q.release(); dx->d_part_s.release(); dx->d_out_s.release();
-  dx->d_part_r.release(); dx->d_out_r.release(); dx->d_q.release();
+  dx->d_part_r.release(); dx->d_out_r.release(); dx->d_q.release(); dx->d_gthr.release();
   for (auto &e : dx->ev) if (e) cudaEventDestroy(e);
   if (dx->stream) cudaStreamDestroy(dx->stream);
   delete dx;
@@ -403,21 +475,41 @@ int kv_dense_topk(kv_dense_index *dx, const uint16_t *q_bf16, int64_t n_q, int k
   rc = make_map(&map_c, dx->rows.p, dx->n_rows, dx->dim, BN);
   if (rc != KV_OK) return rc;
   const int64_t q_tiles = (n_q + BM - 1) / BM, r_tiles = (dx->n_rows + BN - 1) / BN;
-  int64_t n_splits = std::max<int64_t>(1, std::min<int64_t>(r_tiles, ((int64_t)dx->sm_count * 2 + q_tiles - 1) / q_tiles));
-  n_splits = std::min<int64_t>(n_splits, 1024);
-  dx->last_splits = n_splits;
-  KV_CUDA(dx->d_part_s.ensure(n_splits * n_q * k)); KV_CUDA(dx->d_part_r.ensure(n_splits * n_q * k));
+  // row splits: as few as possible (long row ranges keep the k-th-score thresholds high) while the CTA count
+  // fills whole waves of SMs (one CTA per SM)
+  int64_t n_lists = 1;
+  {
+    double best = 1e18;
+    const int64_t lo = std::max<int64_t>(1, (dx->sm_count + q_tiles - 1) / q_tiles);
+    for (int64_t sp = lo; sp <= std::min<int64_t>(r_tiles, lo + 16); sp++) {
+      const int64_t ctas = q_tiles * sp, waves = (ctas + dx->sm_count - 1) / dx->sm_count;
+      const double cost = (double)(waves * dx->sm_count) / (double)ctas * (1.0 + 0.01 * (double)sp);
+      if (cost < best) { best = cost; n_lists = sp; }
+    }
+    n_lists = std::max<int64_t>(1, std::min<int64_t>(n_lists, r_tiles));
+  }
+  dx->last_splits = n_lists;
+  KV_CUDA(dx->d_part_s.ensure(n_lists * n_q * k)); KV_CUDA(dx->d_part_r.ensure(n_lists * n_q * k));
   KV_CUDA(dx->d_out_s.ensure(n_q * k)); KV_CUDA(dx->d_out_r.ensure(n_q * k));
+  KV_CUDA(dx->d_gthr.ensure(n_q));
+  KV_CUDA(cudaMemsetAsync(dx->d_gthr.p, 0, (size_t)n_q * 4, s));
+  // unused (query tile, slot) pairs stay "empty": row -1 (the merge ignores their scores)
+  KV_CUDA(cudaMemsetAsync(dx->d_part_r.p, 0xFF, (size_t)n_lists * n_q * k * 8, s));
+  KV_CUDA(cudaMemsetAsync(dx->d_part_s.p, 0xFF, (size_t)n_lists * n_q * k * 4, s));
   DenseParams P;
-  P.n_rows = dx->n_rows; P.row_base = dx->row_base; P.n_q = n_q; P.dim = dx->dim; P.k = k; P.n_splits = (int)n_splits;
-  P.inv_norm_c = dx->d_inv_c.p; P.inv_norm_q = dx->d_inv_q.p; P.part_scores = dx->d_part_s.p; P.part_rows = dx->d_part_r.p;
+  P.n_rows = dx->n_rows; P.row_base = dx->row_base; P.n_q = n_q; P.dim = dx->dim; P.k = k; P.n_lists = (int)n_lists;
+  P.r_tiles = r_tiles; P.q_tiles = q_tiles;
+  P.dbg = getenv("KAKVEDA_B200_DENSE_DBG") ? atoi(getenv("KAKVEDA_B200_DENSE_DBG")) : 0;
+  P.inv_norm_c = dx->d_inv_c.p; P.inv_norm_q = dx->d_inv_q.p; P.gthr = dx->d_gthr.p;
+  P.part_scores = dx->d_part_s.p; P.part_rows = dx->d_part_r.p;
+  const int64_t grid = q_tiles * n_lists;
   KV_CUDA(cudaEventRecord(dx->ev[0], s));
-  dense_topk_kernel<<<dim3((unsigned)q_tiles, (unsigned)n_splits), N_THREADS, sizeof(DenseSmem) + 1024, s>>>(map_q, map_c, P);
+  dense_topk_kernel<<<(unsigned)grid, N_THREADS, sizeof(DenseSmem) + 1024, s>>>(map_q, map_c, P);
   KV_CUDA(cudaGetLastError());
   KV_CUDA(cudaEventRecord(dx->ev[1], s));
   KV_CUDA(cudaStreamSynchronize(s));
   cudaEventElapsedTime(&dx->last_ms, dx->ev[0], dx->ev[1]);
-  rc = kv_merge_topk_device(dx->device, dx->d_part_s.p, dx->d_part_r.p, (int)n_splits, n_q, k, dx->d_out_s.p, dx->d_out_r.p);
+  rc = kv_merge_topk_device(dx->device, dx->d_part_s.p, dx->d_part_r.p, (int)n_lists, n_q, k, dx->d_out_s.p, dx->d_out_r.p);
   if (rc != KV_OK) return rc;
   KV_CUDA(cudaMemcpy(out_scores, dx->d_out_s.p, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost));
   KV_CUDA(cudaMemcpy(out_rows, dx->d_out_r.p, (size_t)n_q * k * 8, cudaMemcpyDeviceToHost));
