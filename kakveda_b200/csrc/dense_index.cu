@@ -34,12 +34,13 @@ constexpr int BM = 128;        // queries per CTA (TMEM lanes)
 constexpr int BN = 256;        // corpus rows per MMA tile (TMEM columns per accumulator stage)
 constexpr int BK = 64;         // K-slice: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;       // 3 x 48 KiB ring + two list sets fit in 227 KiB
 constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int MAXK = 16;       // per-query list slots that fit beside the 4-stage ring (k <= 16)
-constexpr int N_THREADS = 192;  // 6 warps
+constexpr int N_THREADS = 320;  // 10 warps: TMA, MMA, 8 epilogue
+constexpr int EPI_THREADS = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -127,8 +128,8 @@ struct __align__(1024) DenseSmem {
   uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
   __align__(16) float inv_c[2][BN];
-  float lscore[MAXK][BM];  // [slot][query]: the 32 lanes of a warp hit 32 different banks
-  int lrow[MAXK][BM];
+  float lscore[2][MAXK][BM];  // [column half][slot][query]: the 32 lanes of a warp hit 32 different banks
+  int lrow[2][MAXK][BM];
 };
 
 __global__ void __launch_bounds__(N_THREADS, 1)
@@ -146,7 +147,7 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < STAGES; i++) { mbar_init(&S.full_bar[i], 1); mbar_init(&S.empty_bar[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&S.tmem_full[i], 1); mbar_init(&S.tmem_empty[i], 4); }
+    for (int i = 0; i < 2; i++) { mbar_init(&S.tmem_full[i], 1); mbar_init(&S.tmem_empty[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: 512 columns = two 128x256 fp32 accumulators
@@ -202,13 +203,15 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
     }
   } else {
-    // ===== epilogue: warps 2..5; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
+    // ===== epilogue: warps 2..9; a warp may only touch TMEM lanes 32*(warp%4) .. +31, so two warps share
+    // each lane quarter and split the 256 columns of a tile between them (half 0 / half 1) =====
     const int lane_base = 32 * (warp & 3);
     const int qi = lane_base + lane;            // TMEM lane = query inside the tile
-    const int et = (warp - 2) * 32 + lane;      // 0..127 among the epilogue threads
+    const int et = (warp - 2) * 32 + lane;      // 0..255 among the epilogue threads
+    const int half = (warp - 2) >> 2;           // which 128 columns of every tile this thread scans
     const int k = P.k;
-    float *ls = &S.lscore[0][qi];               // element j of this query's list lives at ls[j * BM]
-    int *lr = &S.lrow[0][qi];
+    float *ls = &S.lscore[half][0][qi];         // element j of this thread's list lives at ls[j * BM]
+    int *lr = &S.lrow[half][0][qi];
     int cur_qtile = -1, cnt = 0;
     int64_t q = 0;
     bool q_ok = false;
@@ -219,7 +222,7 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     float lo = INFINITY;         // a row enters the list iff its score > lo
     auto flush = [&]() {    // publish the list of (cur_qtile, this CTA)
       if (cur_qtile < 0 || !q_ok) return;
-      const int slot = (int)my_split;
+      const int slot = (int)my_split * 2 + half;
       for (int j = 0; j < k; j++) {
         const size_t o = ((size_t)slot * P.n_q + q) * k + j;
         P.part_scores[o] = j < cnt ? ls[j * BM] : -INFINITY;
@@ -245,7 +248,7 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       const uint32_t aphase = (uint32_t)((it >> 1) & 1);
       // inverse norms of this tile's rows (0 past the end; such rows are rejected by index below)
       const int64_t row0 = t * BN;
-      for (int c = et; c < BN; c += 128) S.inv_c[as][c] = (row0 + c < P.n_rows) ? P.inv_norm_c[row0 + c] : -INFINITY;  // 0 * -inf = NaN: never a candidate
+      for (int c = et; c < BN; c += EPI_THREADS) S.inv_c[as][c] = (row0 + c < P.n_rows) ? P.inv_norm_c[row0 + c] : -INFINITY;  // 0 * -inf = NaN: never a candidate
       if (q_ok) {
         const unsigned int gk = *(volatile unsigned int *)&P.gthr[q];
         if (gk > fkey(-INFINITY) && fkey_inv(gk) > gth) {
@@ -254,12 +257,12 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           lo = fmaxf(thr, gth_pred);
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&S.tmem_full[as], aphase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < ((P.dbg == 1) ? 0 : BN); c0 += 32) {
+      for (int c0 = half * (BN / 2); c0 < ((P.dbg == 1) ? 0 : (half + 1) * (BN / 2)); c0 += 32) {
         uint32_t v[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -489,13 +492,14 @@ int kv_dense_topk(kv_dense_index *dx, const uint16_t *q_bf16, int64_t n_q, int k
     n_lists = std::max<int64_t>(1, std::min<int64_t>(n_lists, r_tiles));
   }
   dx->last_splits = n_lists;
-  KV_CUDA(dx->d_part_s.ensure(n_lists * n_q * k)); KV_CUDA(dx->d_part_r.ensure(n_lists * n_q * k));
+  const int64_t n_part = n_lists * 2;  // two epilogue threads (column halves) per query and CTA
+  KV_CUDA(dx->d_part_s.ensure(n_part * n_q * k)); KV_CUDA(dx->d_part_r.ensure(n_part * n_q * k));
   KV_CUDA(dx->d_out_s.ensure(n_q * k)); KV_CUDA(dx->d_out_r.ensure(n_q * k));
   KV_CUDA(dx->d_gthr.ensure(n_q));
   KV_CUDA(cudaMemsetAsync(dx->d_gthr.p, 0, (size_t)n_q * 4, s));
   // unused (query tile, slot) pairs stay "empty": row -1 (the merge ignores their scores)
-  KV_CUDA(cudaMemsetAsync(dx->d_part_r.p, 0xFF, (size_t)n_lists * n_q * k * 8, s));
-  KV_CUDA(cudaMemsetAsync(dx->d_part_s.p, 0xFF, (size_t)n_lists * n_q * k * 4, s));
+  KV_CUDA(cudaMemsetAsync(dx->d_part_r.p, 0xFF, (size_t)n_part * n_q * k * 8, s));
+  KV_CUDA(cudaMemsetAsync(dx->d_part_s.p, 0xFF, (size_t)n_part * n_q * k * 4, s));
   DenseParams P;
   P.n_rows = dx->n_rows; P.row_base = dx->row_base; P.n_q = n_q; P.dim = dx->dim; P.k = k; P.n_lists = (int)n_lists;
   P.r_tiles = r_tiles; P.q_tiles = q_tiles;
@@ -509,7 +513,7 @@ int kv_dense_topk(kv_dense_index *dx, const uint16_t *q_bf16, int64_t n_q, int k
   KV_CUDA(cudaEventRecord(dx->ev[1], s));
   KV_CUDA(cudaStreamSynchronize(s));
   cudaEventElapsedTime(&dx->last_ms, dx->ev[0], dx->ev[1]);
-  rc = kv_merge_topk_device(dx->device, dx->d_part_s.p, dx->d_part_r.p, (int)n_lists, n_q, k, dx->d_out_s.p, dx->d_out_r.p);
+  rc = kv_merge_topk_device(dx->device, dx->d_part_s.p, dx->d_part_r.p, (int)n_part, n_q, k, dx->d_out_s.p, dx->d_out_r.p);
   if (rc != KV_OK) return rc;
   KV_CUDA(cudaMemcpy(out_scores, dx->d_out_s.p, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost));
   KV_CUDA(cudaMemcpy(out_rows, dx->d_out_r.p, (size_t)n_q * k * 8, cudaMemcpyDeviceToHost));
