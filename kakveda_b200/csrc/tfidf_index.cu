@@ -6,10 +6,12 @@
 #include "tfidf_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -78,6 +80,7 @@ struct kv_index {
   std::vector<uint32_t> h_df;
   std::vector<uint8_t> h_univ;
   std::vector<uint32_t> h_utf;
+  std::vector<std::pair<uint32_t, uint32_t>> h_su;  // summary-universal features (fid, tf), sorted
   int64_t n_univ = 0;
 
   // query scratch
@@ -117,7 +120,7 @@ struct kv_index {
 namespace {
 
 struct QueryPrep {
-  double nq = 0, dotU = 0, corrU = 0;
+  double nq = 0, dotU = 0, corrU = 0, dotS = 0, corrS = 0;  // S: bound start = universal + summary-universal part
   std::vector<uint32_t> fid;  // non-universal, in-vocabulary features
   std::vector<uint32_t> tfq;
 };
@@ -132,7 +135,7 @@ inline void idf_host(int64_t n_total, uint32_t df, double &a, double &d) {
 
 void prep_query(const kv_index *ix, const uint32_t *ids, const uint32_t *tf, int64_t nnz, double oov_tf2,
                 QueryPrep &out) {
-  out.dotU = out.corrU = 0;
+  out.dotU = out.corrU = out.dotS = out.corrS = 0;
   out.fid.clear();
   out.tfq.clear();
   double idf0 = std::log((double)(ix->n_total + 2) / 2.0) + 1.0;  // df == 0 features of the query
@@ -154,8 +157,16 @@ void prep_query(const kv_index *ix, const uint32_t *ids, const uint32_t *tf, int
     } else {
       out.fid.push_back(t);
       out.tfq.push_back(tf[i]);
+      auto it = std::lower_bound(ix->h_su.begin(), ix->h_su.end(), std::make_pair(t, 0u));
+      if (it != ix->h_su.end() && it->first == t) {
+        double u = (double)it->second;
+        out.dotS += f * u * a;
+        out.corrS += u * u * d;
+      }
     }
   }
+  out.dotS += out.dotU;
+  out.corrS += out.corrU;
 }
 
 // lexicographic order of two id sequences (shorter prefix first)
@@ -419,7 +430,8 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
     std::vector<int64_t> chunkptr((size_t)ix->n_chunks + 1, 0), sumptr((size_t)ix->n_chunks + 1, 0);
     std::vector<std::vector<uint32_t>> part((size_t)T), spart((size_t)T);
     std::vector<std::vector<std::pair<unsigned long long, uint32_t>>> povf((size_t)T);
-    std::vector<int64_t> chunk_len((size_t)ix->n_chunks, 0), sum_len((size_t)ix->n_chunks, 0);
+    std::vector<int64_t> chunk_len((size_t)ix->n_chunks, 0), sum_len((size_t)ix->n_chunks, 0), union_len((size_t)ix->n_chunks, 0);
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> punion((size_t)T);  // chunk unions (fid, max tf), per thread
     parallel_for(ix->n_chunks, T, [&](int t, int64_t c0, int64_t c1) {
       std::vector<std::pair<uint32_t, uint32_t>> u;                       // (fid, tf) of the whole chunk
       std::vector<std::vector<std::pair<uint32_t, uint32_t>>> kept;       // stored entries per row
@@ -464,15 +476,60 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
           out.back() |= 0x80000000u;
         }
         chunk_len[(size_t)c] = (int64_t)(out.size() - before);
-        // summary pseudo-row: union of the stored features with the max tf
+        // union of the chunk's stored features with the max tf (summaries are emitted below)
         std::sort(u.begin(), u.end());
-        const size_t sbefore = sout.size();
+        const size_t ubefore = punion[(size_t)t].size();
         for (size_t i = 0; i < u.size();) {
           size_t j = i;
           while (j + 1 < u.size() && u[j + 1].first == u[i].first) j++;
-          emit(sout, (unsigned long long)(n + c), u[i].first, u[j].second);  // sorted: last of the run = max tf
+          punion[(size_t)t].emplace_back(u[i].first, u[j].second);  // sorted: last of the run = max tf
           i = j + 1;
         }
+        union_len[(size_t)c] = (int64_t)(punion[(size_t)t].size() - ubefore);
+      }
+    });
+    // "summary-universal" features: present in >= 90 % of the chunk unions.  The bounds assume them present
+    // in EVERY chunk with their largest tf (a valid over-estimate), so the summaries need not store them.
+    {
+      std::unique_ptr<std::atomic<uint32_t>[]> cnt(new std::atomic<uint32_t>[(size_t)Vz]);
+      std::unique_ptr<std::atomic<uint32_t>[]> tfm(new std::atomic<uint32_t>[(size_t)Vz]);
+      parallel_for(Vz, T, [&](int, int64_t a0, int64_t a1) {
+        for (int64_t i = a0; i < a1; i++) { cnt[(size_t)i].store(0, std::memory_order_relaxed); tfm[(size_t)i].store(0, std::memory_order_relaxed); }
+      });
+      parallel_for(T, T, [&](int, int64_t t0, int64_t t1) {
+        for (int64_t t = t0; t < t1; t++)
+          for (const auto &e : punion[(size_t)t]) {
+            cnt[e.first].fetch_add(1, std::memory_order_relaxed);
+            uint32_t cur = tfm[e.first].load(std::memory_order_relaxed);
+            while (e.second > cur && !tfm[e.first].compare_exchange_weak(cur, e.second, std::memory_order_relaxed)) {}
+          }
+      });
+      ix->h_su.clear();
+      const uint32_t need = (uint32_t)std::max<int64_t>(2, (ix->n_chunks * 9 + 9) / 10);
+      for (int64_t f = 0; f < V; f++)
+        if (cnt[(size_t)f].load(std::memory_order_relaxed) >= need) ix->h_su.emplace_back((uint32_t)f, tfm[(size_t)f].load(std::memory_order_relaxed));
+    }
+    parallel_for(ix->n_chunks, T, [&](int t, int64_t c0, int64_t c1) {
+      std::vector<uint32_t> &sout = spart[(size_t)t];
+      auto &ovf = povf[(size_t)t];
+      const auto &src = punion[(size_t)t];
+      size_t off = 0;
+      for (int64_t c = c0; c < c1; c++) {
+        // summary pseudo-row: the union minus the summary-universal features
+        const size_t sbefore = sout.size();
+        for (size_t i = off; i < off + (size_t)union_len[(size_t)c]; i++) {
+          {
+            auto it = std::lower_bound(ix->h_su.begin(), ix->h_su.end(), std::make_pair(src[i].first, 0u));
+            if (it != ix->h_su.end() && it->first == src[i].first) continue;
+          }
+          uint32_t f = src[i].first, tfv = src[i].second;
+          if (tfv >= TF_OVF) {
+            ovf.emplace_back(((unsigned long long)(n + c) << 32) | f, tfv);
+            tfv = TF_OVF;
+          }
+          sout.push_back((f << 5) | tfv);
+        }
+        off += (size_t)union_len[(size_t)c];
         if (sout.size() == sbefore) sout.push_back(PAD_ENTRY);
         sout.back() |= 0x80000000u;
         sum_len[(size_t)c] = (int64_t)(sout.size() - sbefore);
@@ -600,7 +657,7 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
       return kv_fail(KV_ERR_INVALID, "kv_topk: bad query CSR");
 
   // ---- host: per-query constants (float64), text order of the queries, tile tables ----
-  KV_CUDA(ix->h_qconst.ensure(4 * n_q));
+  KV_CUDA(ix->h_qconst.ensure(6 * n_q));
   KV_CUDA(ix->h_qperm.ensure(2 * n_q));
   std::vector<QueryPrep> qp((size_t)n_q);
   const int T = host_threads();
@@ -622,6 +679,7 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
     return cmp_seq(q_ids + q_indptr[a], q_indptr[a + 1] - q_indptr[a], q_ids + q_indptr[b], q_indptr[b + 1] - q_indptr[b]) < 0;
   });
   float *c_nq = ix->h_qconst.p, *c_dotU = c_nq + n_q, *c_corrU = c_dotU + n_q, *c_ninf = c_corrU + n_q;
+  float *c_dotS = c_ninf + n_q, *c_corrS = c_dotS + n_q;
   int *qperm = ix->h_qperm.p, *null_list = qperm + n_q;
   int64_t n_null = 0;
   std::vector<char> skip((size_t)n_q, 0);  // by sorted slot: not part of any tile table
@@ -632,6 +690,8 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
     c_dotU[i] = (float)p.dotU;
     c_corrU[i] = (float)p.corrU;
     c_ninf[i] = -INFINITY;
+    c_dotS[i] = (float)(p.dotS * (1.0 + 1e-6));  // bounds may only err upwards
+    c_corrS[i] = (float)p.corrS;
     int nx = 0;
     for (uint32_t f : p.tfq) nx += f > 1;
     const bool null_q = p.nq <= 0.0 || (p.fid.empty() && p.dotU == 0.0);  // every score is 0
@@ -721,19 +781,19 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
 
   KV_CUDA(ix->d_tables.ensure(n_tiles * (int64_t)Tile::table_bytes));
   KV_CUDA(ix->d_tiles.ensure(n_tiles));
-  KV_CUDA(ix->d_qconst.ensure(4 * n_q));
+  KV_CUDA(ix->d_qconst.ensure(6 * n_q));
   KV_CUDA(ix->d_qperm.ensure(2 * n_q));
   KV_CUDA(cudaEventRecord(ix->ev[0], s));
   KV_CUDA(cudaMemcpyAsync(ix->d_tables.p, ix->h_tables.p, (size_t)n_tiles * Tile::table_bytes, cudaMemcpyHostToDevice, s));
   KV_CUDA(cudaMemcpyAsync(ix->d_tiles.p, ix->h_tiles.p, (size_t)n_tiles * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
-  KV_CUDA(cudaMemcpyAsync(ix->d_qconst.p, ix->h_qconst.p, (size_t)4 * n_q * sizeof(float), cudaMemcpyHostToDevice, s));
+  KV_CUDA(cudaMemcpyAsync(ix->d_qconst.p, ix->h_qconst.p, (size_t)6 * n_q * sizeof(float), cudaMemcpyHostToDevice, s));
   KV_CUDA(cudaMemcpyAsync(ix->d_qperm.p, ix->h_qperm.p, (size_t)2 * n_q * sizeof(int), cudaMemcpyHostToDevice, s));
   KV_CUDA(cudaEventRecord(ix->ev[1], s));
   KV_CUDA(cudaStreamSynchronize(s));  // the pinned staging buffers may be rewritten by the next call
   ix->batch_q = n_q;
   ix->batch_tiles = n_tiles;
   ix->batch_null = n_null;
-  ix->batch_h2d_bytes = n_tiles * (int64_t)(Tile::table_bytes + sizeof(TileDesc)) + 4 * n_q * (int64_t)sizeof(float) +
+  ix->batch_h2d_bytes = n_tiles * (int64_t)(Tile::table_bytes + sizeof(TileDesc)) + 6 * n_q * (int64_t)sizeof(float) +
                         2 * n_q * (int64_t)sizeof(int);
   ix->batch_valid = true;
   cudaEventElapsedTime(&ix->last_ms[0], ix->ev[0], ix->ev[1]);
@@ -776,6 +836,7 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
     P.row_base = ix->row_base; P.B32 = ix->d_B32.p; P.ovf_keys = ix->d_ovf_keys.p; P.ovf_vals = ix->d_ovf_vals.p;
     P.n_ovf = ix->n_ovf; P.tables = ix->d_tables.p; P.tiles = ix->d_tiles.p;
     P.q_nq = ix->d_qconst.p; P.q_dotU = P.q_nq + n_q; P.q_corrU = P.q_dotU + n_q;
+    P.q_dotS = P.q_nq + 4 * n_q; P.q_corrS = P.q_nq + 5 * n_q;
     P.gthr = ix->d_gthr.p; P.ubuf = ix->d_ubuf.p; P.stats = ix->d_stats.p;
     P.n_q = n_q; P.k = k; P.n_splits = (int)n_splits; P.prune = prune;
     P.part_scores = ix->d_part_s.p; P.part_rows = ix->d_part_r.p;

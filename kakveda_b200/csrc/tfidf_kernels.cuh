@@ -27,14 +27,15 @@
 //     entry order, so the result is bit-identical to an unfactored scan;
 //   * per chunk a summary pseudo-row (union of the chunk's features with the max tf, in the same
 //     entry format) and the smallest row norm: evaluating it like a row yields an upper bound of
-//     every score in the chunk (block-max pruning, exact);
+//     every score in the chunk (block-max pruning, exact); features that every chunk summary contains
+//     with one tf are kept out of the summaries and enter the bounds as per-query constants;
 //   * B32/B64: row norms B_c by position.
 #pragma once
 #include "kv_cuda.cuh"
 
 namespace kvk {
 
-constexpr int CHUNK_ROWS = 128;
+constexpr int CHUNK_ROWS = 64;
 constexpr uint32_t FID_BITS = 26;
 constexpr uint32_t FID_MASK = (1u << FID_BITS) - 1;
 constexpr uint32_t FID_NONE = FID_MASK;  // sentinel feature id (never in a table)
@@ -274,6 +275,7 @@ struct TopkParams {
   const unsigned char *tables;  // [n_tiles][table_bytes]
   const TileDesc *tiles;
   const float *q_nq, *q_dotU, *q_corrU;  // [n_q] (sorted query order)
+  const float *q_dotS, *q_corrS;         // [n_q] start values of chunk bounds (universal + summary-universal features)
   int *gthr;                             // [n_q] float bits: lower bound of the global k-th score
   float *ubuf;                           // [n_tiles][n_chunks] chunk upper bounds (scratch)
   unsigned long long *stats;             // [0] chunks scanned, [1] chunks pruned, [2] summaries evaluated
@@ -318,8 +320,8 @@ __device__ __forceinline__ void scan_entries(const uint32_t *__restrict__ stream
                                              int64_t ovf_pos0, int64_t ovf_core_key, const uint32_t *s_keys,
                                              const float2 *s_ad, const uint32_t *s_masks, const uint32_t *s_xkey,
                                              const float *s_xtf, int n_extras, const unsigned long long *ovf_keys,
-                                             const uint32_t *ovf_vals, int n_ovf, const Lanes<G> &L, uint32_t gmask,
-                                             RowFn &&on_row) {
+                                             const uint32_t *ovf_vals, int n_ovf, const float (&dot0)[G],
+                                             const float (&corr0)[G], uint32_t gmask, RowFn &&on_row) {
   // gmask: bit g set = the 32 queries of group g take part (warp-uniform); others are skipped.
   // HAS_CORE: the range starts with the chunk's shared prefix, closed by a marker entry; the sums
   // reached at the marker are the state every row of the chunk restarts from.
@@ -327,7 +329,7 @@ __device__ __forceinline__ void scan_entries(const uint32_t *__restrict__ stream
   const int lane = threadIdx.x & 31;
   float dot[G], corr[G], dotc[G], corrc[G];
 #pragma unroll
-  for (int g = 0; g < G; g++) { dot[g] = dotc[g] = L.dotU[g]; corr[g] = corrc[g] = L.corrU[g]; }
+  for (int g = 0; g < G; g++) { dot[g] = dotc[g] = dot0[g]; corr[g] = corrc[g] = corr0[g]; }
   int row_in = 0;
   bool in_core = HAS_CORE;
   for (int64_t p = p0; p < p1; p += 32) {
@@ -488,7 +490,7 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
     const int64_t pos0 = c * CHUNK_ROWS;
     refresh_filters();
     scan_entries<G, LOGH, true>(P.stream, P.chunkptr[c], P.chunkptr[c + 1], pos0, (int64_t)(OVF_CORE_BASE + c), s_keys, s_ad,
-                                s_masks, s_xkey, s_xtf, td.n_extras, P.ovf_keys, P.ovf_vals, P.n_ovf, L, gmask,
+                                s_masks, s_xkey, s_xtf, td.n_extras, P.ovf_keys, P.ovf_vals, P.n_ovf, L.dotU, L.corrU, gmask,
                           [&](int row_in, const float *dot, const float *corr) {
       const float Bc = P.B32[pos0 + row_in];
 #pragma unroll
@@ -552,8 +554,15 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
     for (int64_t c = c_lo + warp; c < c_hi; c += n_warps) {
       const float Bmin = P.chunk_minB[c];
       float best = -INFINITY;
+      float sd[G], sc0[G];  // start of a bound: universal features + the features every chunk summary has
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const int q = td.q_begin + (L.valid[g] ? g * 32 + lane : 0);
+        sd[g] = P.q_dotS[q];
+        sc0[g] = P.q_corrS[q];
+      }
       scan_entries<G, LOGH, false>(P.sum_stream, P.sumptr[c], P.sumptr[c + 1], P.n_rows + c, 0, s_keys, s_ad, s_masks, s_xkey,
-                                   s_xtf, td.n_extras, P.ovf_keys, P.ovf_vals, P.n_ovf, L, FULL,
+                                   s_xtf, td.n_extras, P.ovf_keys, P.ovf_vals, P.n_ovf, sd, sc0, FULL,
                             [&](int, const float *dot, const float *corr) {
 #pragma unroll
         for (int g = 0; g < G; g++) {
@@ -615,8 +624,15 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
           const float Bmin = P.chunk_minB[cc];
           long long t1 = clock64();
           uint32_t may = 0;  // bit g: this lane's query of group g could still place a row of the chunk
+          float sd[G], sc0[G];
+#pragma unroll
+          for (int g = 0; g < G; g++) {
+            const int q = td.q_begin + (L.valid[g] ? g * 32 + lane : 0);
+            sd[g] = P.q_dotS[q];
+            sc0[g] = P.q_corrS[q];
+          }
           scan_entries<G, LOGH, false>(P.sum_stream, P.sumptr[cc], P.sumptr[cc + 1], P.n_rows + cc, 0, s_keys, s_ad, s_masks,
-                                       s_xkey, s_xtf, td.n_extras, P.ovf_keys, P.ovf_vals, P.n_ovf, L, FULL,
+                                       s_xkey, s_xtf, td.n_extras, P.ovf_keys, P.ovf_vals, P.n_ovf, sd, sc0, FULL,
                                 [&](int, const float *dot, const float *corr) {
 #pragma unroll
             for (int g = 0; g < G; g++) {

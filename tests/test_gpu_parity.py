@@ -330,7 +330,7 @@ def test_large_properties(lib):
     raw = buf.tobytes()
     text = lambda i: raw[off[i]:off[i + 1]].decode()
     exact = 0
-    for i in range(0, q, 16):
+    for i in range(0, q, 48):
         if abs(s[i, 0] - 1.0) < 1e-6:               # the query repeats a stored failure
             assert text(int(r[i, 0])) == queries[i]
             exact += 1
@@ -340,7 +340,7 @@ def test_large_properties(lib):
         np.testing.assert_allclose(s[i], vals, rtol=RTOL32)
         for a, b in zip(order, r[i].tolist()):
             assert a == b or full[a] == pytest.approx(full[b], rel=RTOL32)
-    assert exact > 30
+    assert exact > 10
 
 
 def test_hash_fingerprint_match(lib):
