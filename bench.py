@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=50_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="rows", choices=["rows", "queries"],
+                    help="rows: corpus rows sharded over the GPUs (BASELINE configs[2]); queries: index replicated, queries split")
     return ap.parse_args()
 
 
@@ -55,7 +57,9 @@ def workload_config(a, world):
                     "%d-query batch (seed 0xFACADE, ~50%% exact repeats of stored rows), TF-IDF(1,2-gram) cosine, fused top-k=%d"
                     % (a.rows, a.queries, a.k),
         "rows": a.rows, "queries": a.queries, "k": a.k,
-        "parallelism": "corpus rows sharded over %d GPU(s); queries replicated; 1 all-gather of partial top-k" % world,
+        "parallelism": ("corpus rows sharded over %d GPU(s); queries replicated; 1 all-gather of partial top-k" % world)
+                       if getattr(a, "shard", "rows") == "rows" else
+                       ("index replicated on %d GPU(s); query batch split; 1 all-gather of the results" % world),
         "l2": "inputs larger than L2 (scan stream >> 126 MB); no explicit flush",
     }
 
@@ -212,7 +216,7 @@ def run_ours(a):
     t0 = time.perf_counter()
     buf, off = synth.signatures_packed(synth.CORPUS_SEED, 0, a.rows)
     t_gen = time.perf_counter() - t0
-    shard = ShardedGfkb(device=local, rank=rank, world=world)
+    shard = ShardedGfkb(device=local, rank=rank, world=world, mode=a.shard)
     t0 = time.perf_counter()
     shard.build_packed(buf, off, 0, n_threads=threads)
     t_build = time.perf_counter() - t0

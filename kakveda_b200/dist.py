@@ -68,9 +68,19 @@ def merge_on_device(device: int, gs, gr):
 
 
 class ShardedGfkb:
-    """This rank's shard of a GFKB spread over ``world`` GPUs."""
+    """This rank's share of a GFKB job spread over ``world`` GPUs.
 
-    def __init__(self, device: int, rank: int = 0, world: int = 1, group=None):
+    ``mode="rows"`` (default, BASELINE configs[2]): the corpus rows are sharded, every rank scans its rows for
+    ALL queries, one all-gather of partial top-k + merge.  ``mode="queries"``: every rank holds the WHOLE index
+    (0.9 GB at 10M rows -- trivial next to 180 GB of HBM) and answers its contiguous slice of the query batch; the
+    only exchange is the all-gather of the finished results.  Pruning thresholds are as tight as on one GPU, so
+    this mode scales almost linearly; it is offered because the index is so small, not used for the headline.
+    """
+
+    def __init__(self, device: int, rank: int = 0, world: int = 1, group=None, mode: str = "rows"):
+        if mode not in ("rows", "queries"):
+            raise ValueError("mode must be 'rows' or 'queries'")
+        self.mode = mode
         self.device, self.rank, self.world, self.group = device, rank, world, group
         self.vocab = Vocabulary()
         self.index: Optional[GfkbIndex] = None
@@ -81,17 +91,28 @@ class ShardedGfkb:
 
         fb = self.vocab.featurize_packed(data, offsets, mode, grow=True, n_threads=n_threads)
         self.n_global = fb.n
-        lo, hi = shard_bounds(fb.n, self.world, self.rank)
+        lo, hi = shard_bounds(fb.n, self.world, self.rank) if self.mode == "rows" else (0, fb.n)
         self.index = GfkbIndex(device=self.device, row_base=lo, vocab=self.vocab)
         self.index.add_features(fb, lo, hi)
         fb.close()
-        if self.world > 1:
+        if self.world > 1 and self.mode == "rows":
             df = torch.from_numpy(self.index.local_df().astype(np.int32)).to(f"cuda:{self.device}")
             allreduce_df(df, self.group)
             self.index.set_global_df(df.cpu().numpy().astype(np.uint32), self.n_global)
         self.index.finalize()
 
     def upload(self, qfb: FeatureBatch) -> None:
+        if self.mode == "queries" and self.world > 1:
+            # this rank's slice of the batch: re-pack the CSR rows [lo, hi)
+            lo, hi = shard_bounds(qfb.n, self.world, self.rank)
+            self._qslice = (lo, hi)
+            ip = np.ascontiguousarray(qfb.indptr[lo:hi + 1])
+            _capi.check(_capi.load().kv_query_upload(self.index._h, ip.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                     qfb.ids.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                     qfb.tf.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                     np.ascontiguousarray(qfb.oov[lo:hi]).ctypes.data_as(C.POINTER(C.c_double)),
+                                                     hi - lo))
+            return
         self.index.upload_queries(qfb)
 
     def topk_resident(self, k: int):
@@ -100,6 +121,22 @@ class ShardedGfkb:
 
         q = self._resident_q
         dev = f"cuda:{self.device}"
+        if self.mode == "queries" and self.world > 1:
+            import torch.distributed as dist
+
+            lo, hi = self._qslice
+            per = (q + self.world - 1) // self.world  # equal-sized slots for the all-gather
+            s = torch.full((per, k), float("-inf"), dtype=torch.float32, device=dev)
+            r = torch.full((per, k), -1, dtype=torch.int64, device=dev)
+            if hi > lo:
+                self.index.topk_resident(k, s.data_ptr(), r.data_ptr())
+            gs = torch.empty((self.world * per, k), dtype=torch.float32, device=dev)
+            gr = torch.empty((self.world * per, k), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(gs, s, group=self.group)
+            dist.all_gather_into_tensor(gr, r, group=self.group)
+            keep = torch.cat([torch.arange(w * per, w * per + (shard_bounds(q, self.world, w)[1] - shard_bounds(q, self.world, w)[0]),
+                                           device=dev) for w in range(self.world)])
+            return gs[keep], gr[keep]
         s = torch.empty((q, k), dtype=torch.float32, device=dev)
         r = torch.empty((q, k), dtype=torch.int64, device=dev)
         self.index.topk_resident(k, s.data_ptr(), r.data_ptr())

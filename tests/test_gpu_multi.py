@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n, q, k, tmp):
+def _worker(rank, world, port, n, q, k, tmp, mode):
     import torch
     import torch.distributed as dist
 
@@ -32,16 +32,17 @@ def _worker(rank, world, port, n, q, k, tmp):
 
         buf, off = synth.signatures_packed(synth.CORPUS_SEED, 0, n)
         qbuf, qoff = synth.signatures_packed(synth.QUERY_SEED, 0, q, dup_of_seed=synth.CORPUS_SEED, dup_rows=n)
-        sh = ShardedGfkb(device=rank, rank=rank, world=world)
+        sh = ShardedGfkb(device=rank, rank=rank, world=world, mode=mode)
         sh.build_packed(buf, off, 0, n_threads=8)
         s, r = sh.topk_packed(qbuf, qoff, k)
-        np.save(Path(tmp, f"s{rank}.npy"), s)
-        np.save(Path(tmp, f"r{rank}.npy"), r)
+        np.save(Path(tmp, f"s{rank}{mode}.npy"), s)
+        np.save(Path(tmp, f"r{rank}{mode}.npy"), r)
     finally:
         dist.destroy_process_group()
 
 
-def test_two_rank_sharded_topk(built_lib, tmp_path):
+@pytest.mark.parametrize("mode", ["rows", "queries"])
+def test_two_rank_sharded_topk(built_lib, tmp_path, mode):
     import torch
     import torch.multiprocessing as mp
 
@@ -50,9 +51,9 @@ def test_two_rank_sharded_topk(built_lib, tmp_path):
     from kakveda_b200 import GfkbIndex, synth
 
     n, q, k = 200_000, 1000, 16
-    mp.spawn(_worker, args=(2, _free_port(), n, q, k, str(tmp_path)), nprocs=2, join=True)
-    s0, r0 = np.load(tmp_path / "s0.npy"), np.load(tmp_path / "r0.npy")
-    s1, r1 = np.load(tmp_path / "s1.npy"), np.load(tmp_path / "r1.npy")
+    mp.spawn(_worker, args=(2, _free_port(), n, q, k, str(tmp_path), mode), nprocs=2, join=True)
+    s0, r0 = np.load(tmp_path / f"s0{mode}.npy"), np.load(tmp_path / f"r0{mode}.npy")
+    s1, r1 = np.load(tmp_path / f"s1{mode}.npy"), np.load(tmp_path / f"r1{mode}.npy")
     np.testing.assert_array_equal(r0, r1)  # every rank ends with the same merged result
     np.testing.assert_array_equal(s0, s1)
     one = GfkbIndex()
