@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
 #include <limits>
 #include <memory>
 #include <mutex>
@@ -71,12 +72,12 @@ struct kv_index {
   DevBuf<float> d_B32, d_cminB;
   DevBuf<uint8_t> d_univ;
   DevBuf<int> d_perm;
-  DevBuf<int64_t> d_chunkptr, d_sumptr;
-  DevBuf<uint32_t> d_stream, d_sum_stream;
+  DevBuf<int64_t> d_chunkptr, d_sumptr, d_grpptr;
+  DevBuf<uint32_t> d_stream, d_sum_stream, d_grp_stream;
   DevBuf<unsigned long long> d_ovf_keys;
   DevBuf<uint32_t> d_ovf_vals;
   int n_ovf = 0;
-  int64_t stream_len = 0, sum_len = 0, n_chunks = 0;
+  int64_t stream_len = 0, sum_len = 0, grp_len = 0, n_chunks = 0;
   std::vector<uint32_t> h_df;
   std::vector<uint8_t> h_univ;
   std::vector<uint32_t> h_utf;
@@ -250,7 +251,7 @@ void kv_index_destroy(kv_index *ix) {
   ix->d_df.release(); ix->d_cnt.release(); ix->d_tfmin.release(); ix->d_tfmax.release(); ix->d_utf.release();
   ix->d_a64.release(); ix->d_d64.release(); ix->d_bb64.release(); ix->d_B64.release();
   ix->d_B32.release(); ix->d_cminB.release(); ix->d_univ.release(); ix->d_perm.release();
-  ix->d_chunkptr.release(); ix->d_sumptr.release();
+  ix->d_chunkptr.release(); ix->d_sumptr.release(); ix->d_grpptr.release(); ix->d_grp_stream.release();
   ix->d_stream.release(); ix->d_sum_stream.release();
   ix->d_ovf_keys.release(); ix->d_ovf_vals.release();
   ix->h_tables.release(); ix->h_tiles.release(); ix->h_qconst.release(); ix->h_qperm.release();
@@ -556,6 +557,82 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
     }
     KV_CUDA(cudaMemcpyAsync(ix->d_chunkptr.p, chunkptr.data(), (size_t)(ix->n_chunks + 1) * 8, cudaMemcpyHostToDevice, s));
     KV_CUDA(cudaMemcpyAsync(ix->d_sumptr.p, sumptr.data(), (size_t)(ix->n_chunks + 1) * 8, cudaMemcpyHostToDevice, s));
+    // ---- bound-pass layout: the chunk summaries again, in groups of SUM_GROUP with their shared part first ----
+    {
+      const int64_t n_groups = (ix->n_chunks + SUM_GROUP - 1) / SUM_GROUP;
+      std::vector<int64_t> uoff((size_t)ix->n_chunks, 0);  // offset of a chunk's union inside its thread's buffer
+      std::vector<int> uthr((size_t)ix->n_chunks, 0);
+      for (int t = 0; t < T; t++) {
+        int64_t off = 0;
+        for (int64_t c = ix->n_chunks * t / T; c < ix->n_chunks * (t + 1) / T; c++) {
+          uoff[(size_t)c] = off;
+          uthr[(size_t)c] = t;
+          off += union_len[(size_t)c];
+        }
+      }
+      const int T2 = (int)std::max<int64_t>(1, std::min<int64_t>(T, n_groups));
+      std::vector<std::vector<uint32_t>> gp((size_t)T2);
+      std::vector<std::vector<std::pair<unsigned long long, uint32_t>>> govf((size_t)T2);
+      std::vector<int64_t> glen((size_t)n_groups, 0), grpptr((size_t)n_groups + 1, 0);
+      auto is_su = [&](uint32_t f) {
+        auto it = std::lower_bound(ix->h_su.begin(), ix->h_su.end(), std::make_pair(f, 0u));
+        return it != ix->h_su.end() && it->first == f;
+      };
+      parallel_for(n_groups, T2, [&](int t, int64_t a, int64_t b) {
+        std::vector<std::pair<uint32_t, uint32_t>> core, tmp;
+        auto &out = gp[(size_t)t];
+        auto push = [&](unsigned long long key_pos, uint32_t f, uint32_t tfv) {
+          if (tfv >= TF_OVF) {
+            govf[(size_t)t].emplace_back((key_pos << 32) | f, tfv);
+            tfv = TF_OVF;
+          }
+          out.push_back((f << 5) | tfv);
+        };
+        for (int64_t g = a; g < b; g++) {
+          const int64_t c0 = g * SUM_GROUP, c1 = std::min<int64_t>(ix->n_chunks, c0 + SUM_GROUP);
+          auto span = [&](int64_t c) {
+            const auto &src = punion[(size_t)uthr[(size_t)c]];
+            return std::make_pair(src.begin() + (std::ptrdiff_t)uoff[(size_t)c],
+                                  src.begin() + (std::ptrdiff_t)(uoff[(size_t)c] + union_len[(size_t)c]));
+          };
+          // core = entries (fid, tf) present in every chunk union of the group (sorted ranges -> set_intersection)
+          core.assign(span(c0).first, span(c0).second);
+          for (int64_t c = c0 + 1; c < c1 && !core.empty(); c++) {
+            tmp.clear();
+            std::set_intersection(core.begin(), core.end(), span(c).first, span(c).second, std::back_inserter(tmp));
+            core.swap(tmp);
+          }
+          const size_t before = out.size();
+          for (auto &e : core)
+            if (!is_su(e.first)) push(OVF_GCORE_BASE + (unsigned long long)g, e.first, e.second);
+          out.push_back(CORE_ENTRY);
+          for (int64_t c = c0; c < c1; c++) {
+            const size_t row_begin = out.size();
+            auto sp = span(c);
+            for (auto it = sp.first; it != sp.second; ++it) {
+              if (is_su(it->first) || std::binary_search(core.begin(), core.end(), *it)) continue;
+              push((unsigned long long)(n + ix->n_chunks + c), it->first, it->second);
+            }
+            if (out.size() == row_begin) out.push_back(PAD_ENTRY);
+            out.back() |= 0x80000000u;
+          }
+          glen[(size_t)g] = (int64_t)(out.size() - before);
+        }
+      });
+      for (int64_t g = 0; g < n_groups; g++) grpptr[(size_t)g + 1] = grpptr[(size_t)g] + glen[(size_t)g];
+      ix->grp_len = grpptr[(size_t)n_groups];
+      KV_CUDA(ix->d_grp_stream.ensure(ix->grp_len + 32));
+      KV_CUDA(ix->d_grpptr.ensure(n_groups + 1));
+      for (int t = 0; t < T2; t++) {
+        const int64_t g0 = n_groups * t / T2;
+        if (!gp[(size_t)t].empty())
+          KV_CUDA(cudaMemcpyAsync(ix->d_grp_stream.p + grpptr[(size_t)g0], gp[(size_t)t].data(), gp[(size_t)t].size() * 4,
+                                  cudaMemcpyHostToDevice, s));
+        ovf_all.insert(ovf_all.end(), govf[(size_t)t].begin(), govf[(size_t)t].end());
+      }
+      KV_CUDA(cudaMemcpyAsync(ix->d_grpptr.p, grpptr.data(), (size_t)(n_groups + 1) * 8, cudaMemcpyHostToDevice, s));
+      KV_CUDA(cudaStreamSynchronize(s));  // gp goes out of scope
+    }
     std::sort(ovf_all.begin(), ovf_all.end());
     ix->n_ovf = (int)ovf_all.size();
     KV_CUDA(ix->d_ovf_keys.ensure(std::max(1, ix->n_ovf))); KV_CUDA(ix->d_ovf_vals.ensure(std::max(1, ix->n_ovf)));
@@ -570,6 +647,9 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
   } else {
     KV_CUDA(ix->d_stream.ensure(32));
     KV_CUDA(ix->d_sum_stream.ensure(32));
+    KV_CUDA(ix->d_grp_stream.ensure(32));
+    KV_CUDA(ix->d_grpptr.ensure(1));
+    KV_CUDA(cudaMemsetAsync(ix->d_grpptr.p, 0, sizeof(int64_t), s));
     KV_CUDA(cudaMemsetAsync(ix->d_chunkptr.p, 0, sizeof(int64_t), s));
     KV_CUDA(cudaMemsetAsync(ix->d_sumptr.p, 0, sizeof(int64_t), s));
     KV_CUDA(cudaStreamSynchronize(s));
@@ -815,7 +895,7 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
   const int ctas_per_sm = 3;
   int64_t want = (int64_t)ix->sm_count * ctas_per_sm * 8;
   int64_t n_splits = (want + n_tiles - 1) / n_tiles;
-  n_splits = std::max<int64_t>(1, std::min<int64_t>(n_splits, std::max<int64_t>(1, ix->n_chunks / 8)));
+  n_splits = std::max<int64_t>(1, std::min<int64_t>(n_splits, std::max<int64_t>(1, ix->n_chunks / (2 * SUM_GROUP))));
   n_splits = std::min<int64_t>(n_splits, 2048);
   ix->last_tiles = n_tiles; ix->last_splits = n_splits; ix->last_ctas = n_tiles * n_splits;
   KV_CUDA(ix->d_gthr.ensure(n_q));
@@ -832,6 +912,7 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
     TopkParams P;
     P.stream = ix->d_stream.p; P.chunkptr = ix->d_chunkptr.p; P.sum_stream = ix->d_sum_stream.p; P.sumptr = ix->d_sumptr.p;
     P.chunk_minB = ix->d_cminB.p; P.perm = ix->d_perm.p;
+    P.grp_stream = ix->d_grp_stream.p; P.grpptr = ix->d_grpptr.p;
     P.n_chunks = ix->n_chunks; P.n_rows = ix->n_rows;
     P.row_base = ix->row_base; P.B32 = ix->d_B32.p; P.ovf_keys = ix->d_ovf_keys.p; P.ovf_vals = ix->d_ovf_vals.p;
     P.n_ovf = ix->n_ovf; P.tables = ix->d_tables.p; P.tiles = ix->d_tiles.p;
@@ -974,7 +1055,7 @@ int kv_index_layout(const kv_index *ix, int64_t bytes[4], int64_t counts[17]) {
   bytes[0] = ix->stream_len * 4;
   bytes[1] = ix->n_rows * 4;
   bytes[2] = (ix->n_chunks + 1) * 8;
-  bytes[3] = ix->sum_len * 4 + (ix->n_chunks + 1) * 12;
+  bytes[3] = (ix->sum_len + ix->grp_len) * 4 + (ix->n_chunks + 1) * 12;
   counts[0] = ix->stream_len; counts[1] = ix->n_univ; counts[2] = ix->n_rows;
   counts[3] = ix->last_ctas; counts[4] = ix->last_tiles; counts[5] = ix->last_splits;
   counts[6] = ix->batch_h2d_bytes; counts[7] = ix->n_ovf;

@@ -36,6 +36,8 @@
 namespace kvk {
 
 constexpr int CHUNK_ROWS = 64;
+constexpr int SUM_GROUP = 16;  // chunk summaries per group in the bound pass (their shared features are evaluated once)
+constexpr unsigned long long OVF_GCORE_BASE = 0xD0000000ULL;  // overflow-key position of a summary-group core: BASE + group
 constexpr uint32_t FID_BITS = 26;
 constexpr uint32_t FID_MASK = (1u << FID_BITS) - 1;
 constexpr uint32_t FID_NONE = FID_MASK;  // sentinel feature id (never in a table)
@@ -265,6 +267,8 @@ struct TopkParams {
   const int64_t *chunkptr;
   const uint32_t *sum_stream;  // chunk summaries (pseudo-rows)
   const int64_t *sumptr;
+  const uint32_t *grp_stream;  // the same summaries in groups of SUM_GROUP: shared core + per-chunk residuals
+  const int64_t *grpptr;
   const float *chunk_minB;
   const int *perm;
   int64_t n_chunks, n_rows, row_base;
@@ -541,7 +545,9 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
 
   long long t_ph1 = 0, t_re = 0, t_scan = 0, t_wait = 0;  // per-warp cycle counters (profiling aid)
   // chunks of this split
-  const int64_t c_lo = P.n_chunks * split / P.n_splits, c_hi = P.n_chunks * (split + 1) / P.n_splits;
+  const int64_t n_groups = (P.n_chunks + SUM_GROUP - 1) / SUM_GROUP;
+  const int64_t g_lo = n_groups * split / P.n_splits, g_hi = n_groups * (split + 1) / P.n_splits;
+  const int64_t c_lo = min(P.n_chunks, g_lo * SUM_GROUP), c_hi = min(P.n_chunks, g_hi * SUM_GROUP);
 
   if (!P.prune) {
     unsigned done = 0;
@@ -551,19 +557,23 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
     // ---- phase 1: an upper bound of every score in each chunk, from the chunk's summary pseudo-row ----
     float *ub = P.ubuf + (size_t)tile * P.n_chunks;
     long long t0 = clock64();
-    for (int64_t c = c_lo + warp; c < c_hi; c += n_warps) {
-      const float Bmin = P.chunk_minB[c];
-      float best = -INFINITY;
-      float sd[G], sc0[G];  // start of a bound: universal features + the features every chunk summary has
+    for (int64_t gg = g_lo + warp; gg < g_hi; gg += n_warps) {
+      float sd[G], sc0[G];  // start of a bound: universal features + the features (nearly) every chunk summary has
 #pragma unroll
       for (int g = 0; g < G; g++) {
         const int q = td.q_begin + (L.valid[g] ? g * 32 + lane : 0);
         sd[g] = P.q_dotS[q];
         sc0[g] = P.q_corrS[q];
       }
-      scan_entries<G, LOGH, false>(P.sum_stream, P.sumptr[c], P.sumptr[c + 1], P.n_rows + c, 0, s_keys, s_ad, s_masks, s_xkey,
-                                   s_xtf, td.n_extras, P.ovf_keys, P.ovf_vals, P.n_ovf, sd, sc0, FULL,
-                            [&](int, const float *dot, const float *corr) {
+      // one group = SUM_GROUP chunk summaries: the features they all share are evaluated once (core), then
+      // every chunk's residual -> its bound
+      scan_entries<G, LOGH, true>(P.grp_stream, P.grpptr[gg], P.grpptr[gg + 1], P.n_rows + P.n_chunks + gg * SUM_GROUP,
+                                  (int64_t)(OVF_GCORE_BASE + gg), s_keys, s_ad, s_masks, s_xkey, s_xtf, td.n_extras,
+                                  P.ovf_keys, P.ovf_vals, P.n_ovf, sd, sc0, FULL,
+                                  [&](int row_in, const float *dot, const float *corr) {
+        const int64_t c = gg * SUM_GROUP + row_in;
+        const float Bmin = P.chunk_minB[c];
+        float best = -INFINITY;
 #pragma unroll
         for (int g = 0; g < G; g++) {
           if (!L.valid[g]) continue;
@@ -571,9 +581,9 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
           const float b = den > 0.f ? __fdiv_rn(dot[g], __fsqrt_rn(den)) : INFINITY;
           best = fmaxf(best, b);
         }
+        for (int o = 16; o; o >>= 1) best = fmaxf(best, __shfl_xor_sync(FULL, best, o));
+        if (lane == 0) ub[c] = best;
       });
-      for (int o = 16; o; o >>= 1) best = fmaxf(best, __shfl_xor_sync(FULL, best, o));
-      if (lane == 0) ub[c] = best;
     }
     t_ph1 = clock64() - t0;
     t0 = clock64();
