@@ -92,6 +92,18 @@ void kv_index_destroy(kv_index *ix);
 int kv_index_append(kv_index *ix, const int64_t *indptr, const uint32_t *ids, const uint32_t *tf,
                     int64_t n_rows);
 
+/* K3: switch the index to token-set Jaccard before finalize (default KV_MODE_TFIDF_COSINE).  Rows and
+ * queries are then token-id SETS (every tf = 1; the id space is whatever the caller's vocabulary is),
+ * score = |q ∩ row| / |q ∪ row| (0 for two empty sets).  The reference has no Jaccard path (its docs
+ * list it as a possible measure, docs/failure-intelligence.md:43-46): parity UNPINNED, oracle = Python
+ * sets.  kv_topk then ranks by float32 inter/union; kv_jaccard_counts returns the exact integers of the
+ * selected pairs so that the caller can form the float64 ratio bit-exactly. */
+#define KV_MODE_TFIDF_COSINE 0
+#define KV_MODE_JACCARD 1
+int kv_index_set_mode(kv_index *ix, int mode);
+int kv_jaccard_counts(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const double *q_oov_tf2,
+                      int64_t n_q, int k, const int64_t *rows, int32_t *out_inter, int32_t *out_union);
+
 /* Optional, before finalize, for a corpus sharded over several GPUs: the GLOBAL document
  * frequency per feature id and the GLOBAL row count (else both come from the local rows). */
 int kv_index_set_global_df(kv_index *ix, const uint32_t *df, int64_t vocab_size, int64_t n_rows_global);

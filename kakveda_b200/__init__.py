@@ -8,10 +8,11 @@ sm_100a CUDA behind a C ABI (include/kakveda_b200.h).  See DESIGN.md.
 from .fingerprint import fingerprint_text, fingerprint_u64, normalize_prompt, signature_text
 from .denseindex import DenseIndex
 from .hashindex import HashIndex
+from .jaccardindex import JaccardIndex
 from .similarity import FeatureBatch, GfkbIndex, SimilarityEngine, Vocabulary
 
 __all__ = [
-    "SimilarityEngine", "GfkbIndex", "Vocabulary", "FeatureBatch", "HashIndex", "DenseIndex",
+    "SimilarityEngine", "GfkbIndex", "Vocabulary", "FeatureBatch", "HashIndex", "DenseIndex", "JaccardIndex",
     "signature_text", "fingerprint_text", "fingerprint_u64", "normalize_prompt",
 ]
 __version__ = "0.1.0"

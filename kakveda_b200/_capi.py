@@ -37,6 +37,9 @@ SIGNATURES = {
     "kv_index_create": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
     "kv_index_destroy": (None, [C.c_void_p]),
     "kv_index_append": (C.c_int, [C.c_void_p, c_i64p, c_u32p, c_u32p, C.c_int64]),
+    "kv_index_set_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "kv_jaccard_counts": (C.c_int, [C.c_void_p, c_i64p, c_u32p, c_f64p, C.c_int64, C.c_int, c_i64p,
+                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "kv_index_set_global_df": (C.c_int, [C.c_void_p, c_u32p, C.c_int64, C.c_int64]),
     "kv_index_local_df": (C.c_int, [C.c_void_p, c_u32p, C.c_int64]),
     "kv_index_finalize": (C.c_int, [C.c_void_p, C.c_int64]),

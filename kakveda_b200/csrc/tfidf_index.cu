@@ -66,6 +66,7 @@ struct kv_index {
   int64_t n_global = 0;
 
   bool finalized = false;
+  int jaccard = 0;  // 0: TF-IDF cosine (the reference's measure), 1: token-set Jaccard (K3)
   int64_t V = 0, n_total = 0;
   DevBuf<uint32_t> d_df, d_cnt, d_tfmin, d_tfmax, d_utf;
   DevBuf<double> d_a64, d_d64, d_bb64, d_B64;
@@ -126,7 +127,8 @@ struct QueryPrep {
   std::vector<uint32_t> tfq;
 };
 
-inline void idf_host(int64_t n_total, uint32_t df, double &a, double &d) {
+inline void idf_host(int64_t n_total, uint32_t df, double &a, double &d, int jaccard = 0) {
+  if (jaccard) { a = 1.0; d = 0.0; return; }
   double num = (double)(n_total + 2);
   double ib = std::log(num / ((double)df + 1.0)) + 1.0;
   double iq = std::log(num / ((double)df + 2.0)) + 1.0;
@@ -139,7 +141,7 @@ void prep_query(const kv_index *ix, const uint32_t *ids, const uint32_t *tf, int
   out.dotU = out.corrU = out.dotS = out.corrS = 0;
   out.fid.clear();
   out.tfq.clear();
-  double idf0 = std::log((double)(ix->n_total + 2) / 2.0) + 1.0;  // df == 0 features of the query
+  double idf0 = ix->jaccard ? 1.0 : std::log((double)(ix->n_total + 2) / 2.0) + 1.0;  // df == 0 features of the query
   out.nq = oov_tf2 * idf0 * idf0;
   for (int64_t i = 0; i < nnz; i++) {
     uint32_t t = ids[i];
@@ -149,7 +151,7 @@ void prep_query(const kv_index *ix, const uint32_t *ids, const uint32_t *tf, int
       continue;
     }
     double a, d;
-    idf_host(ix->n_total, ix->h_df[t], a, d);
+    idf_host(ix->n_total, ix->h_df[t], a, d, ix->jaccard);
     out.nq += f * f * a;
     if (ix->h_univ[t]) {
       double u = (double)ix->h_utf[t];
@@ -280,8 +282,8 @@ int kv_index_append(kv_index *ix, const int64_t *indptr, const uint32_t *ids, co
     if (indptr[i] < indptr[i - 1]) return kv_fail(KV_ERR_INVALID, "kv_index_append: indptr not monotone");
   const uint32_t *tfs = tf + indptr[0];
   for (int64_t i = 0; i < add; i++)
-    if (tfs[i] == 0 || tfs[i] > 65535u)
-      return kv_fail(KV_ERR_INVALID, "kv_index_append: term frequency %u outside 1..65535", tfs[i]);
+    if (tfs[i] == 0 || tfs[i] > 65535u || (ix->jaccard && tfs[i] != 1))
+      return kv_fail(KV_ERR_INVALID, "kv_index_append: term frequency %u outside 1..65535 (or != 1 in Jaccard mode)", tfs[i]);
   try {
     ix->h_indptr.reserve((size_t)(ix->n_rows + n_rows + 1));
     for (int64_t i = 1; i <= n_rows; i++) ix->h_indptr.push_back(indptr[i] - indptr[0] + ix->nnz);
@@ -309,6 +311,47 @@ int kv_index_append(kv_index *ix, const int64_t *indptr, const uint32_t *ids, co
   ix->ids.n = ix->nnz;
   ix->tf.n = ix->nnz;
   ix->finalized = false;
+  return KV_OK;
+}
+
+int kv_index_set_mode(kv_index *ix, int mode) {
+  if (!ix || (mode != KV_MODE_TFIDF_COSINE && mode != KV_MODE_JACCARD))
+    return kv_fail(KV_ERR_INVALID, "kv_index_set_mode: mode must be KV_MODE_TFIDF_COSINE or KV_MODE_JACCARD");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (mode == KV_MODE_JACCARD)
+    for (uint16_t f : ix->h_tf)
+      if (f != 1) return kv_fail(KV_ERR_INVALID, "kv_index_set_mode: Jaccard rows are token SETS (every tf must be 1)");
+  ix->jaccard = mode;
+  ix->finalized = false;
+  return KV_OK;
+}
+
+// |q ∩ row| and |q ∪ row| of already selected (query, row) pairs, exact integers (host; Q*k pairs)
+int kv_jaccard_counts(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const double *q_oov_tf2, int64_t n_q,
+                      int k, const int64_t *rows, int32_t *out_inter, int32_t *out_union) {
+  if (!ix || n_q < 0 || k < 1 || (n_q > 0 && (!q_indptr || !rows || !out_inter || !out_union)))
+    return kv_fail(KV_ERR_INVALID, "kv_jaccard_counts: bad arguments");
+  std::lock_guard<std::mutex> g(ix->mu);
+  std::vector<uint32_t> qs, rs;
+  for (int64_t q = 0; q < n_q; q++) {
+    qs.assign(q_ids + q_indptr[q], q_ids + q_indptr[q + 1]);
+    std::sort(qs.begin(), qs.end());
+    const int64_t nq = (int64_t)qs.size() + (q_oov_tf2 ? (int64_t)q_oov_tf2[q] : 0);
+    for (int j = 0; j < k; j++) {
+      const int64_t r = rows[q * k + j] - ix->row_base;
+      if (rows[q * k + j] < 0 || r < 0 || r >= ix->n_rows) { out_inter[q * k + j] = out_union[q * k + j] = -1; continue; }
+      rs.assign(ix->h_ids.begin() + ix->h_indptr[(size_t)r], ix->h_ids.begin() + ix->h_indptr[(size_t)r + 1]);
+      std::sort(rs.begin(), rs.end());
+      int32_t inter = 0;
+      for (size_t a = 0, b = 0; a < qs.size() && b < rs.size();) {
+        if (qs[a] == rs[b]) { inter++; a++; b++; }
+        else if (qs[a] < rs[b]) a++;
+        else b++;
+      }
+      out_inter[q * k + j] = inter;
+      out_union[q * k + j] = (int32_t)(nq + (int64_t)rs.size() - inter);
+    }
+  }
   return KV_OK;
 }
 
@@ -382,7 +425,7 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
   if (V) {
     IdfTables T{ix->d_a64.p, ix->d_d64.p, ix->d_bb64.p, ix->d_univ.p, ix->d_utf.p};
     idf_kernel<<<(unsigned)((V + 255) / 256), 256, 0, s>>>(ix->d_df.p, ix->d_cnt.p, ix->d_tfmin.p, ix->d_tfmax.p, V,
-                                                            ix->n_total, n, T);
+                                                            ix->n_total, n, ix->jaccard, T);
     KV_CUDA(cudaGetLastError());
   }
   ix->h_df.assign((size_t)V, 0);
@@ -685,7 +728,7 @@ static int score_impl(kv_index *ix, const uint32_t *q_ids, const uint32_t *q_tf,
     uint32_t h = (t * 0x9E3779B1u) >> (32 - log_h);
     while (tk[h] != KEY_EMPTY) h = (h + 1) & (H - 1);
     double a, d;
-    idf_host(ix->n_total, ix->h_df[t], a, d);
+    idf_host(ix->n_total, ix->h_df[t], a, d, ix->jaccard);
     tk[h] = t;
     tw[h] = (double)qp.tfq[i] * a;
     tdd[h] = d;
@@ -699,7 +742,7 @@ static int score_impl(kv_index *ix, const uint32_t *q_ids, const uint32_t *q_tf,
   P.B64 = ix->d_B64.p; P.ovf_keys = ix->d_ovf_keys.p; P.ovf_vals = ix->d_ovf_vals.p; P.n_ovf = ix->n_ovf;
   P.qw = (const double *)ix->d_qtab.p; P.qd = P.qw + H; P.qkeys = (const uint32_t *)(P.qd + H);
   P.log_h = log_h; P.table_in_smem = tab_bytes <= 40 * 1024;
-  P.nq = qp.nq; P.dotU = qp.dotU; P.corrU = qp.corrU; P.out = ix->d_scores.p;
+  P.nq = qp.nq; P.dotU = qp.dotU; P.corrU = qp.corrU; P.jaccard = ix->jaccard; P.out = ix->d_scores.p;
   int blocks = (int)std::min<int64_t>((ix->n_chunks + 7) / 8, (int64_t)ix->sm_count * 8);
   if (blocks < 1) blocks = 1;
   KV_CUDA(cudaEventRecord(ix->ev[1], s));
@@ -837,7 +880,7 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
         if (keys[h] == KEY_EMPTY) {
           keys[h] = f;
           double a, d;
-          idf_host(ix->n_total, ix->h_df[f], a, d);
+          idf_host(ix->n_total, ix->h_df[f], a, d, ix->jaccard);
           ad[2 * h] = (float)a;
           ad[2 * h + 1] = (float)d;
           cur_feats++;
@@ -919,7 +962,7 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
     P.q_nq = ix->d_qconst.p; P.q_dotU = P.q_nq + n_q; P.q_corrU = P.q_dotU + n_q;
     P.q_dotS = P.q_nq + 4 * n_q; P.q_corrS = P.q_nq + 5 * n_q;
     P.gthr = ix->d_gthr.p; P.ubuf = ix->d_ubuf.p; P.stats = ix->d_stats.p;
-    P.n_q = n_q; P.k = k; P.n_splits = (int)n_splits; P.prune = prune;
+    P.n_q = n_q; P.k = k; P.n_splits = (int)n_splits; P.prune = prune; P.jaccard = ix->jaccard;
     P.part_scores = ix->d_part_s.p; P.part_rows = ix->d_part_r.p;
     const size_t smem = Tile::smem_bytes(k);
     static bool attr_set[64] = {false};

@@ -75,12 +75,12 @@ struct IdfTables {
 
 __global__ void idf_kernel(const uint32_t *__restrict__ df, const uint32_t *__restrict__ cnt,
                            const uint32_t *__restrict__ tfmin, const uint32_t *__restrict__ tfmax, int64_t V,
-                           int64_t n_total, int64_t n_local, IdfTables T) {
+                           int64_t n_total, int64_t n_local, int jaccard, IdfTables T) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= V) return;
   double num = (double)(n_total + 2);
-  double ib = log(num / ((double)df[t] + 1.0)) + 1.0;
-  double iq = log(num / ((double)df[t] + 2.0)) + 1.0;
+  double ib = jaccard ? 1.0 : log(num / ((double)df[t] + 1.0)) + 1.0;  // Jaccard: every token weighs 1
+  double iq = jaccard ? 1.0 : log(num / ((double)df[t] + 2.0)) + 1.0;
   double a = iq * iq, bb = ib * ib;
   T.a64[t] = a; T.d64[t] = a - bb; T.bb64[t] = bb;
   bool u = n_local > 0 && (int64_t)cnt[t] == n_local && tfmin[t] == tfmax[t];
@@ -166,6 +166,7 @@ struct ScoreParams {
   int log_h;
   int table_in_smem;
   double nq, dotU, corrU;
+  int jaccard;
   double *out;  // by ORIGINAL row
 };
 
@@ -242,8 +243,14 @@ __global__ void __launch_bounds__(256) tfidf_score_kernel(ScoreParams P) {
         if ((lastmask >> j) & 1u) {
           in_core = false;
           const double dot = P.dotU + du;
-          const double den = P.nq * (P.B64[pos0 + row_in] + P.corrU + dv);
-          const double sc = (den > 0.0 && dot != 0.0) ? dot / sqrt(den) : 0.0;
+          double sc;
+          if (P.jaccard) {
+            const double den = P.nq + P.B64[pos0 + row_in] - dot;
+            sc = (den > 0.0 && dot != 0.0) ? dot / den : 0.0;
+          } else {
+            const double den = P.nq * (P.B64[pos0 + row_in] + P.corrU + dv);
+            sc = (den > 0.0 && dot != 0.0) ? dot / sqrt(den) : 0.0;
+          }
           if ((row_in & 31) == lane) mine = sc;
           row_in++;
           du = cu; dv = cv;
@@ -284,7 +291,7 @@ struct TopkParams {
   float *ubuf;                           // [n_tiles][n_chunks] chunk upper bounds (scratch)
   unsigned long long *stats;             // [0] chunks scanned, [1] chunks pruned, [2] summaries evaluated
   int64_t n_q;
-  int k, n_splits, prune;
+  int k, n_splits, prune, jaccard;
   float *part_scores;  // [n_splits][n_q][k]
   long long *part_rows;
 };
@@ -305,16 +312,38 @@ struct TileLayout {
 template <int G>
 struct Lanes {  // per-lane state of the G queries a lane owns (query g*32+lane of the tile)
   float nq[G], dotU[G], corrU[G];
-  float filt[G], fq[G];  // filter threshold (a score) and its squared-domain factor
+  float filt[G], fq[G];  // filter threshold (a score) and the factor of the division-free pre-test
   int krow[G];
   bool valid[G];
+  int jaccard;           // 0: TF-IDF cosine, 1: token-set Jaccard (warp-uniform)
 };
+
+// score of one (query, row) pair from the accumulated sums.  Cosine: dot / sqrt(|q|^2 (B + corr)).
+// Jaccard (a = 1, d = 0, B = |row|, nq = |query|): dot / (|query| + |row| - dot) -- exact small integers.
+__device__ __forceinline__ float pair_score(int jaccard, float dot, float nq, float t) {
+  if (jaccard) {
+    const float den = nq + t - dot;
+    return den > 0.f ? __fdiv_rn(dot, den) : 0.f;
+  }
+  const float den = nq * t;
+  return den > 0.f ? __fdiv_rn(dot, __fsqrt_rn(den)) : 0.f;
+}
+// upper bound from a summary (max dot, min norm): +inf when the denominator bound is not positive
+__device__ __forceinline__ float bound_score(int jaccard, float dot, float nq, float t) {
+  if (jaccard) {
+    const float den = nq + t - dot;
+    return den > 0.f ? __fdiv_rn(dot, den) : INFINITY;
+  }
+  const float den = nq * t;
+  return den > 0.f ? __fdiv_rn(dot, __fsqrt_rn(den)) : INFINITY;
+}
 
 template <int G>
 __device__ __forceinline__ void set_filter(Lanes<G> &L, int g, float ks, int kr) {
   L.filt[g] = ks;
   L.krow[g] = kr;
-  L.fq[g] = ks > 0.f ? ks * ks * L.nq[g] * FILTER_SLACK : -1.f;
+  // pre-test without division: cosine  dot^2 >= fq * (B + corr);  Jaccard  dot >= fq * (|q| + |row| - dot)
+  L.fq[g] = ks > 0.f ? (L.jaccard ? ks * FILTER_SLACK : ks * ks * L.nq[g] * FILTER_SLACK) : -1.f;
 }
 
 // Walk the entries [p0,p1) of one chunk (or of one summary pseudo-row).  For every row end the
@@ -459,6 +488,7 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   Lanes<G> L;
+  L.jaccard = P.jaccard;
 #pragma unroll
   for (int g = 0; g < G; g++) {
     int qi = g * 32 + lane;
@@ -501,10 +531,10 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
       for (int g = 0; g < G; g++) {
         if (!((gmask >> g) & 1u)) continue;
         const float t = Bc + corr[g];
-        const float lhs = dot[g] * dot[g];
-        if (L.valid[g] && lhs >= L.fq[g] * t) {
-          const float den = L.nq[g] * t;
-          const float s = (den > 0.f) ? __fdiv_rn(dot[g], __fsqrt_rn(den)) : 0.f;
+        const float lhs = L.jaccard ? dot[g] : dot[g] * dot[g];
+        const float rhs = L.fq[g] * (L.jaccard ? (L.nq[g] + t - dot[g]) : t);
+        if (L.valid[g] && lhs >= rhs) {
+          const float s = pair_score(L.jaccard, dot[g], L.nq[g], t);
           const int row = P.perm[pos0 + row_in];
           if (s > L.filt[g] || (s == L.filt[g] && row < L.krow[g])) {
             const int qi = g * 32 + lane;
@@ -577,8 +607,7 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
 #pragma unroll
         for (int g = 0; g < G; g++) {
           if (!L.valid[g]) continue;
-          const float den = L.nq[g] * (Bmin + corr[g]);
-          const float b = den > 0.f ? __fdiv_rn(dot[g], __fsqrt_rn(den)) : INFINITY;
+          const float b = bound_score(L.jaccard, dot[g], L.nq[g], Bmin + corr[g]);
           best = fmaxf(best, b);
         }
         for (int o = 16; o; o >>= 1) best = fmaxf(best, __shfl_xor_sync(FULL, best, o));
@@ -647,8 +676,7 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
 #pragma unroll
             for (int g = 0; g < G; g++) {
               if (!L.valid[g]) continue;
-              const float den = L.nq[g] * (Bmin + corr[g]);
-              const float b2 = den > 0.f ? __fdiv_rn(dot[g], __fsqrt_rn(den)) : INFINITY;
+              const float b2 = bound_score(L.jaccard, dot[g], L.nq[g], Bmin + corr[g]);
               if (b2 * PRUNE_SLACK >= L.filt[g]) may |= 1u << g;
             }
           });

@@ -409,3 +409,36 @@ def test_dense_cosine_topk(lib, n, d, q):
     assert np.allclose(s[:min(q, 50), 0], 1.0, atol=1e-5)
     if n > 1000:
         assert r[min(q, 50), :2].tolist() == [1000, 1001]
+
+
+def test_jaccard_token_sets(lib):
+    """K3 (parity unpinned: no Jaccard in the reference).  Bit-exact: the device ranks by inter/union, the exact
+    integers come back, and float64 inter/union equals Python's set arithmetic."""
+    from kakveda_b200 import JaccardIndex
+
+    rng = np.random.default_rng(5)
+    V, n, q, k = 1 << 14, 6000, 160, 16
+    zipf = lambda size: np.minimum(rng.zipf(1.3, size) - 1, V - 1).astype(np.uint32)
+    rows = [np.unique(zipf(max(1, rng.poisson(40)))) for _ in range(n)]
+    rows[5] = np.zeros(0, dtype=np.uint32)                 # empty set
+    rows[100] = rows[99].copy()                            # duplicate rows tie -> lower row first
+    queries = [np.unique(zipf(max(1, rng.poisson(40)))) for _ in range(q)]
+    queries[0] = rows[99].copy()
+    queries[1] = np.zeros(0, dtype=np.uint32)              # empty query: every score 0
+    queries[2] = np.concatenate([rows[7], np.array([V + 5, V + 9], dtype=np.uint32)])  # ids outside the vocabulary
+    jx = JaccardIndex(V)
+    jx.add_sets(rows[: n // 2])
+    jx.add_sets(rows[n // 2:])
+    jx.finalize()
+    s, r, inter, union = jx.topk_sets(queries, k)
+    for i, qs in enumerate(queries):
+        want = np.array([(lambda iu: iu[0] / iu[1] if iu[1] else 0.0)(O.jaccard_sets(qs.tolist(), c.tolist())) for c in rows])
+        order, vals = O.topk_stable(want.tolist(), k)
+        got64 = np.where(union[i] > 0, inter[i] / np.maximum(union[i], 1), 0.0)
+        assert got64.tolist() == vals, (i, got64, vals)               # bit-exact float64 ratios
+        assert r[i].tolist() == order, (i, r[i], order)               # same rows, ties -> lower row
+        for j in range(k):
+            assert (int(inter[i, j]), int(union[i, j])) == O.jaccard_sets(qs.tolist(), rows[int(r[i, j])].tolist())
+        np.testing.assert_allclose(s[i], vals, rtol=1e-6, atol=1e-7)
+    assert r[0, 0] == 99 and r[0, 1] == 100 and inter[0, 0] == union[0, 0]
+    assert r[1].tolist() == list(range(k))
