@@ -100,6 +100,12 @@ int kv_index_append(kv_index *ix, const int64_t *indptr, const uint32_t *ids, co
  * selected pairs so that the caller can form the float64 ratio bit-exactly. */
 #define KV_MODE_TFIDF_COSINE 0
 #define KV_MODE_JACCARD 1
+/* TF-IDF cosine with the vectoriser fitted on the corpus ALONE (idf = ln((1+N)/(1+df))+1 for both sides; query
+ * features outside the vocabulary are ignored) -- sklearn's usual fit(corpus)/transform(query).  Symmetric, so it
+ * is the measure of the all-pairs self-join that feeds pattern clustering (BASELINE configs[3]; the reference's
+ * pattern_detector groups by failure_type only, services/pattern_detector/app.py:28-60 -- extension, oracle =
+ * cosine_similarity(TfidfVectorizer(ngram_range=(1,2)).fit_transform(corpus))). */
+#define KV_MODE_TFIDF_CORPUS_FIT 2
 int kv_index_set_mode(kv_index *ix, int mode);
 int kv_jaccard_counts(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const double *q_oov_tf2,
                       int64_t n_q, int k, const int64_t *rows, int32_t *out_inter, int32_t *out_union);
@@ -113,6 +119,11 @@ int kv_index_set_global_df(kv_index *ix, const uint32_t *df, int64_t vocab_size,
 int kv_index_local_df(kv_index *ix, uint32_t *df_out, int64_t vocab_size);
 
 int kv_index_finalize(kv_index *ix, int64_t vocab_size);
+/* What the last finalize did: 1 = full rebuild (text sort of the rows, scan stream, chunk summaries), 2 =
+ * statistics-only refresh (the rows of THIS index are unchanged since its last full rebuild and only the global N /
+ * df moved -- rows were appended to another shard or to the tail segment of a resident GFKB: idf tables, row norms
+ * and chunk minima are recomputed on the device, nothing is re-sorted), 0 = never finalized. */
+int kv_index_last_finalize_kind(const kv_index *ix);
 
 int64_t kv_index_rows(const kv_index *ix);
 
@@ -143,6 +154,24 @@ int kv_topk_device(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids,
 int kv_query_upload(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
                     const double *q_oov_tf2, int64_t n_q);
 int kv_topk_resident(kv_index *ix, int k, void *d_scores, void *d_rows);
+/* Same with host outputs (out_scores float32[n_q*k], out_rows int64[n_q*k]). */
+int kv_topk_resident_host(kv_index *ix, int k, float *out_scores, int64_t *out_rows);
+/* Self-join support: after kv_query_upload, query q never matches GLOBAL row exclude_rows[q] (-1: none; rows of
+ * other shards are ignored).  Used when the queries ARE stored rows (all-pairs clustering: every row's k nearest
+ * OTHER rows).  NULL clears; the next kv_query_upload clears too. */
+int kv_query_set_exclusions(kv_index *ix, const int64_t *exclude_rows, int64_t n_q);
+/* All-pairs on one index without re-featurising: local rows [q_begin, q_end) become the resident query batch, each
+ * excluding itself (follow with kv_topk_resident / kv_topk_resident_host). */
+int kv_selfjoin_upload(kv_index *ix, int64_t q_begin, int64_t q_end);
+
+/* K6: float64 scores of selected (query, row) pairs: rows[n_q*k] are GLOBAL row ids (e.g. what kv_topk returned;
+ * -1 = unused slot), out_scores[n_q*k] (host) receives the float64 cosine of SimilarityEngine.score
+ * (similarity.py:14-20) for that row, -inf for unused slots and rows that live on another shard.  Summation follows
+ * the row's stored feature order with nothing folded, so rows with identical text get identical bits on every shard /
+ * segment and services/gfkb/app.py:89's stable sort is reproduced (ties -> lower row).  The batched match path ranks
+ * candidates in float32 (K1b) and re-scores the survivors here. */
+int kv_rescore_pairs(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
+                     const double *q_oov_tf2, int64_t n_q, int k, const int64_t *rows, double *out_scores);
 
 /* K5: merge n_lists partial top-k lists per query (device pointers; list l of query q at
  * [l*n_q*k + q*k], each sorted by (score desc,row asc)) into one [n_q*k] result with the
@@ -173,7 +202,7 @@ int kv_index_layout(const kv_index *ix, int64_t bytes[4], int64_t counts[17]);
  * top-k fused into a tcgen05 GEMM epilogue.  The reference has no embedding path (its docs list
  * embeddings as a possible extension, docs/failure-intelligence.md:43-46): parity UNPINNED, oracle =
  * float64 cosine of the same bf16 inputs.  Inputs are bfloat16 bit patterns (uint16), row-major.
- * kv_dense_topk: per query the k (<=16) best rows by (cosine desc, row asc); host outputs
+ * kv_dense_topk: per query the k (<=32) best rows by (cosine desc, row asc); host outputs
  * float32[n_q*k] / int64[n_q*k]; unused slots (-inf, -1).
  * ---------------------------------------------------------------------------------- */
 typedef struct kv_dense_index kv_dense_index;
@@ -183,6 +212,17 @@ int kv_dense_append(kv_dense_index *dx, const uint16_t *rows_bf16, int64_t n);
 int kv_dense_finalize(kv_dense_index *dx);
 int64_t kv_dense_rows(const kv_dense_index *dx);
 int kv_dense_topk(kv_dense_index *dx, const uint16_t *q_bf16, int64_t n_q, int k, float *out_scores, int64_t *out_rows);
+/* Device-side variants (pointers are device memory owned by the caller, e.g. torch tensors; bf16 data 16-byte
+ * aligned): append rows that are already in HBM; scan with queries and results on the device -- what a rank of
+ * a row-sharded GFKB calls before the NCCL all-gather of partial top-k (BASELINE configs[2]).  exclude_base >= 0:
+ * query q must not match GLOBAL row exclude_base + q (the all-pairs self-join of BASELINE configs[3], where the
+ * queries are the stored rows themselves); -1: no exclusion. */
+int kv_dense_append_device(kv_dense_index *dx, const void *d_rows_bf16, int64_t n);
+int kv_dense_topk_device(kv_dense_index *dx, const void *d_q_bf16, int64_t n_q, int k, int64_t exclude_base,
+                         void *d_scores, void *d_rows);
+/* All-pairs on one shard without copying: local rows [q_begin, q_end) are the queries, each row's own entry is
+ * excluded, results (device) as above. */
+int kv_dense_selfjoin_device(kv_dense_index *dx, int64_t q_begin, int64_t q_end, int k, void *d_scores, void *d_rows);
 /* CUDA-event milliseconds of the GEMM+top-k kernel of the last kv_dense_topk and its row splits. */
 int kv_dense_last_timing(const kv_dense_index *dx, float *gemm_ms, int64_t *splits);
 
@@ -203,6 +243,16 @@ int kv_hash_match(kv_hash_index *hx, const uint64_t *q_hashes, int64_t n_q, int 
 /* CUDA-event milliseconds of the scan kernel launches of the last kv_hash_match, and their number
  * (one pass over all rows per 4096 queries). */
 int kv_hash_last_timing(const kv_hash_index *hx, float *scan_ms, int *passes);
+
+/* ------------------------------------------------------------------------------------
+ * Pattern clustering on top of an all-pairs top-k (BASELINE configs[3]): rows[n*k] / scores[n*k] are every row's k
+ * nearest OTHER rows (kv_selfjoin_upload + kv_topk_resident_host, or kv_dense_selfjoin_device); rows i and j are
+ * linked when either lists the other with score >= threshold; labels[i] = smallest row id of i's connected
+ * component, *n_clusters = number of components.  Host code (union-find).  Extension of
+ * services/pattern_detector/app.py:39-41, which groups by failure_type equality only.
+ * ---------------------------------------------------------------------------------- */
+int kv_cluster_topk(int64_t n, int k, const int64_t *rows, const float *scores, float threshold, int64_t *labels,
+                    int64_t *n_clusters);
 
 /* ------------------------------------------------------------------------------------
  * Synthetic failures.jsonl-shaped signature_text generator (test / bench support; the

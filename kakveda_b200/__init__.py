@@ -10,9 +10,11 @@ from .denseindex import DenseIndex
 from .hashindex import HashIndex
 from .jaccardindex import JaccardIndex
 from .similarity import FeatureBatch, GfkbIndex, SimilarityEngine, Vocabulary
+from .store import GfkbStore
+from . import patterns
 
 __all__ = [
     "SimilarityEngine", "GfkbIndex", "Vocabulary", "FeatureBatch", "HashIndex", "DenseIndex", "JaccardIndex",
-    "signature_text", "fingerprint_text", "fingerprint_u64", "normalize_prompt",
+    "GfkbStore", "patterns", "signature_text", "fingerprint_text", "fingerprint_u64", "normalize_prompt",
 ]
 __version__ = "0.1.0"

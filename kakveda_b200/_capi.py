@@ -43,6 +43,7 @@ SIGNATURES = {
     "kv_index_set_global_df": (C.c_int, [C.c_void_p, c_u32p, C.c_int64, C.c_int64]),
     "kv_index_local_df": (C.c_int, [C.c_void_p, c_u32p, C.c_int64]),
     "kv_index_finalize": (C.c_int, [C.c_void_p, C.c_int64]),
+    "kv_index_last_finalize_kind": (C.c_int, [C.c_void_p]),
     "kv_index_rows": (C.c_int64, [C.c_void_p]),
     "kv_score": (C.c_int, [C.c_void_p, c_u32p, c_u32p, C.c_int64, C.c_double, c_f64p]),
     "kv_topk": (C.c_int, [C.c_void_p, c_i64p, c_u32p, c_u32p, c_f64p, C.c_int64, C.c_int, c_f32p, c_i64p]),
@@ -50,6 +51,11 @@ SIGNATURES = {
                                  C.c_void_p]),
     "kv_query_upload": (C.c_int, [C.c_void_p, c_i64p, c_u32p, c_u32p, c_f64p, C.c_int64]),
     "kv_topk_resident": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "kv_topk_resident_host": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_i64p]),
+    "kv_query_set_exclusions": (C.c_int, [C.c_void_p, c_i64p, C.c_int64]),
+    "kv_selfjoin_upload": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
+    "kv_rescore_pairs": (C.c_int, [C.c_void_p, c_i64p, c_u32p, c_u32p, c_f64p, C.c_int64, C.c_int, c_i64p, c_f64p]),
+    "kv_cluster_topk": (C.c_int, [C.c_int64, C.c_int, c_i64p, c_f32p, C.c_float, c_i64p, c_i64p]),
     "kv_merge_topk_device": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
                                        C.c_void_p]),
     "kv_index_last_timing": (C.c_int, [C.c_void_p, c_f32p]),
@@ -61,6 +67,9 @@ SIGNATURES = {
     "kv_dense_finalize": (C.c_int, [C.c_void_p]),
     "kv_dense_rows": (C.c_int64, [C.c_void_p]),
     "kv_dense_topk": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint16), C.c_int64, C.c_int, c_f32p, c_i64p]),
+    "kv_dense_append_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "kv_dense_topk_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "kv_dense_selfjoin_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "kv_dense_last_timing": (C.c_int, [C.c_void_p, c_f32p, c_i64p]),
     "kv_hash_create": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
     "kv_hash_destroy": (None, [C.c_void_p]),

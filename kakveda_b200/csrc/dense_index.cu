@@ -38,7 +38,7 @@ constexpr int STAGES = 3;       // 3 x 48 KiB ring + two list sets fit in 227 Ki
 constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int MAXK = 16;       // per-query list slots that fit beside the 4-stage ring (k <= 16)
+constexpr int MAXK = 32;       // per-query list slots: 2 x 32 x 128 x 8 B = 64 KiB beside the 3 x 48 KiB ring (k <= 32)
 constexpr int N_THREADS = 320;  // 10 warps: TMA, MMA, 8 epilogue
 constexpr int EPI_THREADS = 256;
 
@@ -105,6 +105,7 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 
 struct DenseParams {
   int64_t n_rows, row_base, n_q;
+  int64_t excl_base;        // self-join: query q must not match global row excl_base + q (-1: no exclusion)
   int64_t r_tiles, q_tiles;  // 256-row tiles, 128-query tiles
   int dim, k, n_lists, dbg;
   const float *inv_norm_c;  // [n_rows]
@@ -213,6 +214,7 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     float *ls = &S.lscore[half][0][qi];         // element j of this thread's list lives at ls[j * BM]
     int *lr = &S.lrow[half][0][qi];
     int cur_qtile = -1, cnt = 0;
+    int excl = -1;          // local row this thread's query must not match (self-join)
     int64_t q = 0;
     bool q_ok = false;
     float inv_q = 0.f;
@@ -239,6 +241,10 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         q = (int64_t)qtile * BM + qi;
         q_ok = q < P.n_q;
         inv_q = q_ok ? P.inv_norm_q[q] : 0.f;
+        {
+          const int64_t e = P.excl_base >= 0 ? P.excl_base + q - P.row_base : -1;
+          excl = (e >= 0 && e < P.n_rows) ? (int)e : -1;
+        }
         cnt = 0;
         thr = gth = gth_pred = -INFINITY;
         lo = q_ok ? -INFINITY : INFINITY;
@@ -298,7 +304,7 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll  // static indices keep tv[] in registers
             for (int j = 8 * sb; j < 8 * sb + 8; j++) {
               const float sc = tv[j] * inv_q;
-              if (sc > lo) {
+              if (sc > lo && (int)(row0 + c0 + j) != excl) {
                 int pos = cnt < k ? cnt++ : k - 1;
                 while (pos > 0 && ls[(pos - 1) * BM] < sc) {
                   ls[pos * BM] = ls[(pos - 1) * BM];
@@ -455,25 +461,22 @@ int kv_dense_finalize(kv_dense_index *dx) {
   return KV_OK;
 }
 
-// q: n_q x dim bfloat16 bit patterns (host).  Outputs (host): scores float32[n_q*k], rows int64[n_q*k],
-// ordered by (score desc, row asc); unused slots (-inf, -1).
-int kv_dense_topk(kv_dense_index *dx, const uint16_t *q_bf16, int64_t n_q, int k, float *out_scores, int64_t *out_rows) {
-  if (!dx || n_q < 0 || k < 1 || k > MAXK || (n_q > 0 && (!q_bf16 || !out_scores || !out_rows)))
-    return kv_fail(KV_ERR_INVALID, "kv_dense_topk: bad arguments (k must be 1..16)");
-  std::lock_guard<std::mutex> g(dx->mu);
-  if (!dx->finalized) return kv_fail(KV_ERR_STATE, "kv_dense_topk: index not finalized");
-  if (n_q == 0) return KV_OK;
-  KV_CUDA(cudaSetDevice(dx->device));
+// scan + merge of n_q queries already on the device (d_q: bf16 [n_q, dim], 16-byte aligned) into device buffers
+static int dense_run(kv_dense_index *dx, const __nv_bfloat16 *d_q, int64_t n_q, int k, int64_t excl_base, float *d_out_s,
+                     long long *d_out_r) {
   cudaStream_t s = dx->stream;
-  for (int64_t i = 0; i < n_q * k; i++) { out_scores[i] = -INFINITY; out_rows[i] = -1; }
-  if (dx->n_rows == 0) return KV_OK;
-  KV_CUDA(dx->d_q.ensure(n_q * dx->dim));
+  if (dx->n_rows == 0) {
+    KV_CUDA(cudaMemsetAsync(d_out_r, 0xFF, (size_t)n_q * k * 8, s));  // row -1
+    std::vector<float> neg((size_t)(n_q * k), -INFINITY);
+    KV_CUDA(cudaMemcpyAsync(d_out_s, neg.data(), neg.size() * 4, cudaMemcpyHostToDevice, s));
+    KV_CUDA(cudaStreamSynchronize(s));
+    return KV_OK;
+  }
   KV_CUDA(dx->d_inv_q.ensure(n_q));
-  KV_CUDA(cudaMemcpyAsync(dx->d_q.p, q_bf16, (size_t)n_q * dx->dim * 2, cudaMemcpyHostToDevice, s));
-  inv_norm_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, s>>>(dx->d_q.p, n_q, dx->dim, dx->d_inv_q.p);
+  inv_norm_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, s>>>(d_q, n_q, dx->dim, dx->d_inv_q.p);
   KV_CUDA(cudaGetLastError());
   CUtensorMap map_q, map_c;
-  int rc = make_map(&map_q, dx->d_q.p, n_q, dx->dim, BM);
+  int rc = make_map(&map_q, d_q, n_q, dx->dim, BM);
   if (rc != KV_OK) return rc;
   rc = make_map(&map_c, dx->rows.p, dx->n_rows, dx->dim, BN);
   if (rc != KV_OK) return rc;
@@ -494,7 +497,6 @@ int kv_dense_topk(kv_dense_index *dx, const uint16_t *q_bf16, int64_t n_q, int k
   dx->last_splits = n_lists;
   const int64_t n_part = n_lists * 2;  // two epilogue threads (column halves) per query and CTA
   KV_CUDA(dx->d_part_s.ensure(n_part * n_q * k)); KV_CUDA(dx->d_part_r.ensure(n_part * n_q * k));
-  KV_CUDA(dx->d_out_s.ensure(n_q * k)); KV_CUDA(dx->d_out_r.ensure(n_q * k));
   KV_CUDA(dx->d_gthr.ensure(n_q));
   KV_CUDA(cudaMemsetAsync(dx->d_gthr.p, 0, (size_t)n_q * 4, s));
   // unused (query tile, slot) pairs stay "empty": row -1 (the merge ignores their scores)
@@ -502,6 +504,7 @@ int kv_dense_topk(kv_dense_index *dx, const uint16_t *q_bf16, int64_t n_q, int k
   KV_CUDA(cudaMemsetAsync(dx->d_part_s.p, 0xFF, (size_t)n_part * n_q * k * 4, s));
   DenseParams P;
   P.n_rows = dx->n_rows; P.row_base = dx->row_base; P.n_q = n_q; P.dim = dx->dim; P.k = k; P.n_lists = (int)n_lists;
+  P.excl_base = excl_base;
   P.r_tiles = r_tiles; P.q_tiles = q_tiles;
   P.dbg = getenv("KAKVEDA_B200_DENSE_DBG") ? atoi(getenv("KAKVEDA_B200_DENSE_DBG")) : 0;
   P.inv_norm_c = dx->d_inv_c.p; P.inv_norm_q = dx->d_inv_q.p; P.gthr = dx->d_gthr.p;
@@ -513,11 +516,69 @@ int kv_dense_topk(kv_dense_index *dx, const uint16_t *q_bf16, int64_t n_q, int k
   KV_CUDA(cudaEventRecord(dx->ev[1], s));
   KV_CUDA(cudaStreamSynchronize(s));
   cudaEventElapsedTime(&dx->last_ms, dx->ev[0], dx->ev[1]);
-  rc = kv_merge_topk_device(dx->device, dx->d_part_s.p, dx->d_part_r.p, (int)n_part, n_q, k, dx->d_out_s.p, dx->d_out_r.p);
+  return kv_merge_topk_device(dx->device, dx->d_part_s.p, dx->d_part_r.p, (int)n_part, n_q, k, d_out_s, d_out_r);
+}
+
+// q: n_q x dim bfloat16 bit patterns (host).  Outputs (host): scores float32[n_q*k], rows int64[n_q*k],
+// ordered by (score desc, row asc); unused slots (-inf, -1).
+int kv_dense_topk(kv_dense_index *dx, const uint16_t *q_bf16, int64_t n_q, int k, float *out_scores, int64_t *out_rows) {
+  if (!dx || n_q < 0 || k < 1 || k > MAXK || (n_q > 0 && (!q_bf16 || !out_scores || !out_rows)))
+    return kv_fail(KV_ERR_INVALID, "kv_dense_topk: bad arguments (k must be 1..32)");
+  std::lock_guard<std::mutex> g(dx->mu);
+  if (!dx->finalized) return kv_fail(KV_ERR_STATE, "kv_dense_topk: index not finalized");
+  if (n_q == 0) return KV_OK;
+  KV_CUDA(cudaSetDevice(dx->device));
+  cudaStream_t s = dx->stream;
+  KV_CUDA(dx->d_q.ensure(n_q * dx->dim));
+  KV_CUDA(cudaMemcpyAsync(dx->d_q.p, q_bf16, (size_t)n_q * dx->dim * 2, cudaMemcpyHostToDevice, s));
+  KV_CUDA(dx->d_out_s.ensure(n_q * k)); KV_CUDA(dx->d_out_r.ensure(n_q * k));
+  int rc = dense_run(dx, dx->d_q.p, n_q, k, -1, dx->d_out_s.p, dx->d_out_r.p);
   if (rc != KV_OK) return rc;
   KV_CUDA(cudaMemcpy(out_scores, dx->d_out_s.p, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost));
   KV_CUDA(cudaMemcpy(out_rows, dx->d_out_r.p, (size_t)n_q * k * 8, cudaMemcpyDeviceToHost));
   return KV_OK;
+}
+
+int kv_dense_topk_device(kv_dense_index *dx, const void *d_q_bf16, int64_t n_q, int k, int64_t exclude_base, void *d_scores,
+                         void *d_rows) {
+  if (!dx || n_q < 0 || k < 1 || k > MAXK || (n_q > 0 && (!d_q_bf16 || !d_scores || !d_rows)))
+    return kv_fail(KV_ERR_INVALID, "kv_dense_topk_device: bad arguments (k must be 1..32)");
+  if (((uintptr_t)d_q_bf16 & 15) != 0) return kv_fail(KV_ERR_INVALID, "kv_dense_topk_device: queries must be 16-byte aligned");
+  std::lock_guard<std::mutex> g(dx->mu);
+  if (!dx->finalized) return kv_fail(KV_ERR_STATE, "kv_dense_topk_device: index not finalized");
+  if (n_q == 0) return KV_OK;
+  KV_CUDA(cudaSetDevice(dx->device));
+  return dense_run(dx, (const __nv_bfloat16 *)d_q_bf16, n_q, k, exclude_base, (float *)d_scores, (long long *)d_rows);
+}
+
+// rows already on the device (e.g. a torch tensor): device-to-device append
+int kv_dense_append_device(kv_dense_index *dx, const void *d_rows_bf16, int64_t n) {
+  if (!dx || n < 0 || (n > 0 && !d_rows_bf16)) return kv_fail(KV_ERR_INVALID, "kv_dense_append_device: bad arguments");
+  if (n == 0) return KV_OK;
+  std::lock_guard<std::mutex> g(dx->mu);
+  KV_CUDA(cudaSetDevice(dx->device));
+  if (dx->n_rows + n >= (1LL << 31) - BN) return kv_fail(KV_ERR_INVALID, "kv_dense_append_device: more than 2^31 rows in one shard");
+  KV_CUDA(dx->rows.reserve((dx->n_rows + n) * dx->dim, dx->stream));
+  KV_CUDA(cudaMemcpyAsync(dx->rows.p + dx->n_rows * dx->dim, d_rows_bf16, (size_t)n * dx->dim * 2, cudaMemcpyDeviceToDevice, dx->stream));
+  KV_CUDA(cudaStreamSynchronize(dx->stream));
+  dx->n_rows += n;
+  dx->rows.n = dx->n_rows * dx->dim;
+  dx->finalized = false;
+  return KV_OK;
+}
+
+// all-pairs (BASELINE configs[3]): local rows [q_begin, q_end) as queries against the whole shard, each row's own
+// entry excluded; outputs on the device
+int kv_dense_selfjoin_device(kv_dense_index *dx, int64_t q_begin, int64_t q_end, int k, void *d_scores, void *d_rows) {
+  if (!dx || q_begin < 0 || q_end < q_begin || k < 1 || k > MAXK || !d_scores || !d_rows)
+    return kv_fail(KV_ERR_INVALID, "kv_dense_selfjoin_device: bad arguments (k must be 1..32)");
+  std::lock_guard<std::mutex> g(dx->mu);
+  if (!dx->finalized) return kv_fail(KV_ERR_STATE, "kv_dense_selfjoin_device: index not finalized");
+  if (q_end > dx->n_rows) return kv_fail(KV_ERR_INVALID, "kv_dense_selfjoin_device: row range outside the index");
+  if (q_end == q_begin) return KV_OK;
+  KV_CUDA(cudaSetDevice(dx->device));
+  return dense_run(dx, dx->rows.p + q_begin * dx->dim, q_end - q_begin, k, dx->row_base + q_begin, (float *)d_scores,
+                   (long long *)d_rows);
 }
 
 int kv_dense_last_timing(const kv_dense_index *dx, float *gemm_ms, int64_t *splits) {

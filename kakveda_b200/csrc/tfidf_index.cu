@@ -67,12 +67,23 @@ struct kv_index {
 
   bool finalized = false;
   int jaccard = 0;  // 0: TF-IDF cosine (the reference's measure), 1: token-set Jaccard (K3)
+  int corpus_fit = 0;  // 1: TF-IDF fitted on the corpus only (self-join / pattern clustering); the query is just transformed
   int64_t V = 0, n_total = 0;
   DevBuf<uint32_t> d_df, d_cnt, d_tfmin, d_tfmax, d_utf;
   DevBuf<double> d_a64, d_d64, d_bb64, d_B64;
   DevBuf<float> d_B32, d_cminB;
   DevBuf<uint8_t> d_univ;
-  DevBuf<int> d_perm;
+  DevBuf<int> d_perm, d_invperm;
+  // scan layout currently on the device (perm, stream, summaries): which rows / universal set it was built for
+  bool layout_valid = false;
+  int64_t layout_rows = -1;
+  std::vector<uint8_t> layout_univ;
+  int last_finalize_kind = 0;  // 1: full rebuild, 2: statistics-only refresh
+  // K6 scratch
+  DevBuf<int64_t> d_rq_indptr;
+  DevBuf<uint32_t> d_rq_ids, d_rq_tf;
+  DevBuf<double> d_rq_const, d_rq_out;
+  DevBuf<long long> d_rq_rows;
   DevBuf<int64_t> d_chunkptr, d_sumptr, d_grpptr;
   DevBuf<uint32_t> d_stream, d_sum_stream, d_grp_stream;
   DevBuf<unsigned long long> d_ovf_keys;
@@ -95,6 +106,9 @@ struct kv_index {
   DevBuf<float> d_qconst;
   DevBuf<int> d_qperm;
   DevBuf<int> d_gthr;
+  DevBuf<int> d_excl_sorted, d_excl_orig;  // self-join exclusions of the resident batch (by sorted slot / by original query)
+  std::vector<int> h_excl_orig;
+  bool has_excl = false;
   DevBuf<float> d_ubuf;
   DevBuf<unsigned long long> d_stats;
   DevBuf<float> d_part_s, d_out_s;
@@ -127,11 +141,11 @@ struct QueryPrep {
   std::vector<uint32_t> tfq;
 };
 
-inline void idf_host(int64_t n_total, uint32_t df, double &a, double &d, int jaccard = 0) {
+inline void idf_host(int64_t n_total, uint32_t df, double &a, double &d, int jaccard, int corpus_fit) {
   if (jaccard) { a = 1.0; d = 0.0; return; }
-  double num = (double)(n_total + 2);
+  double num = (double)(n_total + (corpus_fit ? 1 : 2));
   double ib = std::log(num / ((double)df + 1.0)) + 1.0;
-  double iq = std::log(num / ((double)df + 2.0)) + 1.0;
+  double iq = corpus_fit ? ib : std::log(num / ((double)df + 2.0)) + 1.0;
   a = iq * iq;
   d = a - ib * ib;
 }
@@ -141,7 +155,8 @@ void prep_query(const kv_index *ix, const uint32_t *ids, const uint32_t *tf, int
   out.dotU = out.corrU = out.dotS = out.corrS = 0;
   out.fid.clear();
   out.tfq.clear();
-  double idf0 = ix->jaccard ? 1.0 : std::log((double)(ix->n_total + 2) / 2.0) + 1.0;  // df == 0 features of the query
+  // df == 0 features of the query: the refit gives them idf ln((N+2)/2)+1; a corpus-only fit does not know them at all
+  double idf0 = ix->jaccard ? 1.0 : (ix->corpus_fit ? 0.0 : std::log((double)(ix->n_total + 2) / 2.0) + 1.0);
   out.nq = oov_tf2 * idf0 * idf0;
   for (int64_t i = 0; i < nnz; i++) {
     uint32_t t = ids[i];
@@ -151,7 +166,7 @@ void prep_query(const kv_index *ix, const uint32_t *ids, const uint32_t *tf, int
       continue;
     }
     double a, d;
-    idf_host(ix->n_total, ix->h_df[t], a, d, ix->jaccard);
+    idf_host(ix->n_total, ix->h_df[t], a, d, ix->jaccard, ix->corpus_fit);
     out.nq += f * f * a;
     if (ix->h_univ[t]) {
       double u = (double)ix->h_utf[t];
@@ -258,6 +273,9 @@ void kv_index_destroy(kv_index *ix) {
   ix->d_ovf_keys.release(); ix->d_ovf_vals.release();
   ix->h_tables.release(); ix->h_tiles.release(); ix->h_qconst.release(); ix->h_qperm.release();
   ix->d_tables.release(); ix->d_tiles.release(); ix->d_qconst.release(); ix->d_qperm.release(); ix->d_gthr.release();
+  ix->d_excl_sorted.release(); ix->d_excl_orig.release(); ix->d_invperm.release();
+  ix->d_rq_indptr.release(); ix->d_rq_ids.release(); ix->d_rq_tf.release(); ix->d_rq_const.release(); ix->d_rq_out.release();
+  ix->d_rq_rows.release();
   ix->d_ubuf.release(); ix->d_stats.release();
   ix->d_part_s.release(); ix->d_out_s.release(); ix->d_part_r.release(); ix->d_out_r.release();
   ix->h_out_s.release(); ix->h_out_r.release();
@@ -315,14 +333,16 @@ int kv_index_append(kv_index *ix, const int64_t *indptr, const uint32_t *ids, co
 }
 
 int kv_index_set_mode(kv_index *ix, int mode) {
-  if (!ix || (mode != KV_MODE_TFIDF_COSINE && mode != KV_MODE_JACCARD))
-    return kv_fail(KV_ERR_INVALID, "kv_index_set_mode: mode must be KV_MODE_TFIDF_COSINE or KV_MODE_JACCARD");
+  if (!ix || (mode != KV_MODE_TFIDF_COSINE && mode != KV_MODE_JACCARD && mode != KV_MODE_TFIDF_CORPUS_FIT))
+    return kv_fail(KV_ERR_INVALID, "kv_index_set_mode: mode must be KV_MODE_TFIDF_COSINE, KV_MODE_JACCARD or KV_MODE_TFIDF_CORPUS_FIT");
   std::lock_guard<std::mutex> g(ix->mu);
   if (mode == KV_MODE_JACCARD)
     for (uint16_t f : ix->h_tf)
       if (f != 1) return kv_fail(KV_ERR_INVALID, "kv_index_set_mode: Jaccard rows are token SETS (every tf must be 1)");
-  ix->jaccard = mode;
+  ix->jaccard = mode == KV_MODE_JACCARD;
+  ix->corpus_fit = mode == KV_MODE_TFIDF_CORPUS_FIT;
   ix->finalized = false;
+  ix->layout_valid = false;
   return KV_OK;
 }
 
@@ -384,6 +404,20 @@ int kv_index_local_df(kv_index *ix, uint32_t *df_out, int64_t vocab_size) {
   return KV_OK;
 }
 
+// a(t), d(t) as the HOST computes them (idf_host: the values every query table is built from) -> d_a64/d_d64, so
+// that K6 multiplies the very same doubles as K1a
+static int upload_idf_tables(kv_index *ix, int64_t V) {
+  if (V <= 0) return KV_OK;
+  std::vector<double> ha((size_t)V), hd((size_t)V);
+  parallel_for(V, V >= 65536 ? host_threads() : 1, [&](int, int64_t a0, int64_t a1) {
+    for (int64_t t = a0; t < a1; t++) idf_host(ix->n_total, ix->h_df[(size_t)t], ha[(size_t)t], hd[(size_t)t], ix->jaccard, ix->corpus_fit);
+  });
+  KV_CUDA(cudaMemcpyAsync(ix->d_a64.p, ha.data(), (size_t)V * 8, cudaMemcpyHostToDevice, ix->stream));
+  KV_CUDA(cudaMemcpyAsync(ix->d_d64.p, hd.data(), (size_t)V * 8, cudaMemcpyHostToDevice, ix->stream));
+  KV_CUDA(cudaStreamSynchronize(ix->stream));
+  return KV_OK;
+}
+
 int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
   if (!ix || vocab_size < 0) return kv_fail(KV_ERR_INVALID, "kv_index_finalize: bad arguments");
   std::lock_guard<std::mutex> g(ix->mu);
@@ -425,7 +459,7 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
   if (V) {
     IdfTables T{ix->d_a64.p, ix->d_d64.p, ix->d_bb64.p, ix->d_univ.p, ix->d_utf.p};
     idf_kernel<<<(unsigned)((V + 255) / 256), 256, 0, s>>>(ix->d_df.p, ix->d_cnt.p, ix->d_tfmin.p, ix->d_tfmax.p, V,
-                                                            ix->n_total, n, ix->jaccard, T);
+                                                            ix->n_total, n, ix->jaccard, ix->corpus_fit, T);
     KV_CUDA(cudaGetLastError());
   }
   ix->h_df.assign((size_t)V, 0);
@@ -451,6 +485,33 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
   KV_CUDA(cudaStreamSynchronize(s));
   ix->n_univ = 0;
   for (uint8_t u : ix->h_univ) ix->n_univ += u;
+  {
+    int rc = upload_idf_tables(ix, V);
+    if (rc != KV_OK) return rc;
+  }
+  // ---- statistics-only refresh: the rows (hence text order, stream, chunk summaries) are the ones the device layout
+  // was built from and the set of folded universal features is unchanged; only N / df moved (rows were appended to
+  // ANOTHER shard or segment of the same GFKB).  Row norms and chunk minima are recomputed, nothing is re-sorted.
+  if (ix->layout_valid && ix->layout_rows == n && n > 0 && !getenv("KAKVEDA_B200_FULL_FINALIZE")) {
+    bool same = (int64_t)ix->layout_univ.size() <= V;
+    for (size_t t = 0; same && t < ix->layout_univ.size(); t++) same = ix->layout_univ[t] == ix->h_univ[t];
+    for (size_t t = ix->layout_univ.size(); same && t < (size_t)V; t++) same = ix->h_univ[t] == 0;
+    if (same) {
+      rownorm_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(ix->indptr.p, ix->ids.p, ix->tf.p, ix->d_perm.p, n,
+                                                                      ix->d_bb64.p, ix->d_univ.p, ix->d_B64.p,
+                                                                      ix->d_B32.p, nullptr);
+      KV_CUDA(cudaGetLastError());
+      chunk_meta_kernel<<<(unsigned)((ix->n_chunks + 255) / 256), 256, 0, s>>>(ix->d_B32.p, n, ix->n_chunks, ix->d_cminB.p);
+      KV_CUDA(cudaGetLastError());
+      KV_CUDA(cudaStreamSynchronize(s));
+      ix->V = V;
+      ix->finalized = true;
+      ix->batch_valid = false;
+      ix->last_finalize_kind = 2;
+      return KV_OK;
+    }
+  }
+  ix->layout_valid = false;
   // ---- on the host cores: (norm class, text) order of the rows ----
   std::vector<int> perm;
   sort_rows_by_text(ix->h_indptr, ix->h_ids, n, hB, perm);
@@ -462,6 +523,9 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
   ix->n_ovf = 0;
   if (n) {
     KV_CUDA(cudaMemcpyAsync(ix->d_perm.p, perm.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    KV_CUDA(ix->d_invperm.ensure(n));
+    invperm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ix->d_perm.p, n, ix->d_invperm.p);
+    KV_CUDA(cudaGetLastError());
     rownorm_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(ix->indptr.p, ix->ids.p, ix->tf.p, ix->d_perm.p, n,
                                                                     ix->d_bb64.p, ix->d_univ.p, ix->d_B64.p,
                                                                     ix->d_B32.p, nullptr);
@@ -700,8 +764,14 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
   ix->V = V;
   ix->finalized = true;
   ix->batch_valid = false;
+  ix->layout_valid = n > 0;
+  ix->layout_rows = n;
+  ix->layout_univ = ix->h_univ;
+  ix->last_finalize_kind = 1;
   return KV_OK;
 }
+
+int kv_index_last_finalize_kind(const kv_index *ix) { return ix ? ix->last_finalize_kind : 0; }
 
 // caller holds ix->mu; scores land in ix->d_scores and, when out_scores != NULL, on the host
 static int score_impl(kv_index *ix, const uint32_t *q_ids, const uint32_t *q_tf, int64_t q_nnz, double q_oov_tf2,
@@ -728,7 +798,7 @@ static int score_impl(kv_index *ix, const uint32_t *q_ids, const uint32_t *q_tf,
     uint32_t h = (t * 0x9E3779B1u) >> (32 - log_h);
     while (tk[h] != KEY_EMPTY) h = (h + 1) & (H - 1);
     double a, d;
-    idf_host(ix->n_total, ix->h_df[t], a, d, ix->jaccard);
+    idf_host(ix->n_total, ix->h_df[t], a, d, ix->jaccard, ix->corpus_fit);
     tk[h] = t;
     tw[h] = (double)qp.tfq[i] * a;
     tdd[h] = d;
@@ -774,6 +844,7 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
   cudaStream_t s = ix->stream;
   const int QT = Tile::QT, H = Tile::H;
   ix->batch_valid = false;
+  ix->has_excl = false;
   ix->irr_q.clear(); ix->irr_indptr.assign(1, 0); ix->irr_ids.clear(); ix->irr_tf.clear(); ix->irr_oov.clear();
   for (int64_t q = 0; q < n_q; q++)
     if (q_indptr[q + 1] < q_indptr[q] || (q_indptr[q + 1] > q_indptr[q] && (!q_ids || !q_tf)))
@@ -880,7 +951,7 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
         if (keys[h] == KEY_EMPTY) {
           keys[h] = f;
           double a, d;
-          idf_host(ix->n_total, ix->h_df[f], a, d, ix->jaccard);
+          idf_host(ix->n_total, ix->h_df[f], a, d, ix->jaccard, ix->corpus_fit);
           ad[2 * h] = (float)a;
           ad[2 * h + 1] = (float)d;
           cur_feats++;
@@ -961,6 +1032,7 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
     P.n_ovf = ix->n_ovf; P.tables = ix->d_tables.p; P.tiles = ix->d_tiles.p;
     P.q_nq = ix->d_qconst.p; P.q_dotU = P.q_nq + n_q; P.q_corrU = P.q_dotU + n_q;
     P.q_dotS = P.q_nq + 4 * n_q; P.q_corrS = P.q_nq + 5 * n_q;
+    P.q_excl = ix->has_excl ? ix->d_excl_sorted.p : nullptr;
     P.gthr = ix->d_gthr.p; P.ubuf = ix->d_ubuf.p; P.stats = ix->d_stats.p;
     P.n_q = n_q; P.k = k; P.n_splits = (int)n_splits; P.prune = prune; P.jaccard = ix->jaccard;
     P.part_scores = ix->d_part_s.p; P.part_rows = ix->d_part_r.p;
@@ -980,14 +1052,16 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
     KV_CUDA(cudaGetLastError());
     if (ix->batch_null) {
       fill_null_kernel<<<(unsigned)((ix->batch_null * k + 255) / 256), 256, 0, s>>>(ix->d_qperm.p + n_q, (int)ix->batch_null, k,
-                                                                                    ix->n_rows, ix->row_base, d_out_s, d_out_r);
+                                                                                    ix->n_rows, ix->row_base,
+                                                                                    ix->has_excl ? ix->d_excl_orig.p : nullptr, d_out_s, d_out_r);
       KV_CUDA(cudaGetLastError());
     }
     for (size_t i = 0; i < ix->irr_q.size(); i++) {
       const int64_t q = ix->irr_q[i], a = ix->irr_indptr[i], b = ix->irr_indptr[i + 1];
       int rc = score_impl(ix, ix->irr_ids.data() + a, ix->irr_tf.data() + a, b - a, ix->irr_oov[i], nullptr);
       if (rc != KV_OK) return rc;
-      select_topk_kernel<<<1, 1024, 0, s>>>(ix->d_scores.p, ix->n_rows, ix->row_base, k, d_out_s + q * k, d_out_r + q * k);
+      select_topk_kernel<<<1, 1024, 0, s>>>(ix->d_scores.p, ix->n_rows, ix->row_base, k,
+                                            ix->has_excl ? (int64_t)ix->h_excl_orig[(size_t)q] : -1, d_out_s + q * k, d_out_r + q * k);
       KV_CUDA(cudaGetLastError());
     }
     KV_CUDA(cudaMemcpyAsync(ix->last_stats, ix->d_stats.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -1042,6 +1116,120 @@ int kv_query_upload(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids
   if (!ix || n_q < 1 || !q_indptr) return kv_fail(KV_ERR_INVALID, "kv_query_upload: bad arguments");
   std::lock_guard<std::mutex> g(ix->mu);
   return prepare_batch(ix, q_indptr, q_ids, q_tf, q_oov_tf2, n_q);
+}
+
+static int set_exclusions_locked(kv_index *ix, const int64_t *exclude_rows, int64_t n_q);
+
+int kv_query_set_exclusions(kv_index *ix, const int64_t *exclude_rows, int64_t n_q) {
+  if (!ix) return kv_fail(KV_ERR_INVALID, "kv_query_set_exclusions: NULL handle");
+  std::lock_guard<std::mutex> g(ix->mu);
+  return set_exclusions_locked(ix, exclude_rows, n_q);
+}
+
+int kv_selfjoin_upload(kv_index *ix, int64_t q_begin, int64_t q_end) {
+  if (!ix || q_begin < 0 || q_end <= q_begin) return kv_fail(KV_ERR_INVALID, "kv_selfjoin_upload: bad row range");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (!ix->finalized) return kv_fail(KV_ERR_STATE, "kv_selfjoin_upload: index not finalized");
+  if (q_end > ix->n_rows) return kv_fail(KV_ERR_INVALID, "kv_selfjoin_upload: row range outside the index");
+  const int64_t n = q_end - q_begin, base = ix->h_indptr[(size_t)q_begin];
+  std::vector<int64_t> ip((size_t)n + 1), ex((size_t)n);
+  for (int64_t i = 0; i <= n; i++) ip[(size_t)i] = ix->h_indptr[(size_t)(q_begin + i)] - base;
+  std::vector<uint32_t> tf32((size_t)ip[(size_t)n]);
+  for (size_t i = 0; i < tf32.size(); i++) tf32[i] = ix->h_tf[(size_t)base + i];
+  int rc = prepare_batch(ix, ip.data(), ix->h_ids.data() + base, tf32.data(), nullptr, n);
+  if (rc != KV_OK) return rc;
+  for (int64_t i = 0; i < n; i++) ex[(size_t)i] = ix->row_base + q_begin + i;
+  return set_exclusions_locked(ix, ex.data(), n);
+}
+
+int kv_rescore_pairs(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
+                     const double *q_oov_tf2, int64_t n_q, int k, const int64_t *rows, double *out_scores) {
+  if (!ix || n_q < 0 || k < 1 || (n_q > 0 && (!q_indptr || !rows || !out_scores)))
+    return kv_fail(KV_ERR_INVALID, "kv_rescore_pairs: bad arguments");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (!ix->finalized) return kv_fail(KV_ERR_STATE, "kv_rescore_pairs: index not finalized");
+  if (n_q == 0) return KV_OK;
+  const int64_t nnz = q_indptr[n_q] - q_indptr[0];
+  if (nnz < 0 || (nnz > 0 && (!q_ids || !q_tf))) return kv_fail(KV_ERR_INVALID, "kv_rescore_pairs: bad query CSR");
+  if (ix->n_rows == 0) {
+    for (int64_t i = 0; i < n_q * k; i++) out_scores[i] = -INFINITY;
+    return KV_OK;
+  }
+  KV_CUDA(cudaSetDevice(ix->device));
+  cudaStream_t s = ix->stream;
+  // |q|^2 exactly as K1a gets it (prep_query, float64)
+  std::vector<double> cst((size_t)n_q);
+  std::vector<int64_t> ip((size_t)n_q + 1);
+  for (int64_t q = 0; q <= n_q; q++) ip[(size_t)q] = q_indptr[q] - q_indptr[0];
+  parallel_for(n_q, n_q >= 2048 ? host_threads() : 1, [&](int, int64_t a, int64_t b) {
+    QueryPrep qp;
+    for (int64_t q = a; q < b; q++) {
+      prep_query(ix, q_ids + q_indptr[q], q_tf + q_indptr[q], q_indptr[q + 1] - q_indptr[q], q_oov_tf2 ? q_oov_tf2[q] : 0.0, qp);
+      cst[(size_t)q] = qp.nq;
+    }
+  });
+  KV_CUDA(ix->d_rq_indptr.ensure(n_q + 1)); KV_CUDA(ix->d_rq_ids.ensure(std::max<int64_t>(nnz, 1)));
+  KV_CUDA(ix->d_rq_tf.ensure(std::max<int64_t>(nnz, 1))); KV_CUDA(ix->d_rq_const.ensure(n_q));
+  KV_CUDA(ix->d_rq_out.ensure(n_q * k)); KV_CUDA(ix->d_rq_rows.ensure(n_q * k));
+  KV_CUDA(cudaMemcpyAsync(ix->d_rq_indptr.p, ip.data(), (size_t)(n_q + 1) * 8, cudaMemcpyHostToDevice, s));
+  if (nnz) {
+    KV_CUDA(cudaMemcpyAsync(ix->d_rq_ids.p, q_ids + q_indptr[0], (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
+    KV_CUDA(cudaMemcpyAsync(ix->d_rq_tf.p, q_tf + q_indptr[0], (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
+  }
+  KV_CUDA(cudaMemcpyAsync(ix->d_rq_const.p, cst.data(), (size_t)n_q * 8, cudaMemcpyHostToDevice, s));
+  KV_CUDA(cudaMemcpyAsync(ix->d_rq_rows.p, rows, (size_t)n_q * k * 8, cudaMemcpyHostToDevice, s));
+  RescoreParams P;
+  P.indptr = ix->indptr.p; P.ids = ix->ids.p; P.tf = ix->tf.p;
+  P.a64 = ix->d_a64.p; P.d64 = ix->d_d64.p; P.B64 = ix->d_B64.p; P.invperm = ix->d_invperm.p;
+  P.q_indptr = ix->d_rq_indptr.p; P.q_ids = ix->d_rq_ids.p; P.q_tf = ix->d_rq_tf.p;
+  P.q_nq = ix->d_rq_const.p;
+  P.rows = ix->d_rq_rows.p; P.n_q = n_q; P.n_rows = ix->n_rows; P.row_base = ix->row_base; P.V = ix->V;
+  P.k = k; P.jaccard = ix->jaccard; P.out = ix->d_rq_out.p;
+  rescore_kernel<<<(unsigned)((n_q * k * 32 + 255) / 256), 256, 0, s>>>(P);
+  KV_CUDA(cudaGetLastError());
+  KV_CUDA(cudaMemcpyAsync(out_scores, ix->d_rq_out.p, (size_t)n_q * k * 8, cudaMemcpyDeviceToHost, s));
+  KV_CUDA(cudaStreamSynchronize(s));
+  return KV_OK;
+}
+
+static int set_exclusions_locked(kv_index *ix, const int64_t *exclude_rows, int64_t n_q) {
+  if (!ix->batch_valid) return kv_fail(KV_ERR_STATE, "kv_query_set_exclusions: no query batch uploaded");
+  if (!exclude_rows) { ix->has_excl = false; return KV_OK; }
+  if (n_q != ix->batch_q) return kv_fail(KV_ERR_INVALID, "kv_query_set_exclusions: %lld entries for a batch of %lld queries",
+                                         (long long)n_q, (long long)ix->batch_q);
+  KV_CUDA(cudaSetDevice(ix->device));
+  // global row ids -> local original rows of this shard (-1: none, or the row lives on another shard)
+  ix->h_excl_orig.assign((size_t)n_q, -1);
+  for (int64_t q = 0; q < n_q; q++) {
+    const int64_t r = exclude_rows[q] - ix->row_base;
+    if (exclude_rows[q] >= 0 && r >= 0 && r < ix->n_rows) ix->h_excl_orig[(size_t)q] = (int)r;
+  }
+  std::vector<int> sorted((size_t)n_q);
+  for (int64_t i = 0; i < n_q; i++) sorted[(size_t)i] = ix->h_excl_orig[(size_t)ix->h_qperm.p[i]];
+  KV_CUDA(ix->d_excl_sorted.ensure(n_q)); KV_CUDA(ix->d_excl_orig.ensure(n_q));
+  KV_CUDA(cudaMemcpyAsync(ix->d_excl_sorted.p, sorted.data(), (size_t)n_q * sizeof(int), cudaMemcpyHostToDevice, ix->stream));
+  KV_CUDA(cudaMemcpyAsync(ix->d_excl_orig.p, ix->h_excl_orig.data(), (size_t)n_q * sizeof(int), cudaMemcpyHostToDevice, ix->stream));
+  KV_CUDA(cudaStreamSynchronize(ix->stream));
+  ix->has_excl = true;
+  return KV_OK;
+}
+
+int kv_topk_resident_host(kv_index *ix, int k, float *out_scores, int64_t *out_rows) {
+  if (!ix || !out_scores || !out_rows) return kv_fail(KV_ERR_INVALID, "kv_topk_resident_host: bad arguments");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (!ix->batch_valid) return kv_fail(KV_ERR_STATE, "kv_topk_resident_host: no query batch uploaded");
+  if (k < 1 || k > 32) return kv_fail(KV_ERR_INVALID, "kv_topk: k must be 1..32");
+  const int64_t n_q = ix->batch_q;
+  KV_CUDA(cudaSetDevice(ix->device));
+  KV_CUDA(ix->d_out_s.ensure(n_q * k)); KV_CUDA(ix->d_out_r.ensure(n_q * k));
+  int rc = run_batch(ix, k, ix->d_out_s.p, ix->d_out_r.p);
+  if (rc != KV_OK) return rc;
+  KV_CUDA(cudaMemcpyAsync(out_scores, ix->d_out_s.p, (size_t)n_q * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+  KV_CUDA(cudaMemcpyAsync(out_rows, ix->d_out_r.p, (size_t)n_q * k * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
+  KV_CUDA(cudaEventRecord(ix->ev[4], ix->stream));
+  KV_CUDA(cudaStreamSynchronize(ix->stream));
+  for (int i = 1; i < 4; i++) cudaEventElapsedTime(&ix->last_ms[i], ix->ev[i], ix->ev[i + 1]);
+  return KV_OK;
 }
 
 int kv_topk_resident(kv_index *ix, int k, void *d_scores, void *d_rows) {

@@ -75,12 +75,13 @@ struct IdfTables {
 
 __global__ void idf_kernel(const uint32_t *__restrict__ df, const uint32_t *__restrict__ cnt,
                            const uint32_t *__restrict__ tfmin, const uint32_t *__restrict__ tfmax, int64_t V,
-                           int64_t n_total, int64_t n_local, int jaccard, IdfTables T) {
+                           int64_t n_total, int64_t n_local, int jaccard, int corpus_fit, IdfTables T) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= V) return;
-  double num = (double)(n_total + 2);
+  // corpus_fit: TF-IDF fitted on the corpus alone (the query is only transformed): one idf for both sides
+  double num = (double)(n_total + (corpus_fit ? 1 : 2));
   double ib = jaccard ? 1.0 : log(num / ((double)df[t] + 1.0)) + 1.0;  // Jaccard: every token weighs 1
-  double iq = jaccard ? 1.0 : log(num / ((double)df[t] + 2.0)) + 1.0;
+  double iq = jaccard ? 1.0 : (corpus_fit ? ib : log(num / ((double)df[t] + 2.0)) + 1.0);
   double a = iq * iq, bb = ib * ib;
   T.a64[t] = a; T.d64[t] = a - bb; T.bb64[t] = bb;
   bool u = n_local > 0 && (int64_t)cnt[t] == n_local && tfmin[t] == tfmax[t];
@@ -287,6 +288,7 @@ struct TopkParams {
   const TileDesc *tiles;
   const float *q_nq, *q_dotU, *q_corrU;  // [n_q] (sorted query order)
   const float *q_dotS, *q_corrS;         // [n_q] start values of chunk bounds (universal + summary-universal features)
+  const int *q_excl;                     // [n_q] or NULL: local ORIGINAL row a query must not match (self-join), -1 = none
   int *gthr;                             // [n_q] float bits: lower bound of the global k-th score
   float *ubuf;                           // [n_tiles][n_chunks] chunk upper bounds (scratch)
   unsigned long long *stats;             // [0] chunks scanned, [1] chunks pruned, [2] summaries evaluated
@@ -536,8 +538,10 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
         if (L.valid[g] && lhs >= rhs) {
           const float s = pair_score(L.jaccard, dot[g], L.nq[g], t);
           const int row = P.perm[pos0 + row_in];
-          if (s > L.filt[g] || (s == L.filt[g] && row < L.krow[g])) {
-            const int qi = g * 32 + lane;
+          const int qi = g * 32 + lane;
+          // self-join: a query never matches the row it was taken from (looked up only on this rare path)
+          const bool banned = P.q_excl != nullptr && P.q_excl[td.q_begin + qi] == row;
+          if (!banned && (s > L.filt[g] || (s == L.filt[g] && row < L.krow[g]))) {
             while (atomicCAS(&s_lock[qi], 0, 1) != 0) {}
             __threadfence_block();
             float *ls = s_lscore + qi * k;
@@ -728,6 +732,90 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
 }
 
 // ----------------------------------------------------------------------------------------
+// K6: float64 re-scoring of selected (query, row) pairs -- one warp per pair.  Walks ALL of the row's raw CSR
+// entries in their stored (text) order and sums with explicit round-to-nearest adds/multiplies (no fused
+// multiply-add, no folded constants), so the bits depend only on the row's text, the query and the global
+// statistics -- not on which segment or shard holds the row or which features that shard folded as universal.
+// Rows with identical text therefore tie EXACTLY everywhere, and the (score desc, row asc) order of
+// services/gfkb/app.py:89 is reproduced across segments.  Same formula as K1a (values agree to ~1e-16 relative).
+// Used by the batched match path: K1b selects candidates in float32, K6 gives them float64 scores.
+// ----------------------------------------------------------------------------------------
+struct RescoreParams {
+  const int64_t *indptr;   // raw CSR of the index (device)
+  const uint32_t *ids;
+  const uint16_t *tf;
+  const double *a64, *d64;  // host-computed idf tables (the values K1a's query tables are built from)
+  const double *B64;        // row norms by position
+  const int *invperm;       // original row -> position
+  const int64_t *q_indptr;  // query batch CSR (device)
+  const uint32_t *q_ids, *q_tf;
+  const double *q_nq;
+  const long long *rows;    // [n_q * k] global row ids (-1: unused slot)
+  int64_t n_q, n_rows, row_base, V;
+  int k, jaccard;
+  double *out;              // [n_q * k]; -inf for unused slots and rows of other shards
+};
+
+__global__ void __launch_bounds__(256) rescore_kernel(RescoreParams P) {
+  const int64_t pair = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pair >= P.n_q * P.k) return;
+  const int64_t q = pair / P.k;
+  const long long gr = P.rows[pair];
+  const int64_t r = gr - P.row_base;
+  if (gr < 0 || r < 0 || r >= P.n_rows) {
+    if (lane == 0) P.out[pair] = -INFINITY;
+    return;
+  }
+  const int64_t qa = P.q_indptr[q], qb = P.q_indptr[q + 1];
+  double du = 0.0, dv = 0.0;
+  const int64_t p1 = P.indptr[r + 1];
+  for (int64_t p0 = P.indptr[r]; p0 < p1; p0 += 32) {
+    const int64_t p = p0 + lane;
+    bool hit = false;
+    double wu = 0.0, wv = 0.0;
+    if (p < p1) {
+      const uint32_t t = P.ids[p];
+      if ((int64_t)t < P.V) {
+        for (int64_t j = qa; j < qb; j++)
+          if (P.q_ids[j] == t) {
+            const double f = (double)P.tf[p];
+            wu = __dmul_rn(f, __dmul_rn((double)P.q_tf[j], P.a64[t]));
+            wv = __dmul_rn(__dmul_rn(f, f), P.d64[t]);
+            hit = true;
+            break;
+          }
+      }
+    }
+    uint32_t hm = __ballot_sync(FULL, hit);
+    while (hm) {
+      const int j = __ffs(hm) - 1;
+      hm &= hm - 1;
+      du = __dadd_rn(du, __shfl_sync(FULL, wu, j));
+      dv = __dadd_rn(dv, __shfl_sync(FULL, wv, j));
+    }
+  }
+  if (lane == 0) {
+    const double B = P.B64[P.invperm[r]];
+    const double dot = du;
+    double sc;
+    if (P.jaccard) {
+      const double den = __dadd_rn(__dadd_rn(P.q_nq[q], B), -dot);
+      sc = (den > 0.0 && dot != 0.0) ? dot / den : 0.0;
+    } else {
+      const double den = __dmul_rn(P.q_nq[q], __dadd_rn(B, dv));
+      sc = (den > 0.0 && dot != 0.0) ? dot / sqrt(den) : 0.0;
+    }
+    P.out[pair] = sc;
+  }
+}
+
+__global__ void invperm_kernel(const int *__restrict__ perm, int64_t n, int *invperm) {
+  const int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (pos < n) invperm[perm[pos]] = (int)pos;
+}
+
+// ----------------------------------------------------------------------------------------
 // K5: merge n_lists ordered partial lists per query -- one warp per query
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ bool better(float s1, long long r1, float s2, long long r2) {
@@ -781,16 +869,18 @@ __global__ void merge_topk_kernel(const float *__restrict__ in_s, const long lon
 // Null queries (no feature in common with any row: every score is 0): the stable sort keeps the
 // first k rows.  One thread per (query, slot).
 __global__ void fill_null_kernel(const int *__restrict__ null_q, int n_null, int k, int64_t n_rows, int64_t row_base,
-                                 float *out_s, long long *out_r) {
+                                 const int *__restrict__ excl_by_query, float *out_s, long long *out_r) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_null * k) return;
   int q = null_q[i / k], j = i % k;
-  out_s[(size_t)q * k + j] = j < n_rows ? 0.f : -INFINITY;
-  out_r[(size_t)q * k + j] = j < n_rows ? row_base + j : -1LL;
+  const int ex = excl_by_query ? excl_by_query[q] : -1;  // by ORIGINAL query index
+  const int64_t r = (ex >= 0 && j >= ex) ? j + 1 : j;     // the j-th row once the excluded one is skipped
+  out_s[(size_t)q * k + j] = r < n_rows ? 0.f : -INFINITY;
+  out_r[(size_t)q * k + j] = r < n_rows ? row_base + r : -1LL;
 }
 
 // Fallback selection for one (irregular) query: k passes of block-wide arg-best over float64 scores.
-__global__ void select_topk_kernel(const double *__restrict__ scores, int64_t n, int64_t row_base, int k,
+__global__ void select_topk_kernel(const double *__restrict__ scores, int64_t n, int64_t row_base, int k, int64_t excl,
                                    float *out_s, long long *out_r) {
   __shared__ float s_s[32];
   __shared__ long long s_r[32];
@@ -804,6 +894,7 @@ __global__ void select_topk_kernel(const double *__restrict__ scores, int64_t n,
     const float ps = prev_s;
     const long long pr = prev_r;
     for (int64_t r = threadIdx.x; r < n; r += blockDim.x) {
+      if (r == excl) continue;
       float s = (float)scores[r];
       bool after = (s < ps) || (s == ps && r > pr);  // strictly after the previously selected pair
       if (after && (br < 0 || s > bs || (s == bs && r < br))) { bs = s; br = r; }

@@ -24,15 +24,44 @@ class DenseIndex:
     def __init__(self, dim: int, device: int = 0, row_base: int = 0):
         h = C.c_void_p()
         _capi.check(_capi.load().kv_dense_create(device, dim, row_base, C.byref(h)))
-        self._h, self.dim = h, dim
+        self._h, self.dim, self.device = h, dim, device
 
     def add(self, rows: np.ndarray) -> None:
         bits = rows if rows.dtype == np.uint16 else to_bf16_bits(rows)
         bits = np.ascontiguousarray(bits).reshape(-1, self.dim)
         _capi.check(_capi.load().kv_dense_append(self._h, bits.ctypes.data_as(C.POINTER(C.c_uint16)), bits.shape[0]))
 
+    def add_device(self, rows) -> None:
+        """Append rows that already live in HBM: a contiguous torch bfloat16 tensor [n, dim] on this device."""
+        assert rows.is_cuda and rows.is_contiguous() and rows.element_size() == 2 and rows.shape[-1] == self.dim
+        _capi.check(_capi.load().kv_dense_append_device(self._h, C.c_void_p(rows.data_ptr()), rows.shape[0]))
+
     def finalize(self) -> None:
         _capi.check(_capi.load().kv_dense_finalize(self._h))
+
+    def topk_device(self, queries, k: int = 16, exclude_base: int = -1):
+        """Queries and results on the device (torch): queries bfloat16 [Q, dim]; returns (float32 [Q,k], int64 [Q,k]).
+        ``exclude_base >= 0``: query q never matches GLOBAL row ``exclude_base + q`` (self-join)."""
+        import torch
+
+        assert queries.is_cuda and queries.is_contiguous() and queries.element_size() == 2 and queries.shape[-1] == self.dim
+        n = queries.shape[0]
+        s = torch.empty((n, k), dtype=torch.float32, device=queries.device)
+        r = torch.empty((n, k), dtype=torch.int64, device=queries.device)
+        _capi.check(_capi.load().kv_dense_topk_device(self._h, C.c_void_p(queries.data_ptr()), n, k, exclude_base,
+                                                      C.c_void_p(s.data_ptr()), C.c_void_p(r.data_ptr())))
+        return s, r
+
+    def selfjoin_topk(self, k: int = 32, lo: int = 0, hi: int | None = None, device_out: bool = False):
+        """All-pairs (BASELINE configs[3]): for local rows [lo, hi) the k nearest OTHER rows."""
+        import torch
+
+        hi = self.n_rows if hi is None else hi
+        dev = torch.device("cuda", self.device)
+        s = torch.empty((hi - lo, k), dtype=torch.float32, device=dev)
+        r = torch.empty((hi - lo, k), dtype=torch.int64, device=dev)
+        _capi.check(_capi.load().kv_dense_selfjoin_device(self._h, lo, hi, k, C.c_void_p(s.data_ptr()), C.c_void_p(r.data_ptr())))
+        return (s, r) if device_out else (s.cpu().numpy(), r.cpu().numpy())
 
     @property
     def n_rows(self) -> int:

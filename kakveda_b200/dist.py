@@ -158,3 +158,114 @@ class ShardedGfkb:
             return s.cpu().numpy(), r.cpu().numpy()
         finally:
             qfb.close()
+
+
+class ShardedDense:
+    """Row-sharded dense-embedding GFKB (BASELINE configs[2] read as 768-d bf16 cosine, and configs[3] all-pairs).
+
+    Rank r holds rows [n*r/W, n*(r+1)/W) as a ``DenseIndex`` (K2); queries are replicated; one all-gather of the
+    per-shard partial top-k + K5 merge per batch -- the same exchange as the TF-IDF path, no df all-reduce needed.
+    ``allpairs_topk`` makes every stored row a query: the row shards are all-gathered ONCE over NCCL (N x dim bf16,
+    1.5 GB at 1M x 768) so that each rank can score all N rows against its shard, each query excluding itself.
+    """
+
+    def __init__(self, dim: int, device: int, rank: int = 0, world: int = 1, group=None):
+        from .denseindex import DenseIndex
+
+        self.dim, self.device, self.rank, self.world, self.group = dim, device, rank, world, group
+        self._mk = lambda base: DenseIndex(dim, device=device, row_base=base)
+        self.index = None
+        self.n_global = 0
+        self._local = None
+
+    def build(self, rows_local, n_global: int) -> None:
+        """``rows_local``: this rank's rows, a torch bfloat16 CUDA tensor [n_local, dim] (shard_bounds order)."""
+        lo, hi = shard_bounds(n_global, self.world, self.rank)
+        assert rows_local.shape[0] == hi - lo
+        self.n_global = n_global
+        self.index = self._mk(lo)
+        self.index.add_device(rows_local.contiguous())
+        self.index.finalize()
+        self._local = rows_local
+
+    def topk(self, queries, k: int = 16, exclude_base: int = -1):
+        """queries: torch bfloat16 CUDA [Q, dim], identical on every rank -> ([Q,k] float32, [Q,k] int64) on device."""
+        s, r = self.index.topk_device(queries.contiguous(), k, exclude_base)
+        if self.world == 1:
+            return s, r
+        gs, gr = gather_topk(s, r, self.group)
+        return merge_on_device(self.device, gs, gr)
+
+    def gather_rows(self):
+        """All-gather the row shards into the full [N, dim] matrix (equal-sized slots, padding dropped)."""
+        import torch
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return self._local
+        per = (self.n_global + self.world - 1) // self.world + 1
+        slot = torch.zeros((per, self.dim), dtype=self._local.dtype, device=self._local.device)
+        slot[: self._local.shape[0]] = self._local
+        full = torch.empty((self.world * per, self.dim), dtype=self._local.dtype, device=self._local.device)
+        dist.all_gather_into_tensor(full, slot, group=self.group)
+        parts = []
+        for w in range(self.world):
+            lo, hi = shard_bounds(self.n_global, self.world, w)
+            parts.append(full[w * per: w * per + (hi - lo)])
+        return torch.cat(parts).contiguous()
+
+    def allpairs_topk(self, k: int = 32, block: int = 262144):
+        """Every row's k nearest OTHER rows over the whole sharded GFKB: ([N,k] float32, [N,k] int64), on every rank."""
+        import torch
+
+        allrows = self.gather_rows()
+        out_s, out_r = [], []
+        for b0 in range(0, self.n_global, block):
+            b1 = min(self.n_global, b0 + block)
+            s, r = self.topk(allrows[b0:b1], k, exclude_base=b0)
+            out_s.append(s)
+            out_r.append(r)
+        return torch.cat(out_s), torch.cat(out_r)
+
+
+class ShardedJaccard:
+    """Row-sharded token-set Jaccard GFKB (BASELINE configs[4]: 5M sets on 4 GPUs).  No global statistics exist for
+    Jaccard (every token weighs 1), so the only exchanges are the all-gather of partial top-k and a max-reduce of the
+    exact (|intersection|, |union|) integers, which each rank can only count for the rows it owns."""
+
+    def __init__(self, vocab_size: int, device: int, rank: int = 0, world: int = 1, group=None):
+        from .jaccardindex import JaccardIndex
+
+        self.device, self.rank, self.world, self.group = device, rank, world, group
+        self.vocab_size = vocab_size
+        self._cls = JaccardIndex
+        self.index = None
+        self.n_global = 0
+
+    def build_csr(self, indptr: np.ndarray, ids: np.ndarray) -> None:
+        """``indptr``/``ids``: the WHOLE corpus (every rank passes the same arrays); this rank keeps its row range."""
+        n = len(indptr) - 1
+        self.n_global = n
+        lo, hi = shard_bounds(n, self.world, self.rank)
+        self.index = self._cls(self.vocab_size, device=self.device, row_base=lo)
+        ip = np.ascontiguousarray(indptr[lo:hi + 1], dtype=np.int64)
+        self.index.add_csr(ip - ip[0], np.ascontiguousarray(ids[ip[0]:ip[-1]], dtype=np.uint32))
+        self.index.finalize()
+
+    def topk_csr(self, indptr: np.ndarray, ids: np.ndarray, k: int = 16):
+        """(scores float32, rows int64, inter int32, union int32), each [Q,k], identical on every rank."""
+        import torch
+        import torch.distributed as dist
+
+        s, r, inter, union = self.index.topk_csr(indptr, ids, k)
+        if self.world == 1:
+            return s, r, inter, union
+        dev = f"cuda:{self.device}"
+        gs, gr = gather_topk(torch.from_numpy(s).to(dev), torch.from_numpy(r).to(dev), self.group)
+        ms, mr = merge_on_device(self.device, gs, gr)
+        rows = mr.cpu().numpy()
+        inter, union = self.index.counts_csr(indptr, ids, rows)      # -1 for rows of other shards
+        cnt = torch.from_numpy(np.stack([inter, union])).to(dev)
+        dist.all_reduce(cnt, op=dist.ReduceOp.MAX, group=self.group)
+        cnt = cnt.cpu().numpy()
+        return ms.cpu().numpy(), rows, cnt[0], cnt[1]

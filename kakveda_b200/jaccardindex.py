@@ -75,6 +75,27 @@ class JaccardIndex:
                                           p(rows, C.c_int64), p(inter, C.c_int32), p(union, C.c_int32)))
         return scores, rows, inter, union
 
+    def counts_csr(self, indptr: np.ndarray, ids: np.ndarray, rows: np.ndarray):
+        """Exact (|q ∩ row|, |q ∪ row|) of given (query, GLOBAL row) pairs; -1 for rows this shard does not hold."""
+        lib = _capi.load()
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        n, k = rows.shape
+        inside = ids < self.vocab_size
+        oov = np.zeros(n, dtype=np.float64)
+        if not inside.all():
+            seg = np.repeat(np.arange(n), np.diff(indptr))
+            np.add.at(oov, seg[~inside], 1.0)
+            keep = np.concatenate([[0], np.cumsum(inside)])
+            indptr, ids = keep[indptr].astype(np.int64), ids[inside]
+        inter = np.empty((n, k), dtype=np.int32)
+        union = np.empty((n, k), dtype=np.int32)
+        p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        _capi.check(lib.kv_jaccard_counts(self._h, p(indptr, C.c_int64), p(ids, C.c_uint32), p(oov, C.c_double), n, k,
+                                          p(rows, C.c_int64), p(inter, C.c_int32), p(union, C.c_int32)))
+        return inter, union
+
     def topk_sets(self, queries: Sequence[Sequence[int]], k: int = 16):
         return self.topk_csr(*_csr(queries), k=k)
 

@@ -176,8 +176,18 @@ class GfkbIndex:
         df = np.ascontiguousarray(df, dtype=np.uint32)
         _capi.check(_capi.load().kv_index_set_global_df(self._h, _ptr(df, C.c_uint32), len(df), n_rows_global))
 
+    def set_mode(self, mode: int) -> None:
+        """0 = the reference's refit-per-query TF-IDF cosine (default), 1 = token-set Jaccard, 2 = TF-IDF fitted on
+        the corpus alone (symmetric; the measure of the all-pairs self-join).  Call before ``finalize``."""
+        _capi.check(_capi.load().kv_index_set_mode(self._h, int(mode)))
+
     def finalize(self) -> None:
         _capi.check(_capi.load().kv_index_finalize(self._h, len(self.vocab)))
+
+    @property
+    def last_finalize_kind(self) -> int:
+        """1 = full rebuild, 2 = statistics-only refresh (rows unchanged, only global N / df moved)."""
+        return int(_capi.load().kv_index_last_finalize_kind(self._h))
 
     @property
     def n_rows(self) -> int:
@@ -218,6 +228,39 @@ class GfkbIndex:
         """Make a featurised batch resident on the device (host prep + H2D), for topk_resident."""
         _capi.check(_capi.load().kv_query_upload(self._h, _ptr(fb.indptr, C.c_int64), _ptr(fb.ids, C.c_uint32),
                                                  _ptr(fb.tf, C.c_uint32), _ptr(fb.oov, C.c_double), fb.n))
+
+    def set_exclusions(self, rows: Optional[np.ndarray]) -> None:
+        """Query q of the resident batch must not match GLOBAL row ``rows[q]`` (-1 = none); ``None`` clears."""
+        if rows is None:
+            _capi.check(_capi.load().kv_query_set_exclusions(self._h, None, 0))
+            return
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        _capi.check(_capi.load().kv_query_set_exclusions(self._h, _ptr(rows, C.c_int64), len(rows)))
+
+    def topk_resident_host(self, n_q: int, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Scan + merge of the resident batch of ``n_q`` queries, results copied to the host."""
+        scores = np.empty((n_q, k), dtype=np.float32)
+        rows = np.empty((n_q, k), dtype=np.int64)
+        _capi.check(_capi.load().kv_topk_resident_host(self._h, k, _ptr(scores, C.c_float), _ptr(rows, C.c_int64)))
+        return scores, rows
+
+    def selfjoin_topk(self, k: int, lo: int = 0, hi: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """All-pairs: for local rows [lo, hi) the k best OTHER rows (the row itself is excluded)."""
+        hi = self.n_rows if hi is None else hi
+        if hi <= lo:
+            return np.zeros((0, k), np.float32), np.zeros((0, k), np.int64)
+        _capi.check(_capi.load().kv_selfjoin_upload(self._h, lo, hi))
+        return self.topk_resident_host(hi - lo, k)
+
+    def rescore(self, fb: FeatureBatch, rows: np.ndarray) -> np.ndarray:
+        """K6: float64 scores of the pairs (query q, GLOBAL row rows[q, j]); identical rows tie exactly on every shard."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        k = rows.shape[1]
+        out = np.empty((fb.n, k), dtype=np.float64)
+        _capi.check(_capi.load().kv_rescore_pairs(self._h, _ptr(fb.indptr, C.c_int64), _ptr(fb.ids, C.c_uint32),
+                                                  _ptr(fb.tf, C.c_uint32), _ptr(fb.oov, C.c_double), fb.n, k,
+                                                  _ptr(rows, C.c_int64), _ptr(out, C.c_double)))
+        return out
 
     def topk_resident(self, k: int, d_scores_ptr: int, d_rows_ptr: int) -> None:
         """Device-only scan + merge of the uploaded batch into caller-owned device buffers."""

@@ -1,0 +1,270 @@
+"""Resident GFKB: ``failures.jsonl`` + a device index kept in sync.
+
+The reference's GFKB service re-reads and re-validates the whole JSONL on every request
+(services/gfkb/app.py:49-51,81,106) and refits TF-IDF on it per query (similarity.py:17-18).  ``GfkbStore`` keeps
+the records and their device index resident and reproduces the three handlers that touch the hot path:
+
+* ``upsert``   -- services/gfkb/app.py:104-147: a (failure_type, signature_text) pair seen before appends a NEW
+  version of the latest matching record (version+1, occurrences+1, app merged, fields evolve), otherwise a new
+  ``F-%04d`` record; one JSON line is appended either way.
+* ``match`` / ``match_batch`` -- services/gfkb/app.py:79-102: stable sort by score descending, first 5, THEN the
+  failure_type filter, mapped to FailureMatch fields.
+* ``warn_batch`` -- services/warning_policy/app.py:19-72: signature_text of the request, best match against the
+  threshold, the reference's message strings.
+
+Index layout: a large MAIN segment (text-sorted scan layout, expensive to rebuild) plus a small TAIL segment that
+receives upserts.  TF-IDF statistics are global (every append changes N and df of every row), so after an append
+epoch both segments get the summed df / N -- the main segment through a statistics-only finalize
+(``kv_index_last_finalize_kind`` == 2: idf tables, row norms and chunk minima recomputed on the device, nothing
+re-sorted) -- and the tail is folded into the main segment once it grows past ``tail_limit`` rows.  Queries scan
+both segments (K1b, float32 candidates); the candidates are re-scored in float64 (K6: summed in the row's own
+feature order, so identical rows tie exactly in both segments) and ordered like Python's stable sort.
+"""
+from __future__ import annotations
+
+import json
+import threading
+from datetime import datetime, timezone
+from pathlib import Path
+from typing import Any, Callable, Dict, List, Mapping, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .fingerprint import signature_text as _signature_text
+from .gfkb import MATCH_LIMIT, _to_match
+from .similarity import FeatureBatch, GfkbIndex, Vocabulary
+
+CANDIDATES = 16  # float32 candidates per query and segment that get re-scored in float64 (>= MATCH_LIMIT)
+PATTERN_NAME = "Citation hallucination without sources"  # services/pattern_detector/app.py:48
+
+
+def _iso(dt: datetime) -> str:
+    """pydantic's JSON form of an aware UTC datetime (model_dump(mode="json"), app.py:131,146)."""
+    return dt.isoformat().replace("+00:00", "Z")
+
+
+class GfkbStore:
+    def __init__(self, path: Optional[Path] = None, device: int = 0, tail_limit: int = 65536,
+                 now: Optional[Callable[[], datetime]] = None):
+        self.path = Path(path) if path is not None else None
+        self.device = device
+        self.tail_limit = int(tail_limit)
+        self._now = now or (lambda: datetime.now(timezone.utc))  # app.py:34-35
+        self._lock = threading.RLock()
+        self.records: List[Dict[str, Any]] = []
+        self._latest: Dict[Tuple[str, str], int] = {}  # (failure_type, signature_text) -> index of the newest record
+        self.vocab = Vocabulary()
+        self._main: Optional[GfkbIndex] = None
+        self._tail: Optional[GfkbIndex] = None
+        self._n_main = 0          # records[:_n_main] live in the main segment
+        self._n_indexed = 0       # records[:_n_indexed] are on the device (main + tail)
+        self._main_df: Optional[np.ndarray] = None
+        self._dirty = False
+        self.stats = {"full_rebuilds": 0, "stat_refreshes": 0, "compactions": 0}
+        if self.path is not None and self.path.exists():
+            self.load()
+
+    # -- storage ---------------------------------------------------------------------------------------------
+    def load(self) -> None:
+        """Read the JSONL (app.py:38-46) and build the main segment from it."""
+        with self._lock:
+            rows = []
+            if self.path is not None and self.path.exists():
+                for line in self.path.read_text(encoding="utf-8").splitlines():
+                    if line.strip():
+                        rows.append(json.loads(line))
+            self._reset(rows)
+
+    def _reset(self, rows: List[Dict[str, Any]]) -> None:
+        self.records = list(rows)
+        self._latest = {}
+        for i, r in enumerate(self.records):
+            self._latest[(r["failure_type"], r["signature_text"])] = i
+        self._rebuild_main()
+
+    def _rebuild_main(self) -> None:
+        for ix in (self._main, self._tail):
+            if ix is not None:
+                ix.close()
+        self._main = self._tail = None
+        self._main_df = None
+        n = len(self.records)
+        if n:
+            self._main = GfkbIndex(device=self.device, row_base=0, vocab=self.vocab)
+            self._main.add_texts([r["signature_text"] for r in self.records])
+            self._main.finalize()
+            self.stats["full_rebuilds"] += 1
+        self._n_main = self._n_indexed = n
+        self._dirty = False
+
+    def _sync(self) -> None:
+        """Bring the device index up to date with ``records`` (called lazily before a query)."""
+        if not self._dirty and self._n_indexed == len(self.records):
+            return
+        pending = [r["signature_text"] for r in self.records[self._n_indexed:]]
+        n_tail = len(self.records) - self._n_main
+        if self._main is None or n_tail > max(self.tail_limit, 0):
+            self.stats["compactions"] += self._main is not None
+            self._rebuild_main()
+            return
+        if self._tail is None:
+            self._tail = GfkbIndex(device=self.device, row_base=self._n_main, vocab=self.vocab)
+        if pending:
+            self._tail.add_texts(pending)
+        self._n_indexed = len(self.records)
+        # global statistics = main + tail (the df all-reduce of a sharded GFKB, done in-process)
+        v = len(self.vocab)
+        if self._main_df is None:
+            self._main_df = self._main.local_df().astype(np.int64)
+        df = np.zeros(v, dtype=np.int64)
+        df[: len(self._main_df)] = self._main_df
+        df += self._tail.local_df().astype(np.int64)
+        df32 = df.astype(np.uint32)
+        for ix in (self._main, self._tail):
+            ix.set_global_df(df32, len(self.records))
+            ix.finalize()
+        if self._main.last_finalize_kind == 2:
+            self.stats["stat_refreshes"] += 1
+        else:
+            self.stats["full_rebuilds"] += 1
+        self._dirty = False
+
+    # -- upsert (services/gfkb/app.py:104-147) -----------------------------------------------------------------
+    def upsert(self, req: Mapping[str, Any]) -> Dict[str, Any]:
+        with self._lock:
+            key = (req["failure_type"], req["signature_text"])
+            idx = self._latest.get(key)  # == the reference's reversed() scan for the newest equal record (app.py:108-112)
+            now = _iso(self._now())
+            if idx is None:
+                rec = {
+                    "failure_id": f"F-{len(self.records) + 1:04d}",
+                    "version": 1,
+                    "created_at": now,
+                    "updated_at": now,
+                    "failure_type": req["failure_type"],
+                    "root_cause": req.get("root_cause"),
+                    "context_signature": req["context_signature"],
+                    "impact_severity": getattr(req["impact_severity"], "value", req["impact_severity"]),
+                    "resolution": req.get("resolution"),
+                    "occurrences": 1,
+                    "affected_apps": [req["app_id"]],
+                    "signature_text": req["signature_text"],
+                }
+                created = True
+            else:
+                rec = json.loads(json.dumps(self.records[idx]))  # deep copy (app.py:134)
+                rec["version"] += 1
+                rec["updated_at"] = now
+                rec["occurrences"] += 1
+                if req["app_id"] not in rec["affected_apps"]:
+                    rec["affected_apps"].append(req["app_id"])
+                rec["root_cause"] = req.get("root_cause") or rec["root_cause"]
+                rec["resolution"] = req.get("resolution") or rec["resolution"]
+                rec["context_signature"] = req.get("context_signature") or rec["context_signature"]
+                created = False
+            if self.path is not None:
+                with self.path.open("a", encoding="utf-8") as f:  # app.py:49-51
+                    f.write(json.dumps(rec, ensure_ascii=False) + "\n")
+            self.records.append(rec)
+            self._latest[key] = len(self.records) - 1
+            self._dirty = True
+            return {"ok": True, "created": created, "failure": rec}
+
+    # -- match (services/gfkb/app.py:79-102) -------------------------------------------------------------------
+    def _candidates(self, fb: FeatureBatch, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Per query: candidate rows from both segments with their float64 scores, ordered (score desc, row asc)."""
+        rows_all, f64_all = [], []
+        for ix in (self._main, self._tail):
+            if ix is None or ix.n_rows == 0:
+                continue
+            _, rows = ix.topk_features(fb, min(k, 32))
+            rows_all.append(rows)
+            f64_all.append(ix.rescore(fb, rows))
+        rows = np.concatenate(rows_all, axis=1)
+        f64 = np.concatenate(f64_all, axis=1)
+        big = np.where(rows < 0, np.iinfo(np.int64).max, rows)
+        order = np.lexsort((big, -f64), axis=1)  # last key is primary: score descending, then row ascending
+        return np.take_along_axis(rows, order, axis=1), np.take_along_axis(f64, order, axis=1)
+
+    def match_batch(self, signature_texts: Sequence[str], failure_types: Optional[Sequence[Optional[str]]] = None,
+                    limit: int = MATCH_LIMIT) -> List[List[dict]]:
+        with self._lock:
+            if not self.records:
+                return [[] for _ in signature_texts]  # app.py:82-83
+            self._sync()
+            fb = self.vocab.featurize(list(signature_texts), grow=False)
+            try:
+                rows, f64 = self._candidates(fb, max(CANDIDATES, limit))
+            finally:
+                fb.close()
+            out = []
+            for i in range(len(signature_texts)):
+                ft = failure_types[i] if failure_types is not None else None
+                matches = []
+                for r, s in zip(rows[i, :limit].tolist(), f64[i, :limit].tolist()):
+                    if r < 0:
+                        continue
+                    rec = self.records[r]
+                    if ft and rec["failure_type"] != ft:
+                        continue
+                    matches.append(_to_match(rec, s))
+                out.append(matches)
+            return out
+
+    def match(self, signature_text: str, failure_type: Optional[str] = None) -> List[dict]:
+        return self.match_batch([signature_text], [failure_type])[0]
+
+    def match_exact(self, signature_text: str, failure_type: Optional[str] = None, limit: int = MATCH_LIMIT) -> List[dict]:
+        """The handler on the full float64 score vector (K1a on both segments): no candidate stage at all."""
+        with self._lock:
+            if not self.records:
+                return []
+            self._sync()
+            parts = [ix.score(signature_text) for ix in (self._main, self._tail) if ix is not None and ix.n_rows]
+            scores = np.concatenate(parts).tolist()
+            order = sorted(range(len(scores)), key=lambda i: scores[i], reverse=True)[:limit]
+            out = []
+            for i in order:
+                rec = self.records[i]
+                if failure_type and rec["failure_type"] != failure_type:
+                    continue
+                out.append(_to_match(rec, scores[i]))
+            return out
+
+    # -- warn (services/warning_policy/app.py:19-72) ------------------------------------------------------------
+    def warn_batch(self, requests: Sequence[Mapping[str, Any]], threshold: float = 0.8, default_action: str = "warn",
+                   patterns: Optional[Sequence[Mapping[str, Any]]] = None) -> List[dict]:
+        """One WarningResponse-shaped dict per request; all GFKB lookups go through ONE batched scan."""
+        sigs = [_signature_text(r["prompt"], list(r.get("tools") or []), dict(r.get("env") or {})) for r in requests]
+        all_matches = self.match_batch(sigs)
+        out = []
+        for matches in all_matches:
+            best = matches[0] if matches else None
+            score = float(best.get("score", 0.0)) if best else 0.0
+            pattern_id = None
+            if best and patterns:
+                bt = best.get("failure_type")
+                for p in reversed(list(patterns)):  # app.py:41-45
+                    if p.get("name") == PATTERN_NAME and bt == "HALLUCINATION_CITATION":
+                        pattern_id = p.get("pattern_id")
+                        break
+            if best and score >= threshold:
+                msg = (
+                    f"This execution matches past failure type {best.get('failure_type')} "
+                    f"(failure_id={best.get('failure_id')}, similarity={score:.2f}). "
+                    f"Suggested mitigation: {best.get('suggested_mitigation') or 'n/a'}"
+                )
+                out.append({"action": default_action, "confidence": score, "pattern_id": pattern_id,
+                            "references": [best], "message": msg})
+            else:
+                out.append({"action": "silent" if default_action == "silent" else "warn", "confidence": score,
+                            "pattern_id": pattern_id, "references": [],
+                            "message": "No high-similarity match found in GFKB."})
+        return out
+
+    def close(self) -> None:
+        with self._lock:
+            for ix in (self._main, self._tail):
+                if ix is not None:
+                    ix.close()
+            self._main = self._tail = None

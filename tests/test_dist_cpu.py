@@ -87,3 +87,28 @@ def test_shard_bounds_cover_rows():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def _gather_worker(rank, world, port, n, d, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from kakveda_b200.dist import ShardedDense, shard_bounds
+
+        full = torch.arange(n * d, dtype=torch.float32).reshape(n, d).to(torch.bfloat16)
+        lo, hi = shard_bounds(n, world, rank)
+        sh = ShardedDense(d, device=0, rank=rank, world=world)   # no index is created: only the exchange is exercised
+        sh._local, sh.n_global = full[lo:hi].contiguous(), n
+        got = sh.gather_rows()                                    # the all-gather behind all-pairs (configs[3])
+        assert got.shape == full.shape and torch.equal(got.view(torch.int16), full.view(torch.int16))
+        # all-pairs exclusion bookkeeping: query block b0.. excludes GLOBAL rows b0.., whatever the shard
+        assert [shard_bounds(n, world, w) for w in range(world)][rank] == (lo, hi)
+        Path(tmp, f"g{rank}").write_text("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 1001), (3, 10)])
+def test_allpairs_row_gather(built_lib, tmp_path, world, n):
+    mp.spawn(_gather_worker, args=(world, _free_port(), n, 64, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"g{r}").exists() for r in range(world))

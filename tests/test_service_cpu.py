@@ -1,0 +1,73 @@
+"""CPU-side checks of the widened surface: the oracle's corpus-fit / all-pairs helpers against their sklearn goldens,
+the union-find clustering (host C++ behind the C ABI) against the oracle, and the GFKB store's upsert bookkeeping
+(services/gfkb/app.py:104-147) against the record stream the reference produced -- no device calls."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import tfidf_oracle as O
+
+
+def test_oracle_corpus_fit_matches_golden(golden):
+    from kakveda_b200 import synth
+
+    g = golden("corpus_fit.json")
+    corpus = synth.corpus(g["n"])
+    S = O.corpus_fit_scores(corpus, corpus)
+    np.testing.assert_allclose(S.sum(axis=1), g["row_sums"], rtol=1e-12)
+    rows, vals = O.allpairs_topk(S, g["k"])
+    np.testing.assert_array_equal(rows, np.array(g["allpairs_rows"]))
+    np.testing.assert_allclose(vals, np.array(g["allpairs_scores"]), rtol=1e-12)
+    assert np.allclose(S, S.T, rtol=0, atol=1e-15)  # the corpus-fit measure is symmetric
+
+
+def test_cluster_topk_matches_oracle(built_lib):
+    from kakveda_b200 import patterns
+
+    rng = np.random.default_rng(5)
+    n, k = 500, 6
+    rows = rng.integers(-1, n, size=(n, k)).astype(np.int64)
+    scores = rng.random((n, k)).astype(np.float32)
+    scores[rng.random((n, k)) < 0.02] = np.nan  # NaN never links
+    for thr in (0.0, 0.5, 0.9, 0.97, 2.0):
+        labels, count = patterns.cluster_topk(rows, scores, thr)
+        want = O.components(n, rows, np.nan_to_num(scores, nan=-1.0), thr)
+        np.testing.assert_array_equal(labels, want)
+        assert count == len(set(want))
+        assert np.all(labels <= np.arange(n))  # label = smallest member
+    with pytest.raises(ValueError):
+        patterns.cluster_topk(np.array([[7]], dtype=np.int64), np.ones((1, 1), np.float32), 0.5)
+
+
+def test_pattern_payload_matches_reference_shape():
+    from kakveda_b200 import patterns
+
+    recs = [{"failure_id": "F-0002", "affected_apps": ["b", "a"]}, {"failure_id": "F-0001", "affected_apps": ["a", "c"]},
+            {"failure_id": None, "affected_apps": []}]
+    p = patterns.pattern_payload("n", recs, "d")
+    assert p == {"name": "n", "failure_ids": ["F-0001", "F-0002"], "affected_apps": ["a", "b", "c"], "description": "d"}
+
+
+def test_store_upsert_bookkeeping_matches_reference(golden, built_lib, tmp_path):
+    """Replays the reference's request stream; every returned record and the final JSONL must be identical
+    (timestamps aside).  No query is issued, so no device is needed."""
+    from kakveda_b200 import GfkbStore
+
+    g = golden("service_upsert.json")
+    path = tmp_path / "failures.jsonl"
+    st = GfkbStore(path=path)
+    for step in g["steps"]:
+        out = st.upsert(step["upsert"])
+        assert out["created"] == step["created"]
+        got = {k: v for k, v in out["failure"].items() if k not in ("created_at", "updated_at")}
+        assert got == step["failure"]
+        assert out["failure"]["created_at"].endswith("Z") or "+" in out["failure"]["created_at"]
+    lines = [json.loads(l) for l in path.read_text().splitlines()]
+    assert [{k: v for k, v in r.items() if k not in ("created_at", "updated_at")} for r in lines] == g["final_records"]
+    assert len(lines) == len(g["final_records"]) == len(st.records)
+    # queries need the device: without one the store raises instead of falling back to a CPU path
+    from kakveda_b200 import _capi
+    if _capi.load().kv_device_count() == 0:
+        with pytest.raises(RuntimeError, match="no CUDA device"):
+            st.match("alpha beta gamma")
