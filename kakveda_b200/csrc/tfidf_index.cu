@@ -21,7 +21,7 @@ using namespace kvk;
 
 namespace {
 // tile shape used by the batched scan: 128 queries, 2048-slot feature table
-constexpr int TG = 4, TLOGH = 11, TXCAP = 128;
+constexpr int TG = 4, TLOGH = 11, TXCAP = 32;  // 128 queries, 2048 slots, 32 extra entries (tf_q > 1) per tile
 using Tile = TileLayout<TG, TLOGH, TXCAP>;
 constexpr int TILE_MAX_FEATURES = (Tile::H * 5) / 8;  // load factor cap 0.625 (linear probing)
 
@@ -915,22 +915,54 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
   {
     TileDesc cur{0, 0, 0, 0};
     int cur_feats = 0;
+    struct Exc { uint32_t h, tfq, qi; };
+    std::vector<Exc> exc;                                  // (slot, tf_q > 1, query) of the tile being built
+    std::vector<std::pair<uint32_t, uint32_t>> pairs;      // its distinct (feature, tf_q > 1) pairs = extra entries needed
     new_table();
+    // extra entries of a finished tile: per feature with exceptions one entry per distinct tf_q value t > 1, holding
+    // the weight (t - 1) a(t) and the mask of the queries with exactly that tf_q; the entries of one feature are
+    // consecutive (chain flag in .y), the primary slot's key carries KEY_MULTI and the index of the first one
+    auto finish_tile = [&](TileDesc &td) {
+      unsigned char *tb = tables.data() + tables.size() - Tile::table_bytes;
+      uint32_t *keys = (uint32_t *)(tb + Tile::off_keys);
+      float *xad = (float *)(tb + Tile::off_xad);
+      uint32_t *xmask = (uint32_t *)(tb + Tile::off_xmask);
+      std::sort(exc.begin(), exc.end(), [](const Exc &a, const Exc &b) { return a.h != b.h ? a.h < b.h : (a.tfq != b.tfq ? a.tfq < b.tfq : a.qi < b.qi); });
+      int nx = 0;
+      for (size_t i = 0; i < exc.size();) {
+        const uint32_t h = exc[i].h;
+        keys[h] |= KEY_MULTI | ((uint32_t)nx << FID_BITS);
+        double a, d;
+        idf_host(ix->n_total, ix->h_df[keys[h] & FID_MASK], a, d, ix->jaccard, ix->corpus_fit);
+        while (i < exc.size() && exc[i].h == h) {
+          const uint32_t t = exc[i].tfq;
+          xad[2 * nx] = (float)((double)(t - 1) * a);
+          xad[2 * nx + 1] = 1.f;  // another entry of this feature follows (patched below for the last one)
+          for (; i < exc.size() && exc[i].h == h && exc[i].tfq == t; i++) xmask[(size_t)nx * TG + (exc[i].qi >> 5)] |= 1u << (exc[i].qi & 31);
+          nx++;
+        }
+        xad[2 * (nx - 1) + 1] = 0.f;
+      }
+      td.n_extras = nx;
+      exc.clear();
+      pairs.clear();
+    };
     for (int64_t i = 0; i < n_q; i++) {
       const QueryPrep &p = qp[(size_t)order[(size_t)i]];
       unsigned char *tb = tables.data() + tables.size() - Tile::table_bytes;
       uint32_t *keys = (uint32_t *)(tb + Tile::off_keys);
-      int fresh = 0, nx = 0;
+      int fresh = 0, newp = 0;
       if (!skip[(size_t)i]) {
         for (size_t j = 0; j < p.fid.size(); j++) {
           uint32_t f = p.fid[j];
           uint32_t h = (f * 0x9E3779B1u) >> (32 - TLOGH);
           while (keys[h] != KEY_EMPTY && (keys[h] & FID_MASK) != f) h = (h + 1) & (H - 1);
           fresh += keys[h] == KEY_EMPTY;
-          nx += p.tfq[j] > 1;
+          if (p.tfq[j] > 1) newp += std::find(pairs.begin(), pairs.end(), std::make_pair(f, p.tfq[j])) == pairs.end();
         }
       }
-      if (cur.q_count == QT || cur_feats + fresh > TILE_MAX_FEATURES || cur.n_extras + nx > TXCAP) {
+      if (cur.q_count == QT || cur_feats + fresh > TILE_MAX_FEATURES || (int)pairs.size() + newp > TXCAP) {
+        finish_tile(cur);
         tiles.push_back(cur);
         cur = TileDesc{(int)i, 0, 0, 0};
         cur_feats = 0;
@@ -942,8 +974,6 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
       if (skip[(size_t)i]) continue;
       float *ad = (float *)(tb + Tile::off_ad);
       uint32_t *masks = (uint32_t *)(tb + Tile::off_masks);
-      uint32_t *xkey = (uint32_t *)(tb + Tile::off_xkey);
-      float *xtf = (float *)(tb + Tile::off_xtf);
       for (size_t j = 0; j < p.fid.size(); j++) {
         uint32_t f = p.fid[j];
         uint32_t h = (f * 0x9E3779B1u) >> (32 - TLOGH);
@@ -958,13 +988,12 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
         }
         masks[(size_t)h * TG + (qi >> 5)] |= 1u << (qi & 31);
         if (p.tfq[j] > 1) {
-          keys[h] |= KEY_MULTI;
-          xkey[cur.n_extras] = (h << 8) | (uint32_t)qi;
-          xtf[cur.n_extras] = (float)p.tfq[j];
-          cur.n_extras++;
+          exc.push_back(Exc{h, p.tfq[j], (uint32_t)qi});
+          if (std::find(pairs.begin(), pairs.end(), std::make_pair(f, p.tfq[j])) == pairs.end()) pairs.emplace_back(f, p.tfq[j]);
         }
       }
     }
+    finish_tile(cur);
     tiles.push_back(cur);
   }
   const int64_t n_tiles = (int64_t)tiles.size();

@@ -305,9 +305,11 @@ struct TileLayout {
   static constexpr size_t off_keys = 0;
   static constexpr size_t off_ad = off_keys + sizeof(uint32_t) * H;
   static constexpr size_t off_masks = off_ad + sizeof(float2) * H;
-  static constexpr size_t off_xkey = off_masks + sizeof(uint32_t) * H * G;
-  static constexpr size_t off_xtf = off_xkey + sizeof(uint32_t) * XCAP;
-  static constexpr size_t table_bytes = off_xtf + sizeof(float) * XCAP;  // multiple of 16
+  // XCAP (<= 32) extra entries for features some query of the tile holds with tf_q > 1: (weight (t-1) a(t), chain flag)
+  // + the membership masks of the queries with that tf_q
+  static constexpr size_t off_xad = off_masks + sizeof(uint32_t) * H * G;
+  static constexpr size_t off_xmask = off_xad + sizeof(float2) * XCAP;
+  static constexpr size_t table_bytes = off_xmask + sizeof(uint32_t) * XCAP * G;  // multiple of 16
   static size_t smem_bytes(int k) { return table_bytes + (size_t)QT * k * 8 + (size_t)QT * 8 + 64; }
 };
 
@@ -348,19 +350,55 @@ __device__ __forceinline__ void set_filter(Lanes<G> &L, int g, float ks, int kr)
   L.fq[g] = ks > 0.f ? (L.jaccard ? ks * FILTER_SLACK : ks * ks * L.nq[g] * FILTER_SLACK) : -1.f;
 }
 
+// shared-memory loads through 32-bit shared-window addresses (the tile table is read-only once it is staged): keeps
+// the address arithmetic of the event loop to one multiply-add per load
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+  float2 v;
+  asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+  uint4 v;
+  asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+// values the compiler must keep in a register instead of re-deriving them inside the event loop
+__device__ __forceinline__ uint32_t pinned_lanemask_eq() {
+  uint32_t v;
+  asm volatile("mov.u32 %0, %%lanemask_eq;" : "=r"(v));
+  return v;
+}
+__device__ __forceinline__ uint32_t pinned_shared_addr(const void *p) {
+  uint32_t v;
+  asm volatile("mov.u32 %0, %1;" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return v;
+}
+
 // Walk the entries [p0,p1) of one chunk (or of one summary pseudo-row).  For every row end the
 // functor gets the per-lane sums (dot, corr include the folded universal features).
-template <int G, int LOGH, bool HAS_CORE, class RowFn>
+//
+// Lanes probe 32 stream entries in parallel; the warp then walks the hit / row-end events in stream order (sums
+// must follow each row's own entry order).  A feature for which some query of the tile has tf_q > 1 carries the
+// KEY_MULTI flag and the index of its first EXTRA entry: the primary slot adds the tf_q = 1 part for every query
+// that has the feature, each extra entry adds (t - 1) a(t) tf_c for the queries whose tf_q equals t.
+template <int G, int LOGH, int XCAP, bool HAS_CORE, class RowFn>
 __device__ __forceinline__ void scan_entries(const uint32_t *__restrict__ stream, int64_t p0, int64_t p1,
-                                             int64_t ovf_pos0, int64_t ovf_core_key, const uint32_t *s_keys,
-                                             const float2 *s_ad, const uint32_t *s_masks, const uint32_t *s_xkey,
-                                             const float *s_xtf, int n_extras, const unsigned long long *ovf_keys,
-                                             const uint32_t *ovf_vals, int n_ovf, const float (&dot0)[G],
-                                             const float (&corr0)[G], uint32_t gmask, RowFn &&on_row) {
-  // gmask: bit g set = the 32 queries of group g take part (warp-uniform); others are skipped.
+                                             int64_t ovf_pos0, int64_t ovf_core_key, uint32_t tbl, uint32_t lanebit,
+                                             const unsigned long long *ovf_keys, const uint32_t *ovf_vals, int n_ovf,
+                                             const float (&dot0)[G], const float (&corr0)[G], RowFn &&on_row) {
+  // tbl: shared-window address of the tile table (TileLayout); lanebit: 1 << lane.
   // HAS_CORE: the range starts with the chunk's shared prefix, closed by a marker entry; the sums
   // reached at the marker are the state every row of the chunk restarts from.
+  // Sums are kept for all G groups of the tile -- a group that sits a chunk out is simply not looked at by the row
+  // functor (a predicated-off add costs the same issue slot as a skipped one).
+  using TL = TileLayout<G, LOGH, XCAP>;
   constexpr int H = 1 << LOGH;
+  static_assert(G == 4, "the event loop loads the four membership words of a slot as one uint4");
   const int lane = threadIdx.x & 31;
   float dot[G], corr[G], dotc[G], corrc[G];
 #pragma unroll
@@ -370,84 +408,82 @@ __device__ __forceinline__ void scan_entries(const uint32_t *__restrict__ stream
   for (int64_t p = p0; p < p1; p += 32) {
     const uint32_t e = (p + lane < p1) ? stream[p + lane] : PAD_ENTRY;
     const uint32_t fid = (e >> 5) & FID_MASK;
-    int w = -1;  // (slot << 6) | (multi << 5) | tf  when this lane's entry is in the tile table
+    int w = -1;  // (slot << 11) | (first extra << 6) | (multi << 5) | tf  when this lane's entry is in the tile table
     if (fid < FID_CORE) {
       uint32_t h = hash_fid(fid, LOGH);
       for (;;) {
-        uint32_t key = s_keys[h];
+        const uint32_t key = lds_u32(tbl + (uint32_t)TL::off_keys + h * 4u);
         if (key == KEY_EMPTY) break;
         if ((key & FID_MASK) == fid) {
-          w = (int)((h << 6) | ((key >> 31) << 5) | (e & 31u));
+          w = (int)((h << 11) | (((key >> FID_BITS) & 31u) << 6) | ((key >> 31) << 5) | (e & 31u));
           break;
         }
         h = (h + 1) & (H - 1);
       }
     }
     const uint32_t lastmask = __ballot_sync(FULL, (e >> 31) != 0);
-    const uint32_t coremask = HAS_CORE ? __ballot_sync(FULL, fid == FID_CORE) : 0u;
-    uint32_t ev = __ballot_sync(FULL, w >= 0) | lastmask | coremask;
-    while (ev) {
-      const int j = __ffs(ev) - 1;
-      ev &= ev - 1;
-      const int wj = __shfl_sync(FULL, w, j);
-      if (wj >= 0) {
-        const int slot = wj >> 6;
-        uint32_t tf = wj & 31;
-        if (tf == TF_OVF) {
-          uint32_t fj = __shfl_sync(FULL, fid, j);
-          tf = ovf_lookup(ovf_keys, ovf_vals, n_ovf, in_core ? ovf_core_key : ovf_pos0 + row_in, fj);
-        }
-        const float2 ad = s_ad[slot];
-        const float f = (float)tf;
-        const float u = f * ad.x, v = f * f * ad.y;
-        uint32_t m[G];
-        if (G == 4) {
-          uint4 mm = *(const uint4 *)(s_masks + slot * 4);
-          m[0] = mm.x; m[1 % G] = mm.y; m[2 % G] = mm.z; m[3 % G] = mm.w;
-        } else {
-#pragma unroll
-          for (int g = 0; g < G; g++) m[g] = s_masks[slot * G + g];
-        }
-        if (!(wj & 32)) {
-#pragma unroll
-          for (int g = 0; g < G; g++)
-            if ((gmask >> g) & 1u)
-              if ((m[g] >> lane) & 1u) { dot[g] += u; corr[g] += v; }
-        } else {
-          // some query of this tile has tf_q > 1 for this feature: fetch the per-query multipliers
-          // (lanes search the tile's short exception list in parallel, then hand each match to its owner)
-          float mul[G];
-#pragma unroll
-          for (int g = 0; g < G; g++) mul[g] = 1.f;
-          for (int x0 = 0; x0 < n_extras; x0 += 32) {
-            const int x = x0 + lane;
-            const uint32_t xk = x < n_extras ? s_xkey[x] : 0xFFFFFFFFu;
-            uint32_t found = __ballot_sync(FULL, (int)(xk >> 8) == slot);
-            while (found) {
-              const int l = __ffs(found) - 1;
-              found &= found - 1;
-              const int qi = __shfl_sync(FULL, (int)(xk & 255u), l);
-              const float tfq = s_xtf[x0 + l];
-#pragma unroll
-              for (int g = 0; g < G; g++)
-                if (qi == g * 32 + lane) mul[g] = tfq;
+    const uint32_t ev_all = __ballot_sync(FULL, w >= 0) | lastmask;
+    // the core marker (once per chunk) splits its batch in two: events before it close the shared prefix
+    uint32_t ev_first = ev_all, ev_second = 0;
+    bool split = false;
+    if (HAS_CORE) {
+      const uint32_t coremask = __ballot_sync(FULL, fid == FID_CORE);
+      if (coremask) {
+        const int cj = __ffs(coremask) - 1;
+        ev_first = ev_all & ((1u << cj) - 1u);
+        ev_second = ev_all & ~((2u << cj) - 1u);
+        split = true;
+      }
+    }
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      uint32_t ev = pass == 0 ? ev_first : ev_second;
+      while (ev) {
+        const int j = __ffs(ev) - 1;
+        ev &= ev - 1;
+        const int wj = __shfl_sync(FULL, w, j);
+        if (wj >= 0) {
+          const uint32_t slot = (uint32_t)wj >> 11;
+          uint32_t tf = wj & 31;
+          if (tf == TF_OVF) {
+            uint32_t fj = __shfl_sync(FULL, fid, j);
+            tf = ovf_lookup(ovf_keys, ovf_vals, n_ovf, in_core ? ovf_core_key : ovf_pos0 + row_in, fj);
+          }
+          const uint4 mm = lds_u4(tbl + (uint32_t)TL::off_masks + slot * 16u);
+          const float2 ad = lds_f2(tbl + (uint32_t)TL::off_ad + slot * 8u);
+          const float f = (float)tf;
+          const float u = f * ad.x, v = f * f * ad.y;
+          if (mm.x & lanebit) { dot[0] += u; corr[0] += v; }
+          if (mm.y & lanebit) { dot[1] += u; corr[1] += v; }
+          if (mm.z & lanebit) { dot[2] += u; corr[2] += v; }
+          if (mm.w & lanebit) { dot[3] += u; corr[3] += v; }
+          if (wj & 32) {  // rare: the queries with tf_q = t > 1 get the remaining (t - 1) parts
+            uint32_t x = ((uint32_t)wj >> 6) & 31u;
+            for (;;) {
+              const float2 xa = lds_f2(tbl + (uint32_t)TL::off_xad + x * 8u);
+              const uint4 xm = lds_u4(tbl + (uint32_t)TL::off_xmask + x * 16u);
+              const float u2 = f * xa.x;
+              if (xm.x & lanebit) dot[0] += u2;
+              if (xm.y & lanebit) dot[1] += u2;
+              if (xm.z & lanebit) dot[2] += u2;
+              if (xm.w & lanebit) dot[3] += u2;
+              if (xa.y == 0.f) break;  // last extra entry of this feature
+              x++;
             }
           }
+        }
+        if ((lastmask >> j) & 1u) {
+          on_row(row_in, dot, corr);
 #pragma unroll
-          for (int g = 0; g < G; g++)
-            if ((m[g] >> lane) & 1u) { dot[g] += mul[g] * u; corr[g] += v; }
+          for (int g = 0; g < G; g++) { dot[g] = dotc[g]; corr[g] = corrc[g]; }
+          row_in++;
         }
       }
-      if (HAS_CORE && ((coremask >> j) & 1u)) {
+      if (!split) break;
+      if (pass == 0) {
 #pragma unroll
         for (int g = 0; g < G; g++) { dotc[g] = dot[g]; corrc[g] = corr[g]; }
         in_core = false;
-      }
-      if ((lastmask >> j) & 1u) {
-        on_row(row_in, dot, corr);
-#pragma unroll
-        for (int g = 0; g < G; g++) { dot[g] = dotc[g]; corr[g] = corrc[g]; }
-        row_in++;
       }
     }
   }
@@ -458,11 +494,8 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
   using TL = TileLayout<G, LOGH, XCAP>;
   constexpr int QT = TL::QT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t *s_keys = (uint32_t *)(smem_raw + TL::off_keys);
-  float2 *s_ad = (float2 *)(smem_raw + TL::off_ad);
-  uint32_t *s_masks = (uint32_t *)(smem_raw + TL::off_masks);
-  uint32_t *s_xkey = (uint32_t *)(smem_raw + TL::off_xkey);
-  float *s_xtf = (float *)(smem_raw + TL::off_xtf);
+  const uint32_t tbl = pinned_shared_addr(smem_raw);  // tile table (keys, (a,d), membership masks, extras)
+  const uint32_t lanebit = pinned_lanemask_eq();
   float *s_lscore = (float *)(smem_raw + TL::table_bytes);  // [QT][k]
   int *s_lrow = (int *)(s_lscore + QT * P.k);               // [QT][k]
   int *s_cnt = s_lrow + QT * P.k;                           // [QT]
@@ -525,8 +558,8 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
   auto process_chunk = [&](int64_t c, uint32_t gmask) {
     const int64_t pos0 = c * CHUNK_ROWS;
     refresh_filters();
-    scan_entries<G, LOGH, true>(P.stream, P.chunkptr[c], P.chunkptr[c + 1], pos0, (int64_t)(OVF_CORE_BASE + c), s_keys, s_ad,
-                                s_masks, s_xkey, s_xtf, td.n_extras, P.ovf_keys, P.ovf_vals, P.n_ovf, L.dotU, L.corrU, gmask,
+    scan_entries<G, LOGH, XCAP, true>(P.stream, P.chunkptr[c], P.chunkptr[c + 1], pos0, (int64_t)(OVF_CORE_BASE + c), tbl, lanebit,
+                                P.ovf_keys, P.ovf_vals, P.n_ovf, L.dotU, L.corrU,
                           [&](int row_in, const float *dot, const float *corr) {
       const float Bc = P.B32[pos0 + row_in];
 #pragma unroll
@@ -601,9 +634,9 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
       }
       // one group = SUM_GROUP chunk summaries: the features they all share are evaluated once (core), then
       // every chunk's residual -> its bound
-      scan_entries<G, LOGH, true>(P.grp_stream, P.grpptr[gg], P.grpptr[gg + 1], P.n_rows + P.n_chunks + gg * SUM_GROUP,
-                                  (int64_t)(OVF_GCORE_BASE + gg), s_keys, s_ad, s_masks, s_xkey, s_xtf, td.n_extras,
-                                  P.ovf_keys, P.ovf_vals, P.n_ovf, sd, sc0, FULL,
+      scan_entries<G, LOGH, XCAP, true>(P.grp_stream, P.grpptr[gg], P.grpptr[gg + 1], P.n_rows + P.n_chunks + gg * SUM_GROUP,
+                                  (int64_t)(OVF_GCORE_BASE + gg), tbl, lanebit,
+                                  P.ovf_keys, P.ovf_vals, P.n_ovf, sd, sc0,
                                   [&](int row_in, const float *dot, const float *corr) {
         const int64_t c = gg * SUM_GROUP + row_in;
         const float Bmin = P.chunk_minB[c];
@@ -674,8 +707,8 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
             sd[g] = P.q_dotS[q];
             sc0[g] = P.q_corrS[q];
           }
-          scan_entries<G, LOGH, false>(P.sum_stream, P.sumptr[cc], P.sumptr[cc + 1], P.n_rows + cc, 0, s_keys, s_ad, s_masks,
-                                       s_xkey, s_xtf, td.n_extras, P.ovf_keys, P.ovf_vals, P.n_ovf, sd, sc0, FULL,
+          scan_entries<G, LOGH, XCAP, false>(P.sum_stream, P.sumptr[cc], P.sumptr[cc + 1], P.n_rows + cc, 0, tbl, lanebit,
+                                       P.ovf_keys, P.ovf_vals, P.n_ovf, sd, sc0,
                                 [&](int, const float *dot, const float *corr) {
 #pragma unroll
             for (int g = 0; g < G; g++) {
