@@ -310,7 +310,7 @@ struct TileLayout {
   static constexpr size_t off_xad = off_masks + sizeof(uint32_t) * H * G;
   static constexpr size_t off_xmask = off_xad + sizeof(float2) * XCAP;
   static constexpr size_t table_bytes = off_xmask + sizeof(uint32_t) * XCAP * G;  // multiple of 16
-  static size_t smem_bytes(int k) { return table_bytes + (size_t)QT * k * 8 + (size_t)QT * 8 + 64; }
+  static size_t smem_bytes(int k) { return table_bytes + (size_t)QT * k * 8 + (size_t)QT * 8 + 288; }
 };
 
 template <int G>
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
   int *s_lock = s_cnt + QT;                                 // [QT]
   float *s_thrmin = (float *)(s_lock + QT);                 // [1] min over the tile of the k-th scores
   unsigned int *s_stat = (unsigned int *)(s_thrmin + 1);    // [4]
-  long long *s_next = (long long *)(s_stat + 5);            // [1] (8-byte aligned: s_thrmin sits on a 16-byte boundary)
+  long long *s_next = (long long *)(s_stat + 5);            // [N_LEVELS + 1] chunk cursors, one per bound level (8-byte aligned: s_thrmin sits on a 16-byte boundary)
 
   const int tile = blockIdx.x, split = blockIdx.y;
   const TileDesc td = P.tiles[tile];
@@ -611,6 +611,7 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
   };
 
   long long t_ph1 = 0, t_re = 0, t_scan = 0, t_wait = 0;  // per-warp cycle counters (profiling aid)
+  constexpr int N_LEVELS = 24;  // bound levels of the visit order
   // chunks of this split
   const int64_t n_groups = (P.n_chunks + SUM_GROUP - 1) / SUM_GROUP;
   const int64_t g_lo = n_groups * split / P.n_splits, g_hi = n_groups * (split + 1) / P.n_splits;
@@ -652,41 +653,38 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
       });
     }
     t_ph1 = clock64() - t0;
+    if (threadIdx.x <= N_LEVELS) s_next[threadIdx.x] = (long long)c_lo;
     t0 = clock64();
     __syncthreads();
     t_wait += clock64() - t0;
-    // ---- phase 2: visit chunks by descending bound; stop once no remaining chunk can beat the
-    //      weakest k-th score of the tile ----
-    constexpr int N_LEVELS = 24;
+    // ---- phase 2: visit chunks by descending bound level; a warp stops once no remaining chunk can beat the
+    //      weakest k-th score of the tile.  Every level has its own chunk cursor, so warps move on to the next
+    //      level on their own (no barrier, no idle tail per level); each warp derives the tile-wide threshold
+    //      from the shared lists itself ----
+    auto tile_threshold = [&]() {  // weakest k-th score over the tile's queries (-inf while some query lacks k candidates)
+      refresh_filters();
+      float m = INFINITY;
+#pragma unroll
+      for (int g = 0; g < G; g++)
+        if (L.valid[g]) m = fminf(m, L.filt[g]);
+      for (int o = 16; o; o >>= 1) m = fminf(m, __shfl_xor_sync(FULL, m, o));
+      return m;
+    };
     for (int lev = 0; lev <= N_LEVELS; lev++) {
       const float hi = lev == 0 ? INFINITY : 1.0f - (lev - 1) * (1.0f / (N_LEVELS - 1));
       const float lo = lev == N_LEVELS ? -INFINITY : 1.0f - lev * (1.0f / (N_LEVELS - 1));
-      // weakest threshold over the tile's queries (-inf while some query has no k candidates yet)
-      if (warp == 0) {
-        refresh_filters();
-        float m = INFINITY;
-#pragma unroll
-        for (int g = 0; g < G; g++)
-          if (L.valid[g]) m = fminf(m, L.filt[g]);
-        for (int o = 16; o; o >>= 1) m = fminf(m, __shfl_xor_sync(FULL, m, o));
-        if (lane == 0) {
-          *s_thrmin = m;
-          *s_next = (long long)c_lo;  // chunk cursor of this level (warps grab 32 chunks at a time)
-        }
-      }
-      __syncthreads();
-      const float thr_min = *s_thrmin;
-      if (hi * PRUNE_SLACK < thr_min) break;  // uniform: every remaining bound is below every k-th score
+      float thr_min = tile_threshold();
+      if (hi * PRUNE_SLACK < thr_min) break;  // every remaining bound is below every k-th score
       for (;;) {
         long long nb = 0;
-        if (lane == 0) nb = atomicAdd((unsigned long long *)s_next, 32ULL);
+        if (lane == 0) nb = atomicAdd((unsigned long long *)&s_next[lev], 32ULL);  // warps grab 32 chunks at a time
         const int64_t base = __shfl_sync(FULL, nb, 0);
         if (base >= c_hi) break;
         const int64_t c = base + lane;
         const float b = c < c_hi ? ub[c] : -INFINITY;
         const bool in_level = c < c_hi && b >= lo && (b < hi || lev == 0);  // level 0 takes +inf bounds too
-        const float tm = *(volatile float *)s_thrmin;
-        uint32_t m = __ballot_sync(FULL, in_level && b * PRUNE_SLACK >= tm);
+        uint32_t m = __ballot_sync(FULL, in_level && b * PRUNE_SLACK >= thr_min);
+        const bool visited = m != 0;
         if (lane == 0) {
           atomicAdd(&s_stat[0], (unsigned)__popc(m));
         }
@@ -731,11 +729,12 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
             atomicAdd(&s_stat[1], 1u);
           }
         }
+        if (visited) thr_min = tile_threshold();
       }
-      t0 = clock64();
-      __syncthreads();
-      t_wait += clock64() - t0;
     }
+    t0 = clock64();
+    __syncthreads();
+    t_wait += clock64() - t0;
     if (threadIdx.x == 0) s_stat[2] = (unsigned)(c_hi - c_lo);
     if (lane == 0 && P.stats) {
       atomicAdd(&P.stats[4], (unsigned long long)t_ph1);
