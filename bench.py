@@ -324,22 +324,47 @@ def run_ours(a):
             hx.match_hashes(hq, 4)
             hms.append(hx.last_timing()[0])
         hx.close()
-        # K2 (BASELINE configs[1]): 1M x 768 bf16 embeddings, 10k queries, fused top-16
+        # K2: synthetic bf16 embeddings generated ON the device (random sign/mantissa, exponent 2^-7..2^0), 1M rows at a time
         from kakveda_b200 import DenseIndex
-        dn, dd, dq = 1_000_000, 768, 10_000
-        raw = rng.integers(0, 2**16, size=(dn + dq) * dd, dtype=np.uint16)
-        emb = ((raw & np.uint16(0x807F)) | ((np.uint16(120) + ((raw >> np.uint16(7)) & np.uint16(7))) << np.uint16(7))).reshape(dn + dq, dd)
-        del raw
+        dd = 768
+
+        def dense_rows(count, seed):
+            g = torch.Generator(device=dev).manual_seed(seed)
+            raw = torch.randint(0, 2**16, (count, dd), generator=g, device=dev, dtype=torch.int32)
+            bits = (raw & 0x807F) | ((120 + ((raw >> 7) & 7)) << 7)
+            return torch.where(bits >= 32768, bits - 65536, bits).to(torch.int16).view(torch.bfloat16).contiguous()
+
+        # (BASELINE configs[1]) 1M x 768, 10k queries, fused top-16
+        dn, dq = 1_000_000, 10_000
         dxi = DenseIndex(dd, device=local)
-        dxi.add(emb[:dn])
+        dxi.add_device(dense_rows(dn, 100))
         dxi.finalize()
+        dqs = dense_rows(100_000, 999)
         dms = []
         for _ in range(3):
-            dxi.topk(emb[dn:], 16)
+            dxi.topk_device(dqs[:dq], 16)
             dms.append(dxi.last_timing()[0])
         dsplits = dxi.last_timing()[1]
+        # (BASELINE configs[3]) all-pairs on the same 1M rows: every row's 32 nearest OTHER rows (self excluded)
+        ams = []
+        for _ in range(2):
+            ap_s, ap_r = dxi.selfjoin_topk(32, device_out=True)
+            ams.append(dxi.last_timing()[0])
+        assert not bool((ap_r == torch.arange(dn, device=dev)[:, None]).any())
+        del ap_s, ap_r
+        # (BASELINE configs[2] read as dense embeddings, 1-GPU variant) 10M x 768 (15.4 GB), 100k queries, fused top-16
+        d10 = 10_000_000
+        for i in range(1, d10 // dn):
+            dxi.add_device(dense_rows(dn, 100 + i))
+        dxi.finalize()
+        d10ms = []
+        for _ in range(2):
+            dxi.topk_device(dqs, 16)
+            d10ms.append(dxi.last_timing()[0])
+        d10splits = dxi.last_timing()[1]
         dxi.close()
-        del emb
+        del dqs
+        torch.cuda.empty_cache()
         # K3 (BASELINE configs[4] shape at 1 GPU): token-set Jaccard, 1M rows x ~55 distinct tokens (64 Zipf draws over 2^20)
         from kakveda_b200 import JaccardIndex
         jn, jq, jv = 1_000_000, 2048, 1 << 20
@@ -363,13 +388,25 @@ def run_ours(a):
         jx.close()
         dflops = 2.0 * dn * dq * dd
         tpeak = float(peaks.get("bf16_tflops", 1590.0))
+        tsust = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
         secondary = {
             "k2_dense_cosine_1Mx768_10k_queries": {"kernel": "dense_topk_kernel", "ms": min(dms), "flops": dflops,
                                                    "achieved_tflops": dflops / (min(dms) / 1e3) / 1e12,
                                                    "frac_of_bf16_burst_peak": dflops / (min(dms) / 1e3) / 1e12 / tpeak,
                                                    "queries_per_s": dq / (min(dms) / 1e3), "row_splits": int(dsplits),
-                                                   "note": "tcgen05 cta_group::1 M128 N256 K16, 3-stage TMA ring, 8 epilogue warps, fused top-16; synthetic bf16 "
-                                                           "embeddings (random sign/mantissa, exponent 2^-7..2^0); parity unpinned"},
+                                                   "note": "BASELINE configs[1]; tcgen05 cta_group::1 M128 N256 K16, 3-stage TMA ring, 8 epilogue warps, fused top-16; "
+                                                           "synthetic bf16 embeddings (random sign/mantissa, exponent 2^-7..2^0); parity unpinned"},
+            "k2_dense_cosine_10Mx768_100k_queries_1gpu": {"kernel": "dense_topk_kernel", "ms": min(d10ms), "flops": 2.0 * d10 * 100_000 * dd,
+                                                          "achieved_tflops": 2.0 * d10 * 100_000 * dd / (min(d10ms) / 1e3) / 1e12,
+                                                          "frac_of_bf16_sustained_peak": 2.0 * d10 * 100_000 * dd / (min(d10ms) / 1e3) / 1e12 / tsust,
+                                                          "queries_per_s": 100_000 / (min(d10ms) / 1e3), "row_splits": int(d10splits),
+                                                          "note": "BASELINE configs[2] read as 768-d bf16 embeddings (SURVEY 8(d) cfg3, 1-GPU variant): 10M rows = 15.4 GB resident, "
+                                                                  "100k-query batch, fused top-16; kernel time only; parity unpinned"},
+            "k2_dense_allpairs_1Mx1M_top32": {"kernel": "dense_topk_kernel (self-join, own row excluded)", "ms": min(ams),
+                                              "flops": 2.0 * dn * dn * dd, "achieved_tflops": 2.0 * dn * dn * dd / (min(ams) / 1e3) / 1e12,
+                                              "frac_of_bf16_sustained_peak": 2.0 * dn * dn * dd / (min(ams) / 1e3) / 1e12 / tsust,
+                                              "rows_per_s": dn / (min(ams) / 1e3),
+                                              "note": "BASELINE configs[3]: every row's 32 nearest other rows; full N x N (symmetry not exploited); parity unpinned"},
             "k3_jaccard_1M_sets_2048_queries": {"kernel": "tfidf_topk_kernel (Jaccard mode)", "rows": jn, "queries": jq, "ms": min(jms),
                                                 "queries_per_s": jq / (min(jms) / 1e3), "avg_tokens_per_row": jentries / jn,
                                                 "bytes_per_row": 4.0 * jentries / jn + 4.0,

@@ -33,7 +33,10 @@ class DenseIndex:
 
     def add_device(self, rows) -> None:
         """Append rows that already live in HBM: a contiguous torch bfloat16 tensor [n, dim] on this device."""
+        import torch
+
         assert rows.is_cuda and rows.is_contiguous() and rows.element_size() == 2 and rows.shape[-1] == self.dim
+        torch.cuda.current_stream(rows.device).synchronize()  # the library copies on its own stream
         _capi.check(_capi.load().kv_dense_append_device(self._h, C.c_void_p(rows.data_ptr()), rows.shape[0]))
 
     def finalize(self) -> None:
@@ -46,6 +49,7 @@ class DenseIndex:
 
         assert queries.is_cuda and queries.is_contiguous() and queries.element_size() == 2 and queries.shape[-1] == self.dim
         n = queries.shape[0]
+        torch.cuda.current_stream(queries.device).synchronize()  # the library reads the queries on its own stream
         s = torch.empty((n, k), dtype=torch.float32, device=queries.device)
         r = torch.empty((n, k), dtype=torch.int64, device=queries.device)
         _capi.check(_capi.load().kv_dense_topk_device(self._h, C.c_void_p(queries.data_ptr()), n, k, exclude_base,
