@@ -65,10 +65,13 @@ __global__ void __launch_bounds__(1024) hash_scan_kernel(const ulonglong2 *__res
     for (int x = 0; x < 8; x++) {
       const int u = x >> 1, h = x & 1;
       const unsigned long long key = h ? v[u].y : v[u].x;
+      // No range or sentinel test per key: loads past the end deliver H_EMPTY, the slot after the last row is padded
+      // with H_EMPTY (kv_hash_append), and H_EMPTY can never equal a stored query key -- a probe for it stops at the
+      // first empty slot.  The common case is three 32-bit ALU ops, one LDS and one predicate per key.
+      const uint32_t lo = (uint32_t)key;
+      const uint32_t wd = s_bits[(lo >> 5) & (HQ_BIT_WORDS - 1)];
+      if (!(wd & (1u << (lo & 31u)))) continue;  // 97 % of the rows stop here (one 4-byte LDS)
       const int64_t row = 2 * (i0 + u * stride) + h;
-      if (row >= n_rows || key == H_EMPTY) continue;
-      const uint32_t b = hbit(key);
-      if (!((s_bits[b >> 5] >> (b & 31)) & 1u)) continue;  // 97 % of the rows stop here (one 4-byte LDS)
       uint32_t s = hslot(key);
       for (;;) {
         unsigned long long k = s_keys[s];
@@ -148,6 +151,7 @@ int kv_hash_append(kv_hash_index *hx, const uint64_t *hashes, int64_t n) {
     if (hashes[i] == H_EMPTY) return kv_fail(KV_ERR_INVALID, "kv_hash_append: hash 0xFFFFFFFFFFFFFFFF is reserved");
   KV_CUDA(hx->rows.reserve(hx->n_rows + n + 2, hx->stream));
   KV_CUDA(cudaMemcpyAsync(hx->rows.p + hx->n_rows, hashes, (size_t)n * 8, cudaMemcpyHostToDevice, hx->stream));
+  KV_CUDA(cudaMemsetAsync(hx->rows.p + hx->n_rows + n, 0xFF, 16, hx->stream));  // H_EMPTY padding: the scan reads row pairs
   KV_CUDA(cudaStreamSynchronize(hx->stream));
   hx->n_rows += n;
   hx->rows.n = hx->n_rows;
