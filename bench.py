@@ -57,7 +57,7 @@ def workload_config(a, world):
                     "%d-query batch (seed 0xFACADE, ~50%% exact repeats of stored rows), TF-IDF(1,2-gram) cosine, fused top-k=%d"
                     % (a.rows, a.queries, a.k),
         "rows": a.rows, "queries": a.queries, "k": a.k,
-        "parallelism": ("corpus rows sharded over %d GPU(s); queries replicated; 1 all-gather of partial top-k" % world)
+        "parallelism": ("corpus rows sharded over %d GPU(s); queries replicated; pruning bounds pushed to peer GPUs over NVLink during the scan; 1 all-gather of partial top-k" % world)
                        if getattr(a, "shard", "rows") == "rows" else
                        ("index replicated on %d GPU(s); query batch split; 1 all-gather of the results" % world),
         "l2": "inputs larger than L2 (scan stream >> 126 MB); no explicit flush",
@@ -302,7 +302,7 @@ def run_ours(a):
 
     # ---- secondary kernels of the path (rank 0): the HBM-bound single-query scan and the hash match ----
     secondary = None
-    if rank == 0:
+    if rank == 0 and world == 1:   # single-GPU runs only: keeps the multi-GPU scaling runs short
         from kakveda_b200 import HashIndex
         ix = shard.index
         sc_ms = []
@@ -431,7 +431,7 @@ def run_ours(a):
 
     if rank == 0:
         cfg = workload_config(a, world)
-        cfg.update({"index_build_s": t_build, "corpus_generate_s": t_gen, "vocab": len(shard.vocab),
+        cfg.update({"threshold_peers": int(getattr(shard, "n_threshold_peers", 0)), "index_build_s": t_build, "corpus_generate_s": t_gen, "vocab": len(shard.vocab),
                     "universal_features_folded": lay["universal_features"], "host_threads_per_rank": threads,
                     "result_checksum": checksum})
         line = {

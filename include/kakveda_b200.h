@@ -173,6 +173,19 @@ int kv_selfjoin_upload(kv_index *ix, int64_t q_begin, int64_t q_end);
 int kv_rescore_pairs(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
                      const double *q_oov_tf2, int64_t n_q, int k, const int64_t *rows, double *out_scores);
 
+/* Cross-GPU pruning thresholds for a row-sharded GFKB (one process per GPU, all ranks hold the SAME resident query
+ * batch).  Block-max pruning needs a lower bound of every query's GLOBAL k-th score; a shard scanning alone only knows
+ * its own.  export: make this index's threshold array (int32 float bits per sorted query slot, `capacity` queries)
+ * visible to the other processes -- writes a 64-byte CUDA IPC handle.  peers: map the arrays the other ranks exported
+ * (n_peers <= 7 handles of 64 bytes, same capacity); from then on every bound a scan CTA establishes is also pushed
+ * into the peers' arrays with system-scope reductions over NVLink/NVSwitch peer memory while the kernels run, so all
+ * shards prune with the best bound known anywhere (n_peers = 0 unmaps).  Results are unchanged -- a pushed value
+ * always is a valid lower bound (k rows at least that good exist in some shard) -- only less is scanned.  Callers must
+ * keep scans of different batches apart with a collective (the all-gather of partial top-k does that) and exchange
+ * again after uploading a batch larger than `capacity` (kv_topk* returns KV_ERR_STATE otherwise). */
+int kv_index_thresholds_export(kv_index *ix, int64_t capacity, void *handle_out);
+int kv_index_thresholds_peers(kv_index *ix, const void *handles, int n_peers, int64_t capacity);
+
 /* K5: merge n_lists partial top-k lists per query (device pointers; list l of query q at
  * [l*n_q*k + q*k], each sorted by (score desc,row asc)) into one [n_q*k] result with the
  * same ordering.  Used after the cross-GPU all-gather. */

@@ -106,6 +106,11 @@ struct kv_index {
   DevBuf<float> d_qconst;
   DevBuf<int> d_qperm;
   DevBuf<int> d_gthr;
+  // cross-GPU threshold exchange (row-sharded GFKB): d_gthr is exported over CUDA IPC, the peers' arrays are mapped here
+  bool gthr_exported = false;
+  int n_peers = 0;
+  int *peer_gthr[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int64_t peer_cap = 0;  // queries the exchanged arrays hold
   DevBuf<int> d_excl_sorted, d_excl_orig;  // self-join exclusions of the resident batch (by sorted slot / by original query)
   std::vector<int> h_excl_orig;
   bool has_excl = false;
@@ -132,6 +137,14 @@ struct kv_index {
   int64_t last_ctas = 0, last_tiles = 0, last_splits = 0;
   unsigned long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+
+static void close_peers(kv_index *ix) {
+  for (int i = 0; i < ix->n_peers; i++)
+    if (ix->peer_gthr[i]) cudaIpcCloseMemHandle(ix->peer_gthr[i]);
+  for (auto &p : ix->peer_gthr) p = nullptr;
+  ix->n_peers = 0;
+  ix->peer_cap = 0;
+}
 
 namespace {
 
@@ -273,6 +286,7 @@ void kv_index_destroy(kv_index *ix) {
   ix->d_ovf_keys.release(); ix->d_ovf_vals.release();
   ix->h_tables.release(); ix->h_tiles.release(); ix->h_qconst.release(); ix->h_qperm.release();
   ix->d_tables.release(); ix->d_tiles.release(); ix->d_qconst.release(); ix->d_qperm.release(); ix->d_gthr.release();
+  close_peers(ix);
   ix->d_excl_sorted.release(); ix->d_excl_orig.release(); ix->d_invperm.release();
   ix->d_rq_indptr.release(); ix->d_rq_ids.release(); ix->d_rq_tf.release(); ix->d_rq_const.release(); ix->d_rq_out.release();
   ix->d_rq_rows.release();
@@ -1041,7 +1055,11 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
   n_splits = std::max<int64_t>(1, std::min<int64_t>(n_splits, std::max<int64_t>(1, ix->n_chunks / (2 * SUM_GROUP))));
   n_splits = std::min<int64_t>(n_splits, 2048);
   ix->last_tiles = n_tiles; ix->last_splits = n_splits; ix->last_ctas = n_tiles * n_splits;
+  if (n_q > ix->d_gthr.cap && (ix->gthr_exported || ix->n_peers))
+    return kv_fail(KV_ERR_STATE, "kv_topk: the query batch outgrew the threshold array shared with the peer GPUs; exchange it again "
+                                 "(kv_index_thresholds_export / kv_index_thresholds_peers)");
   KV_CUDA(ix->d_gthr.ensure(n_q));
+  const int n_peers = (ix->n_peers > 0 && n_q <= ix->peer_cap) ? ix->n_peers : 0;
   KV_CUDA(ix->d_part_s.ensure(n_splits * n_q * k));
   KV_CUDA(ix->d_part_r.ensure(n_splits * n_q * k));
   KV_CUDA(ix->d_stats.ensure(8));
@@ -1064,6 +1082,9 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
     P.q_excl = ix->has_excl ? ix->d_excl_sorted.p : nullptr;
     P.gthr = ix->d_gthr.p; P.ubuf = ix->d_ubuf.p; P.stats = ix->d_stats.p;
     P.n_q = n_q; P.k = k; P.n_splits = (int)n_splits; P.prune = prune; P.jaccard = ix->jaccard;
+    for (int i = 0; i < 7; i++) P.peer_gthr[i] = i < n_peers ? ix->peer_gthr[i] : nullptr;
+    P.n_peers = n_peers;
+    P.share = (n_splits > 1 || n_peers > 0) ? 1 : 0;
     P.part_scores = ix->d_part_s.p; P.part_rows = ix->d_part_r.p;
     const size_t smem = Tile::smem_bytes(k);
     static bool attr_set[64] = {false};
@@ -1258,6 +1279,46 @@ int kv_topk_resident_host(kv_index *ix, int k, float *out_scores, int64_t *out_r
   KV_CUDA(cudaEventRecord(ix->ev[4], ix->stream));
   KV_CUDA(cudaStreamSynchronize(ix->stream));
   for (int i = 1; i < 4; i++) cudaEventElapsedTime(&ix->last_ms[i], ix->ev[i], ix->ev[i + 1]);
+  return KV_OK;
+}
+
+int kv_index_thresholds_export(kv_index *ix, int64_t capacity, void *handle_out) {
+  if (!ix || capacity < 1 || !handle_out) return kv_fail(KV_ERR_INVALID, "kv_index_thresholds_export: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the C ABI documents a 64-byte handle");
+  std::lock_guard<std::mutex> g(ix->mu);
+  KV_CUDA(cudaSetDevice(ix->device));
+  if (ix->n_peers) return kv_fail(KV_ERR_STATE, "kv_index_thresholds_export: clear the peer mapping first (n_peers = 0)");
+  KV_CUDA(ix->d_gthr.ensure(capacity));
+  cudaIpcMemHandle_t h;
+  KV_CUDA(cudaIpcGetMemHandle(&h, ix->d_gthr.p));
+  memcpy(handle_out, &h, sizeof(h));
+  ix->gthr_exported = true;
+  return KV_OK;
+}
+
+int kv_index_thresholds_peers(kv_index *ix, const void *handles, int n_peers, int64_t capacity) {
+  if (!ix || n_peers < 0 || n_peers > 7 || (n_peers > 0 && (!handles || capacity < 1)))
+    return kv_fail(KV_ERR_INVALID, "kv_index_thresholds_peers: bad arguments (at most 7 peers)");
+  std::lock_guard<std::mutex> g(ix->mu);
+  KV_CUDA(cudaSetDevice(ix->device));
+  KV_CUDA(cudaStreamSynchronize(ix->stream));
+  close_peers(ix);
+  if (n_peers == 0) { ix->gthr_exported = false; return KV_OK; }
+  for (int i = 0; i < n_peers; i++) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + (size_t)i * sizeof(h), sizeof(h));
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      ix->n_peers = i;
+      close_peers(ix);
+      return kv_fail(KV_ERR_CUDA, "kv_index_thresholds_peers: cudaIpcOpenMemHandle failed for peer %d: %s", i, cudaGetErrorString(e));
+    }
+    ix->peer_gthr[i] = (int *)p;
+  }
+  ix->n_peers = n_peers;
+  ix->peer_cap = capacity;
   return KV_OK;
 }
 

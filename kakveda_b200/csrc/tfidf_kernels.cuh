@@ -290,6 +290,9 @@ struct TopkParams {
   const float *q_dotS, *q_corrS;         // [n_q] start values of chunk bounds (universal + summary-universal features)
   const int *q_excl;                     // [n_q] or NULL: local ORIGINAL row a query must not match (self-join), -1 = none
   int *gthr;                             // [n_q] float bits: lower bound of the global k-th score
+  int *peer_gthr[7];                     // the same array on the other GPUs of a row-sharded GFKB (peer memory over
+  int n_peers;                           //   NVLink): a raised bound is pushed to every shard, so all of them prune with it
+  int share;                             // thresholds are exchanged (several row splits and/or peers)
   float *ubuf;                           // [n_tiles][n_chunks] chunk upper bounds (scratch)
   unsigned long long *stats;             // [0] chunks scanned, [1] chunks pruned, [2] summaries evaluated
   int64_t n_q;
@@ -536,6 +539,19 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
     set_filter<G>(L, g, L.valid[g] ? __int_as_float(P.gthr[q]) : INFINITY, 0x7fffffff);
   }
 
+  // Publish a lower bound of a query's global k-th score: locally (the CTAs scanning other row ranges) and, when it
+  // raises the local value, on every peer GPU (fire-and-forget system-scope reductions over NVLink peer memory).
+  // Valid for all shards: k rows with at least this score exist somewhere in the GFKB.
+  auto publish_threshold = [&](int64_t q, float ks) {
+    const int v = __float_as_int(ks);
+    const int old = atomicMax(&P.gthr[q], v);
+    if (old < v) {
+#pragma unroll
+      for (int p = 0; p < 7; p++)
+        if (p < P.n_peers) atomicMax_system(P.peer_gthr[p] + q, v);
+    }
+  };
+
   // pick up thresholds raised meanwhile by other warps of the CTA (shared lists) and by the CTAs
   // scanning other row ranges for the same queries (global lower bounds of the k-th score)
   auto refresh_filters = [&]() {
@@ -548,7 +564,7 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
         int kr = s_lrow[qi * k + k - 1];
         if (ks > L.filt[g] || (ks == L.filt[g] && kr < L.krow[g])) set_filter<G>(L, g, ks, kr);
       }
-      if (P.n_splits > 1) {
+      if (P.share) {
         float gs = __int_as_float(*(volatile int *)&P.gthr[td.q_begin + qi]);
         if (gs > L.filt[g]) set_filter<G>(L, g, gs, 0x7fffffff);
       }
@@ -600,7 +616,7 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
               float ks = ls[k - 1];
               int kr = lr[k - 1];
               if (ks > L.filt[g] || (ks == L.filt[g] && kr < L.krow[g])) set_filter<G>(L, g, ks, kr);
-              if (pos >= 0 && P.n_splits > 1) atomicMax(&P.gthr[td.q_begin + qi], __float_as_int(ks));
+              if (pos >= 0 && P.share) publish_threshold(td.q_begin + qi, ks);
             }
             __threadfence_block();
             atomicExch(&s_lock[qi], 0);
@@ -752,7 +768,7 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
     bool used = j < s_cnt[qi];
     P.part_scores[o] = used ? s_lscore[i] : -INFINITY;
     P.part_rows[o] = used ? (long long)(P.row_base + s_lrow[i]) : -1LL;
-    if (j == k - 1 && used) atomicMax(&P.gthr[q], __float_as_int(s_lscore[i]));
+    if (j == k - 1 && used) publish_threshold(q, s_lscore[i]);
   }
   if (threadIdx.x == 0 && P.stats) {
     // s_stat[0]: chunks that passed the tile-wide test, s_stat[1]: of those, rejected per query

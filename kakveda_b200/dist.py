@@ -18,6 +18,7 @@ CPU; the compute stays in libkakveda_b200 (CUDA only).
 from __future__ import annotations
 
 import ctypes as C
+import sys
 from typing import Optional, Tuple
 
 import numpy as np
@@ -101,6 +102,42 @@ class ShardedGfkb:
             self.index.set_global_df(df.cpu().numpy().astype(np.uint32), self.n_global)
         self.index.finalize()
 
+    def _exchange_thresholds(self, n_q: int) -> None:
+        """Row-sharded mode: map every peer's pruning-threshold array into this rank's scan kernel (CUDA IPC over
+        NVLink peer memory), so a k-th-score bound established on one GPU prunes on all of them while the kernels
+        run.  Re-done only when a batch outgrows the exchanged capacity."""
+        import os
+
+        import torch.distributed as dist
+
+        if self.world == 1 or self.mode != "rows" or os.environ.get("KAKVEDA_B200_NO_PEER_THR") == "1":
+            return
+        if n_q <= getattr(self, "_thr_cap", 0):
+            return
+        lib = _capi.load()
+        cap = max(int(n_q), 1 << 20)
+        _capi.check(lib.kv_index_thresholds_peers(self.index._h, None, 0, 0))       # unmap before re-exporting
+        dist.barrier(group=self.group)                                             # nobody pushes into an array being replaced
+        buf = C.create_string_buffer(64)
+        mine = b""
+        try:
+            _capi.check(lib.kv_index_thresholds_export(self.index._h, cap, buf))
+            mine = bytes(buf.raw)
+        except RuntimeError as e:                                                  # no CUDA IPC here: scan with local bounds only
+            print(f"[kakveda_b200] rank {self.rank}: thresholds not exported ({e})", file=sys.stderr)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine, group=self.group)
+        peers = [h for r, h in enumerate(handles) if r != self.rank and h]
+        self.n_threshold_peers = 0
+        if peers:
+            try:
+                _capi.check(lib.kv_index_thresholds_peers(self.index._h, b"".join(peers), len(peers), cap))
+                self.n_threshold_peers = len(peers)
+            except RuntimeError as e:
+                print(f"[kakveda_b200] rank {self.rank}: peer thresholds not mapped ({e})", file=sys.stderr)
+        dist.barrier(group=self.group)
+        self._thr_cap = cap
+
     def upload(self, qfb: FeatureBatch) -> None:
         if self.mode == "queries" and self.world > 1:
             # this rank's slice of the batch: re-pack the CSR rows [lo, hi)
@@ -114,6 +151,7 @@ class ShardedGfkb:
                                                      hi - lo))
             return
         self.index.upload_queries(qfb)
+        self._exchange_thresholds(qfb.n)
 
     def topk_resident(self, k: int):
         """Device-only step on the uploaded batch: local scan+merge, all-gather, global merge."""

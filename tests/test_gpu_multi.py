@@ -37,6 +37,8 @@ def _worker(rank, world, port, n, q, k, tmp, mode):
         s, r = sh.topk_packed(qbuf, qoff, k)
         np.save(Path(tmp, f"s{rank}{mode}.npy"), s)
         np.save(Path(tmp, f"r{rank}{mode}.npy"), r)
+        lay = sh.index.layout()
+        Path(tmp, f"info{rank}{mode}.txt").write_text(f"{getattr(sh, 'n_threshold_peers', 0)} {lay['chunks_scanned']}")
     finally:
         dist.destroy_process_group()
 
@@ -65,6 +67,10 @@ def test_two_rank_sharded_topk(built_lib, tmp_path, mode):
     s, r = one.topk(synth.queries(q, n), k)
     np.testing.assert_array_equal(r0, r)
     np.testing.assert_allclose(s0, s, rtol=2e-6)
+    if mode == "rows":
+        # the shards exchanged their pruning-threshold arrays over CUDA IPC (NVLink peer memory): one peer each
+        peers = [int((tmp_path / f"info{rk}{mode}.txt").read_text().split()[0]) for rk in (0, 1)]
+        assert peers == [1, 1], peers
 
 
 def _dense_worker(rank, world, port, n, d, q, tmp):
