@@ -279,7 +279,7 @@ def run_ours(a):
     achieved = compulsory / scan_s / 1e9
     traffic = ncu_issue = None
     try:  # dram__bytes_read+write of exactly this launch, from the committed ncu capture (same workload only)
-        tr = json.loads((ROOT / "profiles" / "r1e_topk_traffic.json").read_text())
+        tr = json.loads((ROOT / "profiles" / "r1h_topk_traffic.json").read_text())
         if (tr["rows"], tr["queries"], tr["k"], tr["n_gpus"]) == (a.rows, a.queries, a.k, world):
             traffic, ncu_issue = tr["traffic_bytes_per_launch"], tr["issue_active_pct"]
     except Exception:

@@ -17,8 +17,11 @@ namespace {
 
 constexpr int HQ_TILE = 4096;        // queries per pass
 constexpr int HQ_SLOTS = 8192;       // shared-memory table slots (64 KiB of keys + 32 KiB of ids)
-constexpr int HQ_BITS_LOG = 17;      // prefilter bitmap: 2^17 bits (16 KiB), <= 3 % set
-constexpr int HQ_BIT_WORDS = 1 << (HQ_BITS_LOG - 5);
+// Prefilter: two bitmaps of 2^19 bits (64 KiB each), indexed by different hash bits.  One 16 KiB bitmap had 3 % of its
+// bits set -- per key that is fine, per WARP it sent 62 % of the 32-key groups down the probe path (ncu: 42
+// instructions per key).  <= 0.8 % set per bitmap -> the second test runs for ~22 % of the warps, the probe for ~0.2 %.
+constexpr int HQ_BITS_LOG = 19;
+constexpr int HQ_BIT_WORDS = 1 << (HQ_BITS_LOG - 5);  // words per bitmap; the two bitmaps are stored back to back
 constexpr unsigned long long H_EMPTY = 0xFFFFFFFFFFFFFFFFULL;
 
 __host__ __device__ __forceinline__ uint32_t hslot(unsigned long long h) {
@@ -26,6 +29,7 @@ __host__ __device__ __forceinline__ uint32_t hslot(unsigned long long h) {
 }
 // fingerprints are sha256 prefixes (uniform bits): the low bits index the prefilter directly
 __host__ __device__ __forceinline__ uint32_t hbit(unsigned long long h) { return (uint32_t)h & ((1u << HQ_BITS_LOG) - 1); }
+__host__ __device__ __forceinline__ uint32_t hbit2(unsigned long long h) { return (uint32_t)(h >> HQ_BITS_LOG) & ((1u << HQ_BITS_LOG) - 1); }
 
 // table: keys[HQ_SLOTS] (global, built on the host), qidx[HQ_SLOTS] first query with that hash
 __global__ void __launch_bounds__(1024) hash_scan_kernel(const ulonglong2 *__restrict__ rows2, int64_t n_rows,
@@ -40,7 +44,7 @@ __global__ void __launch_bounds__(1024) hash_scan_kernel(const ulonglong2 *__res
   {
     const uint4 *src3 = (const uint4 *)t_bits;
     uint4 *dst3 = (uint4 *)s_bits;
-    for (int i = threadIdx.x; i < HQ_BIT_WORDS / 4; i += blockDim.x) dst3[i] = src3[i];
+    for (int i = threadIdx.x; i < 2 * HQ_BIT_WORDS / 4; i += blockDim.x) dst3[i] = src3[i];
     const uint4 *src = (const uint4 *)t_keys;
     uint4 *dst = (uint4 *)s_keys;
     for (int i = threadIdx.x; i < HQ_SLOTS / 2; i += blockDim.x) dst[i] = src[i];
@@ -70,7 +74,9 @@ __global__ void __launch_bounds__(1024) hash_scan_kernel(const ulonglong2 *__res
       // first empty slot.  The common case is three 32-bit ALU ops, one LDS and one predicate per key.
       const uint32_t lo = (uint32_t)key;
       const uint32_t wd = s_bits[(lo >> 5) & (HQ_BIT_WORDS - 1)];
-      if (!(wd & (1u << (lo & 31u)))) continue;  // 97 % of the rows stop here (one 4-byte LDS)
+      if (!(wd & (1u << (lo & 31u)))) continue;  // > 99 % of the rows stop here (one 4-byte LDS)
+      const uint32_t b2 = hbit2(key);
+      if (!((s_bits[HQ_BIT_WORDS + (b2 >> 5)] >> (b2 & 31u)) & 1u)) continue;
       const int64_t row = 2 * (i0 + u * stride) + h;
       uint32_t s = hslot(key);
       for (;;) {
@@ -125,7 +131,7 @@ int kv_hash_create(int device, int64_t row_base, kv_hash_index **out) {
   hx->sm_count = prop.multiProcessorCount;
   KV_CUDA(cudaStreamCreateWithFlags(&hx->stream, cudaStreamNonBlocking));
   for (auto &e : hx->ev) KV_CUDA(cudaEventCreate(&e));
-  KV_CUDA(cudaFuncSetAttribute(hash_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HQ_SLOTS * 12 + HQ_BIT_WORDS * 4));
+  KV_CUDA(cudaFuncSetAttribute(hash_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HQ_SLOTS * 12 + 2 * HQ_BIT_WORDS * 4));
   *out = hx;
   return KV_OK;
 }
@@ -170,8 +176,8 @@ int kv_hash_match(kv_hash_index *hx, const uint64_t *q_hashes, int64_t n_q, int 
   for (int64_t i = 0; i < n_q; i++) out_counts[i] = 0;
   if (n_q == 0 || hx->n_rows == 0) return KV_OK;
   KV_CUDA(hx->d_keys.ensure(HQ_SLOTS)); KV_CUDA(hx->d_qidx.ensure(HQ_SLOTS)); KV_CUDA(hx->d_count.ensure(1));
-  KV_CUDA(hx->d_bits.ensure(HQ_BIT_WORDS));
-  std::vector<uint32_t> bits(HQ_BIT_WORDS);
+  KV_CUDA(hx->d_bits.ensure(2 * HQ_BIT_WORDS));
+  std::vector<uint32_t> bits(2 * HQ_BIT_WORDS);
   unsigned int cap = 1u << 22;
   std::vector<unsigned long long> keys(HQ_SLOTS), pairs;
   std::vector<int> qidx(HQ_SLOTS);
@@ -190,6 +196,7 @@ int kv_hash_match(kv_hash_index *hx, const uint64_t *q_hashes, int64_t n_q, int 
       if (h == H_EMPTY) continue;
       uint32_t sl = hslot(h);
       bits[hbit(h) >> 5] |= 1u << (hbit(h) & 31);
+      bits[HQ_BIT_WORDS + (hbit2(h) >> 5)] |= 1u << (hbit2(h) & 31);
       while (keys[sl] != H_EMPTY && keys[sl] != h) sl = (sl + 1) & (HQ_SLOTS - 1);
       if (keys[sl] == H_EMPTY) { keys[sl] = h; qidx[sl] = (int)(q - q0); }
       same[(size_t)qidx[sl]].push_back((int)(q - q0));  // duplicates among the queries share one slot
@@ -198,10 +205,10 @@ int kv_hash_match(kv_hash_index *hx, const uint64_t *q_hashes, int64_t n_q, int 
       KV_CUDA(hx->d_pairs.ensure(cap));
       KV_CUDA(cudaMemcpyAsync(hx->d_keys.p, keys.data(), HQ_SLOTS * 8, cudaMemcpyHostToDevice, s));
       KV_CUDA(cudaMemcpyAsync(hx->d_qidx.p, qidx.data(), HQ_SLOTS * 4, cudaMemcpyHostToDevice, s));
-      KV_CUDA(cudaMemcpyAsync(hx->d_bits.p, bits.data(), HQ_BIT_WORDS * 4, cudaMemcpyHostToDevice, s));
+      KV_CUDA(cudaMemcpyAsync(hx->d_bits.p, bits.data(), 2 * HQ_BIT_WORDS * 4, cudaMemcpyHostToDevice, s));
       KV_CUDA(cudaMemsetAsync(hx->d_count.p, 0, 4, s));
       KV_CUDA(cudaEventRecord(hx->ev[0], s));
-      hash_scan_kernel<<<hx->sm_count, 1024, HQ_SLOTS * 12 + HQ_BIT_WORDS * 4, s>>>((const ulonglong2 *)hx->rows.p, hx->n_rows,
+      hash_scan_kernel<<<hx->sm_count, 1024, HQ_SLOTS * 12 + 2 * HQ_BIT_WORDS * 4, s>>>((const ulonglong2 *)hx->rows.p, hx->n_rows,
                                                                     hx->d_keys.p, hx->d_qidx.p, hx->d_bits.p, hx->d_pairs.p,
                                                                     hx->d_count.p, cap);
       KV_CUDA(cudaGetLastError());
