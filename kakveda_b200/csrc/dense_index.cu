@@ -215,7 +215,6 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     int *lr = &S.lrow[half][0][qi];
     int cur_qtile = -1, cnt = 0;
     int excl = -1;          // local row this thread's query must not match (self-join)
-    int minpos = 0;         // slot of the weakest entry once the list is full
     int64_t q = 0;
     bool q_ok = false;
     float inv_q = 0.f;
@@ -223,22 +222,8 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     float gth = -INFINITY;  // k-th score another CTA already secured for this query: ties may still win on row id
     float gth_pred = -INFINITY;  // largest float below gth
     float lo = INFINITY;         // a row enters the list iff its score > lo
-    // The list is kept UNSORTED while scanning (an accepted row overwrites the weakest entry, then the new weakest is
-    // found with k independent loads -- no dependent shift chain in the hot loop); it is sorted once, here.
     auto flush = [&]() {    // publish the list of (cur_qtile, this CTA)
       if (cur_qtile < 0 || !q_ok) return;
-      for (int a = 1; a < cnt; a++) {  // insertion sort by (score desc, row asc)
-        const float sa = ls[a * BM];
-        const int ra = lr[a * BM];
-        int b = a;
-        while (b > 0 && (ls[(b - 1) * BM] < sa || (ls[(b - 1) * BM] == sa && lr[(b - 1) * BM] > ra))) {
-          ls[b * BM] = ls[(b - 1) * BM];
-          lr[b * BM] = lr[(b - 1) * BM];
-          b--;
-        }
-        ls[b * BM] = sa;
-        lr[b * BM] = ra;
-      }
       const int slot = (int)my_split * 2 + half;
       for (int j = 0; j < k; j++) {
         const size_t o = ((size_t)slot * P.n_q + q) * k + j;
@@ -320,21 +305,15 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             for (int j = 8 * sb; j < 8 * sb + 8; j++) {
               const float sc = tv[j] * inv_q;
               if (sc > lo && (int)(row0 + c0 + j) != excl) {
-                const int pos = cnt < k ? cnt++ : minpos;  // rows ascend inside a CTA: a tie with the weakest entry loses (sc > lo)
+                int pos = cnt < k ? cnt++ : k - 1;
+                while (pos > 0 && ls[(pos - 1) * BM] < sc) {
+                  ls[pos * BM] = ls[(pos - 1) * BM];
+                  lr[pos * BM] = lr[(pos - 1) * BM];
+                  pos--;
+                }
                 ls[pos * BM] = sc;
                 lr[pos * BM] = (int)(row0 + c0 + j);
-                if (cnt == k) {  // new weakest entry: lowest score, among equals the highest row
-                  float m = ls[0];
-                  int mr = lr[0], mp = 0;
-                  for (int t2 = 1; t2 < k; t2++) {
-                    const float v2 = ls[t2 * BM];
-                    const int r2 = lr[t2 * BM];
-                    if (v2 < m || (v2 == m && r2 > mr)) { m = v2; mr = r2; mp = t2; }
-                  }
-                  minpos = mp;
-                  thr = m;
-                  lo = fmaxf(thr, gth_pred);
-                }
+                if (cnt == k) { thr = ls[(k - 1) * BM]; lo = fmaxf(thr, gth_pred); }
               }
             }
           }

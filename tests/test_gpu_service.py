@@ -287,3 +287,4 @@ def test_dense_k32_exclusion_and_device_queries(lib):
     for i in range(q):
         assert 1000 + i not in r2[i].tolist()
     np.testing.assert_array_equal(r2.cpu().numpy()[:, :8] - 1000, rs[:q, :8])
+
