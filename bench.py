@@ -298,7 +298,7 @@ def run_ours(a):
         "unbatched_rate_gbs": a.queries * rows_local * bytes_per_row / scan_s / 1e9,
         "note": "algorithmic bytes = query_tiles x rows x bytes_per_row (SURVEY 8(d): each 128-query tile would stream every "
                 "row once); block-max pruning skips ~91% of the chunks and L2 serves most re-reads, so measured DRAM traffic "
-                "is ~10x lower; the kernel is bound by instruction issue / shared-memory lookups (ncu issue-active 66%), "
+                "is ~10x lower; the kernel is bound by instruction issue / shared-memory lookups (ncu issue-active 63%), "
                 "not by HBM -- see DESIGN.md section 6",
     }
 
