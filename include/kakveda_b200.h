@@ -53,6 +53,13 @@ int kv_vocab_create(kv_vocab **out);
 void kv_vocab_destroy(kv_vocab *v);
 int64_t kv_vocab_size(const kv_vocab *v);
 
+/* Persistence of a vocabulary (binary sidecar of failures.jsonl, so that a cold start does not re-tokenise the GFKB):
+ * export writes the 128-bit key of every feature in id order (keys_out[2*id], keys_out[2*id+1]; capacity counts
+ * features); import fills an EMPTY vocabulary so that feature id i has keys[2*i..2*i+1] again -- documents
+ * featurised afterwards get the ids they had, new features continue the numbering. */
+int kv_vocab_export(const kv_vocab *v, uint64_t *keys_out, int64_t capacity);
+int kv_vocab_import(kv_vocab *v, const uint64_t *keys, int64_t n);
+
 #define KV_TEXT_RAW_ASCII 0 /* docs are raw ASCII text: lower-cased + tokenised here       */
 #define KV_TEXT_TOKENS 1    /* docs are tokens already lower-cased, separated by 0x1F (any  */
                             /* UTF-8): used by the Python shim for non-ASCII documents      */

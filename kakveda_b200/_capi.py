@@ -29,6 +29,8 @@ SIGNATURES = {
     "kv_vocab_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "kv_vocab_destroy": (None, [C.c_void_p]),
     "kv_vocab_size": (C.c_int64, [C.c_void_p]),
+    "kv_vocab_export": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int64]),
+    "kv_vocab_import": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int64]),
     "kv_featurize": (C.c_int, [C.c_void_p, C.c_char_p, c_i64p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                C.POINTER(C.c_void_p), c_i64p]),
     "kv_csr_view": (C.c_int, [C.c_void_p, c_i64p, C.POINTER(c_i64p), C.POINTER(c_u32p), C.POINTER(c_u32p),

@@ -248,6 +248,53 @@ void kv_vocab_destroy(kv_vocab *v) { delete v; }
 
 int64_t kv_vocab_size(const kv_vocab *v) { return v ? (int64_t)v->count.load() : 0; }
 
+// Sidecar support: the vocabulary is fully described by the 128-bit key of every
+// feature in id order.
+int kv_vocab_export(const kv_vocab *v, uint64_t *keys_out, int64_t capacity) {
+  if (!v || (!keys_out && capacity > 0)) return kv_fail(KV_ERR_INVALID, "kv_vocab_export: bad arguments");
+  const int64_t n = (int64_t)v->count.load();
+  if (capacity < n) return kv_fail(KV_ERR_INVALID, "kv_vocab_export: room for %lld features needed, %lld given", (long long)n,
+                                   (long long)capacity);
+  for (uint64_t i = 0; i < v->cap; i++) {
+    const uint32_t id = v->slots[i].id.load(std::memory_order_relaxed);
+    if (id == SLOT_EMPTY) continue;
+    if (id >= (uint32_t)n) return kv_fail(KV_ERR_STATE, "kv_vocab_export: vocabulary is being modified");
+    keys_out[2 * (size_t)id] = v->slots[i].k0;
+    keys_out[2 * (size_t)id + 1] = v->slots[i].k1;
+  }
+  return KV_OK;
+}
+
+int kv_vocab_import(kv_vocab *v, const uint64_t *keys, int64_t n) {
+  if (!v || n < 0 || (n > 0 && !keys)) return kv_fail(KV_ERR_INVALID, "kv_vocab_import: bad arguments");
+  if (v->count.load() != 0) return kv_fail(KV_ERR_STATE, "kv_vocab_import: the vocabulary must be empty");
+  if (n >= (int64_t)SLOT_PENDING) return kv_fail(KV_ERR_INVALID, "kv_vocab_import: too many features");
+  try {
+    v->reserve((uint64_t)n + 1024);
+  } catch (const std::bad_alloc &) {
+    return kv_fail(KV_ERR_NOMEM, "kv_vocab_import: out of memory");
+  }
+  for (int64_t id = 0; id < n; id++) {
+    const uint64_t k0 = keys[2 * id], k1 = keys[2 * id + 1];
+    uint64_t j = k0 & (v->cap - 1);
+    for (;;) {
+      const uint32_t cur = v->slots[j].id.load(std::memory_order_relaxed);
+      if (cur == SLOT_EMPTY) break;
+      if (v->slots[j].k0 == k0 && v->slots[j].k1 == k1) {
+        v->alloc(1 << 16);
+        v->count.store(0);
+        return kv_fail(KV_ERR_INVALID, "kv_vocab_import: features %u and %lld have the same key", cur, (long long)id);
+      }
+      j = (j + 1) & (v->cap - 1);
+    }
+    v->slots[j].k0 = k0; v->slots[j].k1 = k1;
+    v->slots[j].first.store(0, std::memory_order_relaxed);
+    v->slots[j].id.store((uint32_t)id, std::memory_order_relaxed);
+  }
+  v->count.store((uint32_t)n);
+  return KV_OK;
+}
+
 int kv_featurize(kv_vocab *v, const char *bytes, const int64_t *offsets, int64_t n_docs, int mode,
                  int grow, int n_threads, kv_csr **out, int64_t *bad_doc) {
   if (!v || !out || n_docs < 0 || (n_docs > 0 && (!bytes || !offsets)))

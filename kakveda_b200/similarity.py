@@ -91,6 +91,23 @@ class FeatureBatch:
             pass
 
 
+class ArrayBatch:
+    """A featurised batch held in plain NumPy arrays (same attributes as :class:`FeatureBatch`): what a sidecar
+    file stores and what ``GfkbIndex.add_features`` / ``upload_queries`` accept."""
+
+    def __init__(self, indptr: np.ndarray, ids: np.ndarray, tf: np.ndarray, oov: Optional[np.ndarray] = None):
+        self.indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        self.ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        self.tf = np.ascontiguousarray(tf, dtype=np.uint32)
+        self.n = len(self.indptr) - 1
+        self.oov = np.zeros(self.n, dtype=np.float64) if oov is None else np.ascontiguousarray(oov, dtype=np.float64)
+        if self.n < 0 or self.indptr[0] != 0 or self.indptr[-1] != len(self.ids) or len(self.ids) != len(self.tf):
+            raise ValueError("ArrayBatch: inconsistent CSR arrays")
+
+    def close(self) -> None:
+        pass
+
+
 class Vocabulary:
     """Word 1,2-gram vocabulary (feature -> uint32 id) shared by corpus rows and queries."""
 
@@ -102,6 +119,21 @@ class Vocabulary:
 
     def __len__(self) -> int:
         return int(_capi.load().kv_vocab_size(self._h))
+
+    def export_keys(self) -> np.ndarray:
+        """uint64 [V, 2]: the 128-bit key of every feature in id order (the whole state of the vocabulary)."""
+        n = len(self)
+        keys = np.zeros((n, 2), dtype=np.uint64)
+        _capi.check(_capi.load().kv_vocab_export(self._h, _ptr(keys, C.c_uint64), n))
+        return keys
+
+    @classmethod
+    def from_keys(cls, keys: np.ndarray) -> "Vocabulary":
+        """Rebuild a vocabulary from ``export_keys`` output: every feature gets its old id back."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64).reshape(-1, 2)
+        v = cls()
+        _capi.check(_capi.load().kv_vocab_import(v._h, _ptr(keys, C.c_uint64), keys.shape[0]))
+        return v
 
     def featurize_packed(self, data, offsets: np.ndarray, mode: int, grow: bool, n_threads: int = 0) -> FeatureBatch:
         lib = _capi.load()

@@ -32,6 +32,7 @@ import numpy as np
 
 from .fingerprint import signature_text as _signature_text
 from .gfkb import MATCH_LIMIT, _to_match
+from . import sidecar as _sidecar
 from .similarity import FeatureBatch, GfkbIndex, Vocabulary
 
 CANDIDATES = 16  # float32 candidates per query and segment that get re-scored in float64 (>= MATCH_LIMIT)
@@ -45,8 +46,11 @@ def _iso(dt: datetime) -> str:
 
 class GfkbStore:
     def __init__(self, path: Optional[Path] = None, device: int = 0, tail_limit: int = 65536,
-                 now: Optional[Callable[[], datetime]] = None):
+                 now: Optional[Callable[[], datetime]] = None, sidecar: Optional[Path] = None):
         self.path = Path(path) if path is not None else None
+        # optional binary sidecar (vocabulary + CSR of the rows, kakveda_b200/sidecar.py): a cold start then skips the
+        # tokenisation of every stored signature_text; it is rewritten whenever the main segment is rebuilt
+        self.sidecar_path = Path(sidecar) if sidecar is not None else None
         self.device = device
         self.tail_limit = int(tail_limit)
         self._now = now or (lambda: datetime.now(timezone.utc))  # app.py:34-35
@@ -90,8 +94,34 @@ class GfkbStore:
         self._main_df = None
         n = len(self.records)
         if n:
-            self._main = GfkbIndex(device=self.device, row_base=0, vocab=self.vocab)
-            self._main.add_texts([r["signature_text"] for r in self.records])
+            texts = [r["signature_text"] for r in self.records]
+            cached = _sidecar.load(self.sidecar_path, texts) if self.sidecar_path is not None else None
+            if cached is not None and len(self.vocab) == 0:
+                # cold start from the sidecar: the vocabulary and the first n0 rows come back as arrays
+                self.vocab.close()
+                self.vocab, head, n0 = cached
+                self._main = GfkbIndex(device=self.device, row_base=0, vocab=self.vocab)
+                self._main.add_features(head)
+                self.stats["sidecar_rows"] = n0
+                if n0 < n:
+                    rest = self.vocab.featurize(texts[n0:], grow=True)
+                    try:
+                        self._main.add_features(rest)
+                        if self.sidecar_path is not None:
+                            both = _sidecar.ArrayBatch(np.concatenate([head.indptr, rest.indptr[1:] + head.indptr[-1]]),
+                                                       np.concatenate([head.ids, rest.ids]), np.concatenate([head.tf, rest.tf]))
+                            _sidecar.save(self.sidecar_path, self.vocab, both, texts)
+                    finally:
+                        rest.close()
+            else:
+                self._main = GfkbIndex(device=self.device, row_base=0, vocab=self.vocab)
+                fb = self.vocab.featurize(texts, grow=True)
+                try:
+                    self._main.add_features(fb)
+                    if self.sidecar_path is not None:
+                        _sidecar.save(self.sidecar_path, self.vocab, fb, texts)
+                finally:
+                    fb.close()
             self._main.finalize()
             self.stats["full_rebuilds"] += 1
         self._n_main = self._n_indexed = n

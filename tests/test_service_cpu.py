@@ -71,3 +71,68 @@ def test_store_upsert_bookkeeping_matches_reference(golden, built_lib, tmp_path)
     if _capi.load().kv_device_count() == 0:
         with pytest.raises(RuntimeError, match="no CUDA device"):
             st.match("alpha beta gamma")
+
+
+def test_vocabulary_export_import_round_trip(built_lib):
+    """Sidecar support: a vocabulary rebuilt from its exported keys hands out the same ids, and keeps growing."""
+    from kakveda_b200 import synth
+    from kakveda_b200.similarity import Vocabulary
+
+    corpus = synth.corpus(3000) + ["Ünïcödé naïve café", "tok " * 40 + "end"]
+    a = Vocabulary()
+    fa = a.featurize(corpus, grow=True)
+    keys = a.export_keys()
+    assert keys.shape == (len(a), 2) and len({(int(x), int(y)) for x, y in keys}) == len(a)
+    b = Vocabulary.from_keys(keys)
+    assert len(b) == len(a)
+    fb = b.featurize(corpus, grow=False)
+    np.testing.assert_array_equal(fa.indptr, fb.indptr)
+    np.testing.assert_array_equal(fa.ids, fb.ids)
+    np.testing.assert_array_equal(fa.tf, fb.tf)
+    assert not fb.oov.any()
+    # new text: both vocabularies assign the same NEW ids (numbering continues after the imported features)
+    more = synth.queries(200, 3000) + ["completely new words zzzqqq yyyxxx"]
+    ga, gb = a.featurize(more, grow=True), b.featurize(more, grow=True)
+    np.testing.assert_array_equal(ga.ids, gb.ids)
+    assert len(a) == len(b) > len(keys)
+    # error conventions
+    with pytest.raises(RuntimeError):
+        b_keys = b.export_keys()
+        from kakveda_b200 import _capi
+        import ctypes as C
+        _capi.check(_capi.load().kv_vocab_import(b._h, b_keys.ctypes.data_as(C.POINTER(C.c_uint64)), len(b_keys)))  # not empty
+    with pytest.raises(ValueError):
+        Vocabulary.from_keys(np.array([[1, 2], [1, 2]], dtype=np.uint64))                                     # duplicate key
+
+
+def test_sidecar_save_load_and_staleness(built_lib, tmp_path):
+    from kakveda_b200 import sidecar, synth
+    from kakveda_b200.similarity import Vocabulary
+
+    texts = synth.corpus(500)
+    v = Vocabulary()
+    fb = v.featurize(texts, grow=True)
+    p = tmp_path / "failures.kvb.npz"
+    sidecar.save(p, v, fb, texts)
+    got = sidecar.load(p, texts)
+    assert got is not None
+    v2, batch, n0 = got
+    assert n0 == 500 and len(v2) == len(v)
+    np.testing.assert_array_equal(batch.indptr, fb.indptr)
+    np.testing.assert_array_equal(batch.ids, fb.ids)
+    np.testing.assert_array_equal(batch.tf, fb.tf)
+    # an appended JSONL is a valid extension (GFKB is append-only): the sidecar covers its first 500 rows
+    more = texts + synth.queries(20, 500)
+    got = sidecar.load(p, more)
+    assert got is not None and got[2] == 500
+    rest = got[0].featurize(more[500:], grow=True)
+    want = v.featurize(more[500:], grow=True)
+    np.testing.assert_array_equal(rest.ids, want.ids)
+    # anything else is stale: an edited row, a shorter file, a missing or corrupt sidecar
+    edited = list(texts)
+    edited[17] += " changed"
+    assert sidecar.load(p, edited) is None
+    assert sidecar.load(p, texts[:499]) is None
+    assert sidecar.load(tmp_path / "absent.npz", texts) is None
+    (tmp_path / "bad.npz").write_bytes(b"not an npz")
+    assert sidecar.load(tmp_path / "bad.npz", texts) is None
