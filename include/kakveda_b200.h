@@ -211,7 +211,7 @@ int kv_index_last_score_ms(const kv_index *ix, float *ms);
  * bytes[3] = chunk summaries (pseudo-rows + pointers + min norms).
  * counts[0] = stored entries, [1] = folded (universal) features, [2] = rows, [3] = CTAs of the
  * last scan launch, [4] = its query tiles, [5] = its row splits, [6] = host->device bytes of the
- * last query upload, [7] = tf-overflow entries, [8] = chunks (128 rows each), and for the last
+ * last query upload, [7] = tf-overflow entries, [8] = chunks (64 rows each), and for the last
  * scan summed over CTAs: [9] = chunks scanned, [10] = chunks pruned, [11] = summaries evaluated,
  * [12] = 32-query groups active in the scanned chunks (of 4 per chunk), [13..16] = warp-cycles
  * spent in: bound pass, per-query bound re-evaluation, chunk scans, barrier waits. */

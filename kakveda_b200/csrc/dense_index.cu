@@ -7,16 +7,17 @@
 //
 // scores[q, r] = <Q[q,:], C[r,:]> / (|Q[q]| |C[r]|): a bf16 GEMM Q * C^T with fp32 accumulation, the
 // norms applied as fp32 scales in the epilogue, and the top-k fused into the epilogue so that the
-// [Q, N] score matrix never exists.  The (query tile, row tile) space is linearised query-tile-major and
-// cut into one contiguous slice per SM (persistent CTAs, no wave tail); a CTA therefore sees long row
-// ranges of at most a few query tiles, which keeps its k-th-score thresholds high.  Per CTA:
-//   warp 0      TMA producer: K-slices (64 elements) of the query tile and of the row tile -> 4-stage
+// [Q, N] score matrix never exists.  A work item is one (128-query tile, row split); items are ordered
+// split-major so that the CTAs resident together (one per SM) stream the same corpus rows through L2.  Few, long
+// row splits keep every list's k-th-score threshold high.  Per CTA (320 threads):
+//   warp 0      TMA producer: K-slices (64 elements) of the query tile and of the row tile -> 3-stage
 //               shared-memory ring (128B-swizzled), mbarrier expect_tx / complete_tx
 //   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16, accumulators in TMEM
 //               (2 x 256 columns, double buffered); tcgen05.commit releases ring slots / publishes a tile
-//   warps 2-5   epilogue: tcgen05.ld of the thread's TMEM lane (= its query), scale, threshold test,
-//               insertion into the thread's own top-k list (ties keep the lower row)
-// Each (query tile, CTA) pair writes one partial list; K5 (kv_merge_topk_device) merges them.  CTAs
+//   warps 2-9   epilogue (two warps per TMEM lane quarter, each scanning half of the 256 columns): tcgen05.ld of
+//               the thread's TMEM lane (= its query), scale, threshold test, insertion into the thread's own sorted
+//               top-k list (k <= 32; ties keep the lower row; a self-join skips the query's own row)
+// Each (query tile, split, column half) writes one partial list; K5 (kv_merge_topk_device) merges them.  CTAs
 // working on the same queries exchange k-th-score lower bounds through global memory (gthr).
 #include "kv_cuda.cuh"
 
