@@ -4,6 +4,7 @@
 // device, text-order sort of the rows and chunk summaries on the host cores), per-batch query
 // preparation (per-query constants in float64, tile tables) and kernel launches.
 #include "tfidf_kernels.cuh"
+#include "tile_builder.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -18,27 +19,15 @@
 #include <vector>
 
 using namespace kvk;
+using namespace kvh;  // tile shape, QueryPrep, idf_host, parallel_for, tile builders (tile_builder.cuh)
 
 namespace {
-// tile shape used by the batched scan: 128 queries, 2048-slot feature table
-constexpr int TG = 4, TLOGH = 11, TXCAP = 32;  // 128 queries, 2048 slots, 32 extra entries (tf_q > 1) per tile
-using Tile = TileLayout<TG, TLOGH, TXCAP>;
-constexpr int TILE_MAX_FEATURES = (Tile::H * 5) / 8;  // load factor cap 0.625 (linear probing)
-
 int host_threads() {
   int t = (int)std::thread::hardware_concurrency();
   if (const char *e = getenv("KAKVEDA_B200_THREADS")) t = atoi(e);
   return std::max(1, std::min(t, 64));
 }
 
-template <class F>
-void parallel_for(int64_t n, int T, F &&body) {  // body(t, begin, end); thread t owns [n*t/T, n*(t+1)/T)
-  T = (int)std::max<int64_t>(1, std::min<int64_t>(T, n));
-  std::vector<std::thread> th;
-  for (int t = 1; t < T; t++) th.emplace_back([&, t] { body(t, n * t / T, n * (t + 1) / T); });
-  body(0, 0, n / T);
-  for (auto &x : th) x.join();
-}
 }  // namespace
 
 // ----------------------------------------------------------------------------------------
@@ -147,21 +136,6 @@ static void close_peers(kv_index *ix) {
 }
 
 namespace {
-
-struct QueryPrep {
-  double nq = 0, dotU = 0, corrU = 0, dotS = 0, corrS = 0;  // S: bound start = universal + summary-universal part
-  std::vector<uint32_t> fid;  // non-universal, in-vocabulary features
-  std::vector<uint32_t> tfq;
-};
-
-inline void idf_host(int64_t n_total, uint32_t df, double &a, double &d, int jaccard, int corpus_fit) {
-  if (jaccard) { a = 1.0; d = 0.0; return; }
-  double num = (double)(n_total + (corpus_fit ? 1 : 2));
-  double ib = std::log(num / ((double)df + 1.0)) + 1.0;
-  double iq = corpus_fit ? ib : std::log(num / ((double)df + 2.0)) + 1.0;
-  a = iq * iq;
-  d = a - ib * ib;
-}
 
 void prep_query(const kv_index *ix, const uint32_t *ids, const uint32_t *tf, int64_t nnz, double oov_tf2,
                 QueryPrep &out) {
@@ -856,7 +830,6 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
   if (n_q >= (1LL << 31)) return kv_fail(KV_ERR_INVALID, "kv_topk: too many queries in one call");
   KV_CUDA(cudaSetDevice(ix->device));
   cudaStream_t s = ix->stream;
-  const int QT = Tile::QT, H = Tile::H;
   ix->batch_valid = false;
   ix->has_excl = false;
   ix->irr_q.clear(); ix->irr_indptr.assign(1, 0); ix->irr_ids.clear(); ix->irr_tf.clear(); ix->irr_oov.clear();
@@ -882,10 +855,10 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
   std::vector<short> qcls((size_t)n_q);
   for (int64_t q = 0; q < n_q; q++)
     qcls[(size_t)q] = qp[(size_t)q].nq > 0 ? (short)std::floor(std::log2(qp[(size_t)q].nq) * 2.0) : (short)-1000;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+  stable_sort_indices(order, [&](int a, int b) {
     if (qcls[(size_t)a] != qcls[(size_t)b]) return qcls[(size_t)a] < qcls[(size_t)b];
     return cmp_seq(q_ids + q_indptr[a], q_indptr[a + 1] - q_indptr[a], q_ids + q_indptr[b], q_indptr[b + 1] - q_indptr[b]) < 0;
-  });
+  }, T);  // == std::stable_sort, on all host threads
   float *c_nq = ix->h_qconst.p, *c_dotU = c_nq + n_q, *c_corrU = c_dotU + n_q, *c_ninf = c_corrU + n_q;
   float *c_dotS = c_ninf + n_q, *c_corrS = c_dotS + n_q;
   int *qperm = ix->h_qperm.p, *null_list = qperm + n_q;
@@ -918,97 +891,14 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
       skip[(size_t)i] = 1;
     }
   }
-  // tiles: consecutive sorted queries, closed when 128 queries are in or the feature table is full
+  // tiles: consecutive sorted queries, closed when 128 queries are in or the feature table is full (tile_builder.cuh:
+  // built on all host threads when no table cap is hit, else by the sequential rule -- identical bytes either way)
   std::vector<TileDesc> tiles;
   std::vector<unsigned char> tables;
-  auto new_table = [&]() {
-    size_t o = tables.size();
-    tables.resize(o + Tile::table_bytes, 0);
-    memset(tables.data() + o + Tile::off_keys, 0xFF, sizeof(uint32_t) * H);
-  };
   {
-    TileDesc cur{0, 0, 0, 0};
-    int cur_feats = 0;
-    struct Exc { uint32_t h, tfq, qi; };
-    std::vector<Exc> exc;                                  // (slot, tf_q > 1, query) of the tile being built
-    std::vector<std::pair<uint32_t, uint32_t>> pairs;      // its distinct (feature, tf_q > 1) pairs = extra entries needed
-    new_table();
-    // extra entries of a finished tile: per feature with exceptions one entry per distinct tf_q value t > 1, holding
-    // the weight (t - 1) a(t) and the mask of the queries with exactly that tf_q; the entries of one feature are
-    // consecutive (chain flag in .y), the primary slot's key carries KEY_MULTI and the index of the first one
-    auto finish_tile = [&](TileDesc &td) {
-      unsigned char *tb = tables.data() + tables.size() - Tile::table_bytes;
-      uint32_t *keys = (uint32_t *)(tb + Tile::off_keys);
-      float *xad = (float *)(tb + Tile::off_xad);
-      uint32_t *xmask = (uint32_t *)(tb + Tile::off_xmask);
-      std::sort(exc.begin(), exc.end(), [](const Exc &a, const Exc &b) { return a.h != b.h ? a.h < b.h : (a.tfq != b.tfq ? a.tfq < b.tfq : a.qi < b.qi); });
-      int nx = 0;
-      for (size_t i = 0; i < exc.size();) {
-        const uint32_t h = exc[i].h;
-        keys[h] |= KEY_MULTI | ((uint32_t)nx << FID_BITS);
-        double a, d;
-        idf_host(ix->n_total, ix->h_df[keys[h] & FID_MASK], a, d, ix->jaccard, ix->corpus_fit);
-        while (i < exc.size() && exc[i].h == h) {
-          const uint32_t t = exc[i].tfq;
-          xad[2 * nx] = (float)((double)(t - 1) * a);
-          xad[2 * nx + 1] = 1.f;  // another entry of this feature follows (patched below for the last one)
-          for (; i < exc.size() && exc[i].h == h && exc[i].tfq == t; i++) xmask[(size_t)nx * TG + (exc[i].qi >> 5)] |= 1u << (exc[i].qi & 31);
-          nx++;
-        }
-        xad[2 * (nx - 1) + 1] = 0.f;
-      }
-      td.n_extras = nx;
-      exc.clear();
-      pairs.clear();
-    };
-    for (int64_t i = 0; i < n_q; i++) {
-      const QueryPrep &p = qp[(size_t)order[(size_t)i]];
-      unsigned char *tb = tables.data() + tables.size() - Tile::table_bytes;
-      uint32_t *keys = (uint32_t *)(tb + Tile::off_keys);
-      int fresh = 0, newp = 0;
-      if (!skip[(size_t)i]) {
-        for (size_t j = 0; j < p.fid.size(); j++) {
-          uint32_t f = p.fid[j];
-          uint32_t h = (f * 0x9E3779B1u) >> (32 - TLOGH);
-          while (keys[h] != KEY_EMPTY && (keys[h] & FID_MASK) != f) h = (h + 1) & (H - 1);
-          fresh += keys[h] == KEY_EMPTY;
-          if (p.tfq[j] > 1) newp += std::find(pairs.begin(), pairs.end(), std::make_pair(f, p.tfq[j])) == pairs.end();
-        }
-      }
-      if (cur.q_count == QT || cur_feats + fresh > TILE_MAX_FEATURES || (int)pairs.size() + newp > TXCAP) {
-        finish_tile(cur);
-        tiles.push_back(cur);
-        cur = TileDesc{(int)i, 0, 0, 0};
-        cur_feats = 0;
-        new_table();
-        tb = tables.data() + tables.size() - Tile::table_bytes;
-        keys = (uint32_t *)(tb + Tile::off_keys);
-      }
-      const int qi = cur.q_count++;
-      if (skip[(size_t)i]) continue;
-      float *ad = (float *)(tb + Tile::off_ad);
-      uint32_t *masks = (uint32_t *)(tb + Tile::off_masks);
-      for (size_t j = 0; j < p.fid.size(); j++) {
-        uint32_t f = p.fid[j];
-        uint32_t h = (f * 0x9E3779B1u) >> (32 - TLOGH);
-        while (keys[h] != KEY_EMPTY && (keys[h] & FID_MASK) != f) h = (h + 1) & (H - 1);
-        if (keys[h] == KEY_EMPTY) {
-          keys[h] = f;
-          double a, d;
-          idf_host(ix->n_total, ix->h_df[f], a, d, ix->jaccard, ix->corpus_fit);
-          ad[2 * h] = (float)a;
-          ad[2 * h + 1] = (float)d;
-          cur_feats++;
-        }
-        masks[(size_t)h * TG + (qi >> 5)] |= 1u << (qi & 31);
-        if (p.tfq[j] > 1) {
-          exc.push_back(Exc{h, p.tfq[j], (uint32_t)qi});
-          if (std::find(pairs.begin(), pairs.end(), std::make_pair(f, p.tfq[j])) == pairs.end()) pairs.emplace_back(f, p.tfq[j]);
-        }
-      }
-    }
-    finish_tile(cur);
-    tiles.push_back(cur);
+    const TileCtx cx{ix->n_total, ix->h_df.data(), ix->jaccard, ix->corpus_fit};
+    if (getenv("KAKVEDA_B200_SERIAL_TILES") || !build_tiles_parallel(cx, qp, order, skip, T, tiles, tables))
+      build_tiles_serial(cx, qp, order, skip, tiles, tables);
   }
   const int64_t n_tiles = (int64_t)tiles.size();
   KV_CUDA(ix->h_tables.ensure(n_tiles * (int64_t)Tile::table_bytes));

@@ -139,3 +139,20 @@ def test_gfkb_match_semantics(golden):
         got = gfkb.match_records(OracleEngine(), case["signature_text"], g["records"], case["failure_type"])
         assert got == case["matches"]
     assert gfkb.match_records(OracleEngine(), "x", []) == []
+
+
+def test_tile_builder_matches_recorded_implementation(tmp_path):
+    """Host-side batch preparation (kakveda_b200/csrc/tile_builder.cuh): the sequential tile builder reproduces,
+    byte for byte, the implementation the GPU parity tests and benchmarks were recorded with; the multi-threaded
+    builder and the parallel index sort equal their sequential counterparts (tests/cpp/tile_builder_check.cu)."""
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = tmp_path / "tile_builder_check"
+    src = REPO / "tests" / "cpp" / "tile_builder_check.cu"
+    subprocess.run([nvcc, "-O2", "-std=c++17", "--expt-relaxed-constexpr", "-Xcompiler", "-pthread", "-w", "-o", str(exe), str(src)],
+                   check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "all tile-builder cases passed" in out.stdout
