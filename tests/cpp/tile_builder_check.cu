@@ -2,7 +2,7 @@
 // in kakveda_b200/csrc/tile_builder.cuh:
 //   * build_tiles_serial must reproduce, byte for byte, the tile builder that ran inside prepare_batch when the GPU
 //     parity tests and benchmarks of round 1 were recorded (kept verbatim below as build_tiles_original, taken from
-//     git revision 1f1c9b5..: kakveda_b200/csrc/tfidf_index.cu);
+//     git revision 8b6e3da, kakveda_b200/csrc/tfidf_index.cu::prepare_batch);
 //   * build_tiles_parallel must equal build_tiles_serial whenever it reports success, and must report failure when a
 //     table cap would have closed a tile early;
 //   * stable_sort_indices must equal std::stable_sort.
