@@ -194,12 +194,48 @@ bool tokenize(const char *doc, int64_t len, int mode, std::string &buf,
 }
 
 // Distinct features of one document with counts, in order of first appearance in the text.
+// Positions interleave 1-grams and 2-grams in token order (t0, t0 t1, t1, t1 t2, ...): rows that share a text prefix
+// share a prefix of their feature lists, which the device index factors out per chunk.
 void doc_features(const std::string &buf, const std::vector<std::pair<uint32_t, uint32_t>> &spans,
                   std::string &scratch, std::vector<Feat> &occ, std::vector<Feat> &out) {
-  occ.clear();
   uint64_t h[2];
-  // positions interleave 1-grams and 2-grams in token order (t0, t0 t1, t1, t1 t2, ...): rows that share
-  // a text prefix share a prefix of their feature lists, which the device index factors out per chunk
+  const size_t n_occ = spans.empty() ? 0 : 2 * spans.size() - 1;
+  constexpr size_t LT = 1024;  // slots of the per-document table (load <= 0.5)
+  if (n_occ <= LT / 2) {
+    // common case (a signature_text has ~40 tokens): walk the occurrences in position order and count them in a small
+    // open-addressing table on the stack -- the first occurrence appends the feature, so `out` is already ordered
+    uint32_t slot[LT];  // index into out (relative to w) + 1, 0 = empty
+    memset(slot, 0, sizeof(slot));
+    const size_t w = out.size();
+    auto add = [&](uint64_t h0, uint64_t h1, uint32_t pos) {
+      size_t j = (size_t)h0 & (LT - 1);
+      for (;;) {
+        const uint32_t s = slot[j];
+        if (s == 0) {
+          out.push_back({h0, h1, 1, pos});
+          slot[j] = (uint32_t)(out.size() - w);
+          return;
+        }
+        Feat &f = out[w + s - 1];
+        if (f.h0 == h0 && f.h1 == h1) { f.tf++; return; }
+        j = (j + 1) & (LT - 1);
+      }
+    };
+    for (size_t i = 0; i < spans.size(); i++) {
+      hash128(buf.data() + spans[i].first, spans[i].second - spans[i].first, 0x6b616b76ULL, h);
+      add(h[0], h[1], (uint32_t)(2 * i));
+      if (i + 1 < spans.size()) {
+        scratch.assign(buf, spans[i].first, spans[i].second - spans[i].first);
+        scratch.push_back(' ');
+        scratch.append(buf, spans[i + 1].first, spans[i + 1].second - spans[i + 1].first);
+        hash128(scratch.data(), scratch.size(), 0x6b616b76ULL, h);
+        add(h[0], h[1], (uint32_t)(2 * i + 1));
+      }
+    }
+    return;
+  }
+  // long documents: sort the occurrences by key, count runs, restore the order of first appearance
+  occ.clear();
   for (size_t i = 0; i < spans.size(); i++) {
     hash128(buf.data() + spans[i].first, spans[i].second - spans[i].first, 0x6b616b76ULL, h);
     occ.push_back({h[0], h[1], 1, (uint32_t)(2 * i)});
