@@ -46,8 +46,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=50_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--shard", default="rows", choices=["rows", "queries"],
-                    help="rows: corpus rows sharded over the GPUs (BASELINE configs[2]); queries: index replicated, queries split")
+    ap.add_argument("--shard", default="rows", choices=["rows", "queries", "rows-text"],
+                    help="rows: corpus rows sharded over the GPUs by row index (BASELINE configs[2]); rows-text: sharded by ranges of "
+                         "the global text order (tighter chunks per shard); queries: index replicated, queries split")
     return ap.parse_args()
 
 
@@ -58,7 +59,7 @@ def workload_config(a, world):
                     % (a.rows, a.queries, a.k),
         "rows": a.rows, "queries": a.queries, "k": a.k,
         "parallelism": ("corpus rows sharded over %d GPU(s); queries replicated; pruning bounds pushed to peer GPUs over NVLink during the scan; 1 all-gather of partial top-k" % world)
-                       if getattr(a, "shard", "rows") == "rows" else
+                       if getattr(a, "shard", "rows").startswith("rows") else
                        ("index replicated on %d GPU(s); query batch split; 1 all-gather of the results" % world),
         "l2": "inputs larger than L2 (scan stream >> 126 MB); no explicit flush",
     }
@@ -249,7 +250,8 @@ def run_ours(a):
     t0 = time.perf_counter()
     buf, off = synth.signatures_packed(synth.CORPUS_SEED, 0, a.rows)
     t_gen = time.perf_counter() - t0
-    shard = ShardedGfkb(device=local, rank=rank, world=world, mode=a.shard)
+    shard = ShardedGfkb(device=local, rank=rank, world=world, mode=a.shard.split("-")[0],
+                        order="text" if a.shard.endswith("-text") else "index")
     t0 = time.perf_counter()
     shard.build_packed(buf, off, 0, n_threads=threads)
     t_build = time.perf_counter() - t0

@@ -81,6 +81,14 @@ int kv_csr_view(const kv_csr *c, int64_t *n_docs, const int64_t **indptr, const 
                 const uint32_t **tf, const double **oov_tf2);
 void kv_csr_destroy(kv_csr *c);
 
+/* Host-only helpers for sharding a GFKB by TEXT RANGE (kakveda_b200/dist.py, order="text"; no device involved):
+ * kv_text_order: perm_out[i] = the row at position i when the rows are sorted by their feature-id sequence (the
+ * text order the scan layout uses; equal rows by row index).  kv_csr_gather_rows: copy the rows `rows[0..n_sel)` of a
+ * CSR into out_* (out_indptr[n_sel+1] prepared by the caller from the row lengths). */
+int kv_text_order(const int64_t *indptr, const uint32_t *ids, int64_t n_rows, int32_t *perm_out, int n_threads);
+int kv_csr_gather_rows(const int64_t *indptr, const uint32_t *ids, const uint32_t *tf, int64_t n_rows, const int64_t *rows,
+                       int64_t n_sel, const int64_t *out_indptr, uint32_t *out_ids, uint32_t *out_tf, int n_threads);
+
 /* ------------------------------------------------------------------------------------
  * TF-IDF cosine index (kernels K1a/K1b/K5): replaces the arithmetic of
  * SimilarityEngine.score -- TfidfTransformer.fit/transform (sklearn text.py:1650-1739),

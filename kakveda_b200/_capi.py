@@ -36,6 +36,8 @@ SIGNATURES = {
     "kv_csr_view": (C.c_int, [C.c_void_p, c_i64p, C.POINTER(c_i64p), C.POINTER(c_u32p), C.POINTER(c_u32p),
                               C.POINTER(c_f64p)]),
     "kv_csr_destroy": (None, [C.c_void_p]),
+    "kv_text_order": (C.c_int, [c_i64p, c_u32p, C.c_int64, C.POINTER(C.c_int32), C.c_int]),
+    "kv_csr_gather_rows": (C.c_int, [c_i64p, c_u32p, c_u32p, C.c_int64, c_i64p, C.c_int64, c_i64p, c_u32p, c_u32p, C.c_int]),
     "kv_index_create": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
     "kv_index_destroy": (None, [C.c_void_p]),
     "kv_index_append": (C.c_int, [C.c_void_p, c_i64p, c_u32p, c_u32p, C.c_int64]),

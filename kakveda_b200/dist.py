@@ -24,11 +24,19 @@ from typing import Optional, Tuple
 import numpy as np
 
 from . import _capi
-from .similarity import FeatureBatch, GfkbIndex, Vocabulary
+from .similarity import FeatureBatch, GfkbIndex, Vocabulary, gather_rows, text_order
 
 
 def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
     return n_rows * rank // world, n_rows * (rank + 1) // world
+
+
+def shard_rows_by_text(batch, world: int, rank: int, n_threads: int = 0) -> np.ndarray:
+    """int64, ascending: the global row ids of the ``rank``-th range of the corpus' text order (every rank computes
+    the same order from the same featurised corpus, so the shards partition the rows without any exchange)."""
+    perm = text_order(batch, n_threads)
+    lo, hi = shard_bounds(batch.n, world, rank)
+    return np.sort(perm[lo:hi].astype(np.int64))
 
 
 def allreduce_df(local_df, group=None):
@@ -78,10 +86,19 @@ class ShardedGfkb:
     this mode scales almost linearly; it is offered because the index is so small, not used for the headline.
     """
 
-    def __init__(self, device: int, rank: int = 0, world: int = 1, group=None, mode: str = "rows"):
+    def __init__(self, device: int, rank: int = 0, world: int = 1, group=None, mode: str = "rows", order: str = "index"):
         if mode not in ("rows", "queries"):
             raise ValueError("mode must be 'rows' or 'queries'")
+        if order not in ("index", "text"):
+            raise ValueError("order must be 'index' or 'text'")
         self.mode = mode
+        # order="text" (rows mode): rank r owns the r-th RANGE OF THE GLOBAL TEXT ORDER instead of a range of row
+        # indices.  Near-duplicate rows then sit in one shard and its 64-row chunks are as tight as the single
+        # index's, which is what block-max pruning lives on; the rows keep their global ids (local results are
+        # mapped through `row_map` before the all-gather; ties still order by global id because every shard keeps
+        # its rows in ascending global order).  Host-only preparation, no kernel is involved.
+        self.order = order
+        self.row_map = None
         self.device, self.rank, self.world, self.group = device, rank, world, group
         self.vocab = Vocabulary()
         self.index: Optional[GfkbIndex] = None
@@ -93,8 +110,14 @@ class ShardedGfkb:
         fb = self.vocab.featurize_packed(data, offsets, mode, grow=True, n_threads=n_threads)
         self.n_global = fb.n
         lo, hi = shard_bounds(fb.n, self.world, self.rank) if self.mode == "rows" else (0, fb.n)
-        self.index = GfkbIndex(device=self.device, row_base=lo, vocab=self.vocab)
-        self.index.add_features(fb, lo, hi)
+        if self.mode == "rows" and self.order == "text" and self.world > 1:
+            sel = shard_rows_by_text(fb, self.world, self.rank, n_threads)
+            self.index = GfkbIndex(device=self.device, row_base=0, vocab=self.vocab)
+            self.index.add_features(gather_rows(fb, sel, n_threads))
+            self.row_map = torch.from_numpy(sel).to(f"cuda:{self.device}")
+        else:
+            self.index = GfkbIndex(device=self.device, row_base=lo, vocab=self.vocab)
+            self.index.add_features(fb, lo, hi)
         fb.close()
         if self.world > 1 and self.mode == "rows":
             df = torch.from_numpy(self.index.local_df().astype(np.int32)).to(f"cuda:{self.device}")
@@ -178,6 +201,8 @@ class ShardedGfkb:
         s = torch.empty((q, k), dtype=torch.float32, device=dev)
         r = torch.empty((q, k), dtype=torch.int64, device=dev)
         self.index.topk_resident(k, s.data_ptr(), r.data_ptr())
+        if self.row_map is not None:  # text-range shard: local row -> global row id (-1 stays -1)
+            r = torch.where(r >= 0, self.row_map[r.clamp(min=0)], r)
         if self.world == 1:
             return s, r
         gs, gr = gather_topk(s, r, self.group)

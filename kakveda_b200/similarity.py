@@ -108,6 +108,30 @@ class ArrayBatch:
         pass
 
 
+def text_order(batch, n_threads: int = 0) -> np.ndarray:
+    """int32 [n]: the rows of a featurised batch in text order (feature-id sequence, equal rows by index) -- host only."""
+    perm = np.empty(batch.n, dtype=np.int32)
+    _capi.check(_capi.load().kv_text_order(_ptr(batch.indptr, C.c_int64), _ptr(batch.ids, C.c_uint32), batch.n,
+                                           perm.ctypes.data_as(C.POINTER(C.c_int32)), n_threads))
+    return perm
+
+
+def gather_rows(batch, rows: np.ndarray, n_threads: int = 0) -> ArrayBatch:
+    """The sub-batch made of ``rows`` (int64 indices into ``batch``), in that order -- host only."""
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    if len(rows) and (rows.min() < 0 or rows.max() >= batch.n):
+        raise ValueError("gather_rows: row index outside the batch")
+    lengths = (batch.indptr[1:] - batch.indptr[:-1])[rows] if len(rows) else np.zeros(0, dtype=np.int64)
+    indptr = np.zeros(len(rows) + 1, dtype=np.int64)
+    np.cumsum(lengths, out=indptr[1:])
+    ids = np.empty(int(indptr[-1]), dtype=np.uint32)
+    tf = np.empty(int(indptr[-1]), dtype=np.uint32)
+    _capi.check(_capi.load().kv_csr_gather_rows(_ptr(batch.indptr, C.c_int64), _ptr(batch.ids, C.c_uint32), _ptr(batch.tf, C.c_uint32),
+                                                batch.n, _ptr(rows, C.c_int64), len(rows), _ptr(indptr, C.c_int64),
+                                                _ptr(ids, C.c_uint32), _ptr(tf, C.c_uint32), n_threads))
+    return ArrayBatch(indptr, ids, tf, np.asarray(batch.oov)[rows] if len(rows) else None)
+
+
 class Vocabulary:
     """Word 1,2-gram vocabulary (feature -> uint32 id) shared by corpus rows and queries."""
 

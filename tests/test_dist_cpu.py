@@ -112,3 +112,30 @@ def _gather_worker(rank, world, port, n, d, tmp):
 def test_allpairs_row_gather(built_lib, tmp_path, world, n):
     mp.spawn(_gather_worker, args=(world, _free_port(), n, 64, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"g{r}").exists() for r in range(world))
+
+
+def test_text_range_sharding_host_side(built_lib):
+    """order="text" (dist.ShardedGfkb): the global text order and the row gather are host-only and must agree with a
+    plain Python sort / slicing; the shards partition the rows, each in ascending global order."""
+    from kakveda_b200 import synth
+    from kakveda_b200.dist import shard_rows_by_text
+    from kakveda_b200.similarity import Vocabulary, gather_rows, text_order
+
+    v = Vocabulary()
+    fb = v.featurize(synth.corpus(60001) + ["", "zz", synth.corpus(5)[3]], grow=True)
+    for threads in (1, 8):
+        perm = text_order(fb, threads)
+        seqs = [tuple(fb.ids[fb.indptr[i]:fb.indptr[i + 1]].tolist()) for i in range(fb.n)]
+        assert perm.tolist() == sorted(range(fb.n), key=lambda i: (seqs[i], i))
+    parts = [shard_rows_by_text(fb, 4, r, 4) for r in range(4)]
+    allr = np.concatenate(parts)
+    assert len(allr) == fb.n == len(set(allr.tolist())) and all(np.all(np.diff(p) > 0) for p in parts)
+    sub = gather_rows(fb, parts[2], 4)
+    assert sub.n == len(parts[2])
+    for j in range(0, sub.n, 997):
+        i = parts[2][j]
+        np.testing.assert_array_equal(sub.ids[sub.indptr[j]:sub.indptr[j + 1]], fb.ids[fb.indptr[i]:fb.indptr[i + 1]])
+        np.testing.assert_array_equal(sub.tf[sub.indptr[j]:sub.indptr[j + 1]], fb.tf[fb.indptr[i]:fb.indptr[i + 1]])
+    assert gather_rows(fb, np.zeros(0, dtype=np.int64)).n == 0
+    with pytest.raises(ValueError):
+        gather_rows(fb, np.array([fb.n], dtype=np.int64))

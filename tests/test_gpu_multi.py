@@ -32,7 +32,7 @@ def _worker(rank, world, port, n, q, k, tmp, mode):
 
         buf, off = synth.signatures_packed(synth.CORPUS_SEED, 0, n)
         qbuf, qoff = synth.signatures_packed(synth.QUERY_SEED, 0, q, dup_of_seed=synth.CORPUS_SEED, dup_rows=n)
-        sh = ShardedGfkb(device=rank, rank=rank, world=world, mode=mode)
+        sh = ShardedGfkb(device=rank, rank=rank, world=world, mode=mode.split("-")[0], order="text" if mode.endswith("-text") else "index")
         sh.build_packed(buf, off, 0, n_threads=8)
         s, r = sh.topk_packed(qbuf, qoff, k)
         np.save(Path(tmp, f"s{rank}{mode}.npy"), s)
@@ -43,7 +43,7 @@ def _worker(rank, world, port, n, q, k, tmp, mode):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["rows", "queries"])
+@pytest.mark.parametrize("mode", ["rows", "queries", "rows-text"])
 def test_two_rank_sharded_topk(built_lib, tmp_path, mode):
     import torch
     import torch.multiprocessing as mp
@@ -67,7 +67,7 @@ def test_two_rank_sharded_topk(built_lib, tmp_path, mode):
     s, r = one.topk(synth.queries(q, n), k)
     np.testing.assert_array_equal(r0, r)
     np.testing.assert_allclose(s0, s, rtol=2e-6)
-    if mode == "rows":
+    if mode.startswith("rows"):
         # the shards exchanged their pruning-threshold arrays over CUDA IPC (NVLink peer memory): one peer each
         peers = [int((tmp_path / f"info{rk}{mode}.txt").read_text().split()[0]) for rk in (0, 1)]
         assert peers == [1, 1], peers
