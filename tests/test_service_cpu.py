@@ -136,3 +136,57 @@ def test_sidecar_save_load_and_staleness(built_lib, tmp_path):
     assert sidecar.load(tmp_path / "absent.npz", texts) is None
     (tmp_path / "bad.npz").write_bytes(b"not an npz")
     assert sidecar.load(tmp_path / "bad.npz", texts) is None
+
+
+def test_store_match_and_warn_host_logic_with_canned_candidates(golden, built_lib, monkeypatch):
+    """The host half of GfkbStore.match_batch / warn_batch (services/gfkb/app.py:88-100,
+    services/warning_policy/app.py:30-72) on CPU: the device stage is replaced by candidates taken from the
+    reference's recorded float64 scores, so the truncate-to-5-THEN-filter rule, the FailureMatch mapping and the
+    warning texts are checked against the reference's recorded /failures/match responses without a GPU."""
+    from kakveda_b200 import GfkbStore
+
+    g = golden("fixture54.json")
+    st = GfkbStore()
+    st.records = [dict(r) for r in g["records"]]
+    monkeypatch.setattr(st, "_sync", lambda: None)
+    by_query = {q: np.array(s) for q, s in zip(g["queries"], g["scores"])}
+    current = {}
+
+    def fake_featurize(texts, grow=False, n_threads=0):
+        current["texts"] = list(texts)
+
+        class _B:
+            n = len(texts)
+
+            def close(self):
+                pass
+        return _B()
+
+    def fake_candidates(fb, k):
+        rows, f64 = [], []
+        for t in current["texts"]:
+            s = by_query[t]
+            order = sorted(range(len(s)), key=lambda i: s[i], reverse=True)[:k]   # stable: ties -> lower row
+            rows.append(order)
+            f64.append([s[i] for i in order])
+        return np.array(rows, dtype=np.int64), np.array(f64)
+
+    monkeypatch.setattr(st.vocab, "featurize", fake_featurize)
+    monkeypatch.setattr(st, "_candidates", fake_candidates)
+    cases = [c for c in g["match"] if c["signature_text"] in by_query]
+    got = st.match_batch([c["signature_text"] for c in cases], [c["failure_type"] for c in cases])
+    assert len(cases) >= 12
+    for c, ms in zip(cases, got):
+        assert ms == c["matches"]            # ids, versions, float64 scores, failure_type, suggested_mitigation
+    # the filter runs AFTER the truncation: a foreign failure_type empties the list instead of digging deeper
+    assert any(c["failure_type"] == "OTHER_TYPE" and c["matches"] == [] for c in cases)
+    # warnings: threshold compare, reference message text, silent default
+    monkeypatch.setattr("kakveda_b200.store._signature_text", lambda prompt, tools, env: prompt)
+    q = cases[0]["signature_text"]
+    w = st.warn_batch([{"app_id": "a", "prompt": q}], threshold=0.0, default_action="warn")[0]
+    best = w["references"][0]
+    assert w["confidence"] == best["score"] and w["message"].startswith("This execution matches past failure type ")
+    assert f"similarity={best['score']:.2f}" in w["message"] and w["message"].endswith(str(best["suggested_mitigation"] or "n/a"))
+    w = st.warn_batch([{"app_id": "a", "prompt": q}], threshold=2.0, default_action="silent")[0]
+    assert w == {"action": "silent", "confidence": best["score"], "pattern_id": None, "references": [],
+                 "message": "No high-similarity match found in GFKB."}
