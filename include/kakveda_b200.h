@@ -206,23 +206,30 @@ int kv_index_thresholds_peers(kv_index *ix, const void *handles, int n_peers, in
  * same ordering.  Used after the cross-GPU all-gather. */
 int kv_merge_topk_device(int device, const void *d_scores_in, const void *d_rows_in, int n_lists,
                          int64_t n_q, int k, void *d_scores_out, void *d_rows_out);
+/* The same on a caller-given CUDA stream (a cudaStream_t, e.g. the stream the all-gather that produced the lists
+ * was enqueued on; NULL = legacy default stream); sync = 0 returns without waiting for the kernel. */
+int kv_merge_topk_device_on(int device, const void *d_scores_in, const void *d_rows_in, int n_lists,
+                            int64_t n_q, int k, void *d_scores_out, void *d_rows_out, void *stream, int sync);
 
 /* Timing of the last kv_topk / kv_topk_device call on this handle, CUDA-event
  * milliseconds on its stream:
- * ms[0] = H2D of query structures, ms[1] = scan kernel, ms[2] = merge kernel, ms[3] = D2H. */
+ * ms[0] = H2D of the query batch, ms[1] = bound + scan kernels, ms[2] = merge (+ fallbacks), ms[3] = D2H. */
 int kv_index_last_timing(const kv_index *ix, float ms[4]);
+/* ... and of its kernels: ms[0] = bound pass 0 (seeds; tcgen05 GEMM + rare-feature join), ms[1] = seed scan,
+ * ms[2] = bound pass 1 (candidate lists), ms[3] = candidate scan, ms[4] = merge.  Exhaustive mode: only [3], [4]. */
+int kv_index_last_kernel_ms(const kv_index *ix, float ms[5]);
 /* CUDA-event milliseconds of the scan kernel of the last kv_score call (K1a). */
 int kv_index_last_score_ms(const kv_index *ix, float *ms);
 
 /* Scan-layout facts for roofline accounting.
- * bytes[0] = row stream, bytes[1] = row norms (float32), bytes[2] = chunk pointers,
- * bytes[3] = chunk summaries (pseudo-rows + pointers + min norms).
- * counts[0] = stored entries, [1] = folded (universal) features, [2] = rows, [3] = CTAs of the
- * last scan launch, [4] = its query tiles, [5] = its row splits, [6] = host->device bytes of the
- * last query upload, [7] = tf-overflow entries, [8] = chunks (64 rows each), and for the last
- * scan summed over CTAs: [9] = chunks scanned, [10] = chunks pruned, [11] = summaries evaluated,
- * [12] = 32-query groups active in the scanned chunks (of 4 per chunk), [13..16] = warp-cycles
- * spent in: bound pass, per-query bound re-evaluation, chunk scans, barrier waits. */
+ * bytes[0] = column blocks, bytes[1] = row norms (float32), bytes[2] = block directory,
+ * bytes[3] = dense frequent-feature matrix (fp16) + chunk min norms.
+ * counts[0] = block entries, [1] = folded (universal) features, [2] = rows, [3] = CTAs of the
+ * last candidate scan, [4] = its 128-query bound tiles, [5] = partial lists per query, [6] = host->device bytes of
+ * the last query upload, [7] = tf-overflow entries, [8] = chunks (32 rows each), and for the last batch:
+ * [9] = (query, chunk) pairs scored exactly (seed scan + candidate scan), [10] = candidate records scanned,
+ * [11] = (query, chunk) pairs whose bound passed, [12] = candidate records written, [13] = kernels launched,
+ * [14] = block entries of non-frequent features, [15] = candidate-pool pages used, [16] = pool pages allocated. */
 int kv_index_layout(const kv_index *ix, int64_t bytes[4], int64_t counts[17]);
 
 /* ------------------------------------------------------------------------------------

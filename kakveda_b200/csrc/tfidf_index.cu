@@ -1,10 +1,11 @@
 // TF-IDF cosine index for the GFKB match path: the kv_index handle and its C ABI
-// (include/kakveda_b200.h).  Device code lives in tfidf_kernels.cuh; see there for the math and
-// the HBM layout.  Host responsibilities: keep the append-only CSR, finalize (statistics on the
-// device, text-order sort of the rows and chunk summaries on the host cores), per-batch query
-// preparation (per-query constants in float64, tile tables) and kernel launches.
-#include "tfidf_kernels.cuh"
-#include "tile_builder.cuh"
+// (include/kakveda_b200.h).  Device code lives in tfidf_kernels.cuh (scan, query preparation, merge) and
+// bound_kernel.cuh (tensor-core chunk bounds); see there for the math and the HBM layout.  Host responsibilities: keep
+// the append-only CSR, finalize (statistics on the device, (norm class, text) order of the rows and the column blocks
+// on the host cores), per-batch query upload (text order of the queries, CSR -> device; tables are built by kernels)
+// and kernel launches.
+#include "block_builder.cuh"
+#include "bound_kernel.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -19,7 +20,7 @@
 #include <vector>
 
 using namespace kvk;
-using namespace kvh;  // tile shape, QueryPrep, idf_host, parallel_for, tile builders (tile_builder.cuh)
+using namespace kvh;  // parallel_for, stable_sort_indices, idf_host, build_blocks (block_builder.cuh)
 
 namespace {
 int host_threads() {
@@ -27,7 +28,6 @@ int host_threads() {
   if (const char *e = getenv("KAKVEDA_B200_THREADS")) t = atoi(e);
   return std::max(1, std::min(t, 64));
 }
-
 }  // namespace
 
 // ----------------------------------------------------------------------------------------
@@ -38,10 +38,11 @@ struct kv_index {
   int64_t row_base = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t evk[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // bound/scan kernel boundaries of a batch
   std::mutex mu;
   int sm_count = 148;
 
-  // raw CSR: device copy for the statistics kernels, host copy for the sort and the summaries
+  // raw CSR: device copy for the statistics kernels and K6, host copy for the sort and the column blocks
   DevVec<int64_t> indptr;  // n_rows + 1 entries once any row exists
   DevVec<uint32_t> ids;
   DevVec<uint16_t> tf;
@@ -63,38 +64,52 @@ struct kv_index {
   DevBuf<float> d_B32, d_cminB;
   DevBuf<uint8_t> d_univ;
   DevBuf<int> d_perm, d_invperm;
-  // scan layout currently on the device (perm, stream, summaries): which rows / universal set it was built for
+  // scan layout currently on the device (perm, column blocks, dense matrix): which rows / universal set it was built for
   bool layout_valid = false;
   int64_t layout_rows = -1;
   std::vector<uint8_t> layout_univ;
   int last_finalize_kind = 0;  // 1: full rebuild, 2: statistics-only refresh
+  DevBuf<uint32_t> d_blk;
+  DevBuf<BlockInfo> d_binfo;
+  DevBuf<__half> d_Uf;
+  DevBuf<short> d_fslot;
+  CUtensorMap map_u;
+  DevBuf<unsigned long long> d_ovf_keys;
+  DevBuf<uint32_t> d_ovf_vals;
+  int n_ovf = 0;
+  int64_t blk_words = 0, n_chunks = 0, n_chunks_pad = 0, n_entries = 0, n_rare_entries = 0;
+  std::vector<uint32_t> h_df, h_tfmax;
+  std::vector<uint8_t> h_univ;
+  std::vector<uint32_t> h_utf;
+  int64_t n_univ = 0;
   // K6 scratch
   DevBuf<int64_t> d_rq_indptr;
   DevBuf<uint32_t> d_rq_ids, d_rq_tf;
   DevBuf<double> d_rq_const, d_rq_out;
   DevBuf<long long> d_rq_rows;
-  DevBuf<int64_t> d_chunkptr, d_sumptr, d_grpptr;
-  DevBuf<uint32_t> d_stream, d_sum_stream, d_grp_stream;
-  DevBuf<unsigned long long> d_ovf_keys;
-  DevBuf<uint32_t> d_ovf_vals;
-  int n_ovf = 0;
-  int64_t stream_len = 0, sum_len = 0, grp_len = 0, n_chunks = 0;
-  std::vector<uint32_t> h_df;
-  std::vector<uint8_t> h_univ;
-  std::vector<uint32_t> h_utf;
-  std::vector<std::pair<uint32_t, uint32_t>> h_su;  // summary-universal features (fid, tf), sorted
-  int64_t n_univ = 0;
 
-  // query scratch
-  PinnedBuf<unsigned char> h_tables;
-  PinnedBuf<TileDesc> h_tiles;
-  PinnedBuf<float> h_qconst;  // 4 * n_q
+  // query batch: pinned staging + device copies of the CSR, per-query tables (built by kernels)
+  PinnedBuf<int64_t> h_q_indptr;
+  PinnedBuf<uint32_t> h_q_ids, h_q_tf;
+  PinnedBuf<double> h_q_oov;
   PinnedBuf<int> h_qperm;     // 2 * n_q: sorted slot -> original query, then null-query list
-  DevBuf<unsigned char> d_tables;
-  DevBuf<TileDesc> d_tiles;
-  DevBuf<float> d_qconst;
+  PinnedBuf<uint8_t> h_flags;
+  DevBuf<int64_t> d_q_indptr;
+  DevBuf<uint32_t> d_q_ids, d_q_tf;
+  DevBuf<double> d_q_oov;
   DevBuf<int> d_qperm;
+  DevBuf<uint8_t> d_flags;
+  DevBuf<float> d_qconst;     // 7 * n_q: nq, dotU, corrU, dotS, corrS, dotX, -inf
+  DevBuf<unsigned char> d_qtab, d_rtab;
+  DevBuf<__half> d_Wf;
+  CUtensorMap map_w;
   DevBuf<int> d_gthr;
+  // candidate lists of a batch
+  DevBuf<int> d_seeds;
+  DevBuf<uint2> d_direct, d_pool;
+  DevBuf<uint32_t> d_list_count, d_list_pages;
+  DevBuf<unsigned int> d_pool_ctl;  // [0] pages handed out, [1] overflow flag
+  int64_t pool_pages = 0;
   // cross-GPU threshold exchange (row-sharded GFKB): d_gthr is exported over CUDA IPC, the peers' arrays are mapped here
   bool gthr_exported = false;
   int n_peers = 0;
@@ -103,7 +118,6 @@ struct kv_index {
   DevBuf<int> d_excl_sorted, d_excl_orig;  // self-join exclusions of the resident batch (by sorted slot / by original query)
   std::vector<int> h_excl_orig;
   bool has_excl = false;
-  DevBuf<float> d_ubuf;
   DevBuf<unsigned long long> d_stats;
   DevBuf<float> d_part_s, d_out_s;
   DevBuf<long long> d_part_r, d_out_r;
@@ -111,7 +125,7 @@ struct kv_index {
   PinnedBuf<long long> h_out_r;
   // single-query scratch
   PinnedBuf<unsigned char> h_qtab;
-  DevBuf<unsigned char> d_qtab;
+  DevBuf<unsigned char> d_qtab1;
   DevBuf<double> d_scores;
 
   // query batch currently resident on the device (kv_query_upload / first half of kv_topk)
@@ -122,8 +136,9 @@ struct kv_index {
   std::vector<double> irr_oov;
 
   float last_ms[4] = {0, 0, 0, 0};
+  float last_kernel_ms[5] = {0, 0, 0, 0, 0};  // bound pass 0, seed scan, bound pass 1, scan, merge
   float last_score_ms = 0;
-  int64_t last_ctas = 0, last_tiles = 0, last_splits = 0;
+  int64_t last_ctas = 0, last_tiles = 0, last_splits = 0, last_launches = 0;
   unsigned long long last_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
@@ -137,41 +152,19 @@ static void close_peers(kv_index *ix) {
 
 namespace {
 
-void prep_query(const kv_index *ix, const uint32_t *ids, const uint32_t *tf, int64_t nnz, double oov_tf2,
-                QueryPrep &out) {
-  out.dotU = out.corrU = out.dotS = out.corrS = 0;
-  out.fid.clear();
-  out.tfq.clear();
-  // df == 0 features of the query: the refit gives them idf ln((N+2)/2)+1; a corpus-only fit does not know them at all
-  double idf0 = ix->jaccard ? 1.0 : (ix->corpus_fit ? 0.0 : std::log((double)(ix->n_total + 2) / 2.0) + 1.0);
-  out.nq = oov_tf2 * idf0 * idf0;
+// |q|^2 in float64, features in CSR order (the value K1a and the prep kernel compute)
+double host_query_norm(const kv_index *ix, const uint32_t *ids, const uint32_t *tf, int64_t nnz, double oov_tf2) {
+  const double idf0 = ix->jaccard ? 1.0 : (ix->corpus_fit ? 0.0 : std::log((double)(ix->n_total + 2) / 2.0) + 1.0);
+  double nq = oov_tf2 * idf0 * idf0;
   for (int64_t i = 0; i < nnz; i++) {
-    uint32_t t = ids[i];
-    double f = (double)tf[i];
-    if ((int64_t)t >= ix->V) {  // id issued after finalize: in no indexed row
-      out.nq += f * f * idf0 * idf0;
-      continue;
-    }
+    const uint32_t t = ids[i];
+    const double f = (double)tf[i];
+    if ((int64_t)t >= ix->V) { nq += f * f * idf0 * idf0; continue; }
     double a, d;
     idf_host(ix->n_total, ix->h_df[t], a, d, ix->jaccard, ix->corpus_fit);
-    out.nq += f * f * a;
-    if (ix->h_univ[t]) {
-      double u = (double)ix->h_utf[t];
-      out.dotU += f * u * a;
-      out.corrU += u * u * d;
-    } else {
-      out.fid.push_back(t);
-      out.tfq.push_back(tf[i]);
-      auto it = std::lower_bound(ix->h_su.begin(), ix->h_su.end(), std::make_pair(t, 0u));
-      if (it != ix->h_su.end() && it->first == t) {
-        double u = (double)it->second;
-        out.dotS += f * u * a;
-        out.corrS += u * u * d;
-      }
-    }
+    nq += f * f * a;
   }
-  out.dotS += out.dotU;
-  out.corrS += out.corrU;
+  return nq;
 }
 
 // lexicographic order of two id sequences (shorter prefix first)
@@ -243,6 +236,7 @@ int kv_index_create(int device, int64_t row_base, kv_index **out) {
   ix->sm_count = prop.multiProcessorCount;
   KV_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
   for (auto &e : ix->ev) KV_CUDA(cudaEventCreate(&e));
+  for (auto &e : ix->evk) KV_CUDA(cudaEventCreate(&e));
   *out = ix;
   return KV_OK;
 }
@@ -254,21 +248,26 @@ void kv_index_destroy(kv_index *ix) {
   ix->indptr.release(); ix->ids.release(); ix->tf.release();
   ix->d_df.release(); ix->d_cnt.release(); ix->d_tfmin.release(); ix->d_tfmax.release(); ix->d_utf.release();
   ix->d_a64.release(); ix->d_d64.release(); ix->d_bb64.release(); ix->d_B64.release();
-  ix->d_B32.release(); ix->d_cminB.release(); ix->d_univ.release(); ix->d_perm.release();
-  ix->d_chunkptr.release(); ix->d_sumptr.release(); ix->d_grpptr.release(); ix->d_grp_stream.release();
-  ix->d_stream.release(); ix->d_sum_stream.release();
+  ix->d_B32.release(); ix->d_cminB.release(); ix->d_univ.release(); ix->d_perm.release(); ix->d_invperm.release();
+  ix->d_blk.release(); ix->d_binfo.release(); ix->d_Uf.release(); ix->d_fslot.release();
   ix->d_ovf_keys.release(); ix->d_ovf_vals.release();
-  ix->h_tables.release(); ix->h_tiles.release(); ix->h_qconst.release(); ix->h_qperm.release();
-  ix->d_tables.release(); ix->d_tiles.release(); ix->d_qconst.release(); ix->d_qperm.release(); ix->d_gthr.release();
-  close_peers(ix);
-  ix->d_excl_sorted.release(); ix->d_excl_orig.release(); ix->d_invperm.release();
   ix->d_rq_indptr.release(); ix->d_rq_ids.release(); ix->d_rq_tf.release(); ix->d_rq_const.release(); ix->d_rq_out.release();
   ix->d_rq_rows.release();
-  ix->d_ubuf.release(); ix->d_stats.release();
+  ix->h_q_indptr.release(); ix->h_q_ids.release(); ix->h_q_tf.release(); ix->h_q_oov.release(); ix->h_qperm.release();
+  ix->h_flags.release();
+  ix->d_q_indptr.release(); ix->d_q_ids.release(); ix->d_q_tf.release(); ix->d_q_oov.release(); ix->d_qperm.release();
+  ix->d_flags.release(); ix->d_qconst.release(); ix->d_qtab.release(); ix->d_rtab.release(); ix->d_Wf.release();
+  ix->d_gthr.release();
+  ix->d_seeds.release(); ix->d_direct.release(); ix->d_pool.release(); ix->d_list_count.release(); ix->d_list_pages.release();
+  ix->d_pool_ctl.release();
+  close_peers(ix);
+  ix->d_excl_sorted.release(); ix->d_excl_orig.release();
+  ix->d_stats.release();
   ix->d_part_s.release(); ix->d_out_s.release(); ix->d_part_r.release(); ix->d_out_r.release();
   ix->h_out_s.release(); ix->h_out_r.release();
-  ix->h_qtab.release(); ix->d_qtab.release(); ix->d_scores.release();
+  ix->h_qtab.release(); ix->d_qtab1.release(); ix->d_scores.release();
   for (auto &e : ix->ev) if (e) cudaEventDestroy(e);
+  for (auto &e : ix->evk) if (e) cudaEventDestroy(e);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   delete ix;
 }
@@ -451,12 +450,14 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
     KV_CUDA(cudaGetLastError());
   }
   ix->h_df.assign((size_t)V, 0);
-  ix->h_univ.assign((size_t)V, 0);
+  ix->h_univ.assign((size_t)Vz, 0);
   ix->h_utf.assign((size_t)V, 0);
+  ix->h_tfmax.assign((size_t)Vz, 0);
   if (V) {
     KV_CUDA(cudaMemcpyAsync(ix->h_df.data(), ix->d_df.p, (size_t)V * 4, cudaMemcpyDeviceToHost, s));
     KV_CUDA(cudaMemcpyAsync(ix->h_univ.data(), ix->d_univ.p, (size_t)V, cudaMemcpyDeviceToHost, s));
     KV_CUDA(cudaMemcpyAsync(ix->h_utf.data(), ix->d_utf.p, (size_t)V * 4, cudaMemcpyDeviceToHost, s));
+    KV_CUDA(cudaMemcpyAsync(ix->h_tfmax.data(), ix->d_tfmax.p, (size_t)V * 4, cudaMemcpyDeviceToHost, s));
   }
   // row norms in original order (the sort key needs them)
   const int64_t nz = n > 0 ? n : 1;
@@ -465,31 +466,32 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
   std::vector<float> hB((size_t)n);
   if (n) {
     rownorm_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(ix->indptr.p, ix->ids.p, ix->tf.p, nullptr, n,
-                                                                    ix->d_bb64.p, ix->d_univ.p, ix->d_B64.p,
-                                                                    ix->d_B32.p, nullptr);
+                                                                    ix->d_bb64.p, ix->d_B64.p, ix->d_B32.p);
     KV_CUDA(cudaGetLastError());
     KV_CUDA(cudaMemcpyAsync(hB.data(), ix->d_B32.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s));
   }
   KV_CUDA(cudaStreamSynchronize(s));
   ix->n_univ = 0;
-  for (uint8_t u : ix->h_univ) ix->n_univ += u;
+  for (int64_t t = 0; t < V; t++) ix->n_univ += ix->h_univ[(size_t)t];
   {
     int rc = upload_idf_tables(ix, V);
     if (rc != KV_OK) return rc;
   }
-  // ---- statistics-only refresh: the rows (hence text order, stream, chunk summaries) are the ones the device layout
-  // was built from and the set of folded universal features is unchanged; only N / df moved (rows were appended to
-  // ANOTHER shard or segment of the same GFKB).  Row norms and chunk minima are recomputed, nothing is re-sorted.
+  // ---- statistics-only refresh: the rows (hence their order and the column blocks, which hold term frequencies and
+  // row masks only) are the ones the device layout was built from and the set of folded universal features is
+  // unchanged; only N / df moved (rows were appended to ANOTHER shard or segment of the same GFKB).  Row norms and chunk
+  // minima are recomputed, nothing is re-sorted.
   if (ix->layout_valid && ix->layout_rows == n && n > 0 && !getenv("KAKVEDA_B200_FULL_FINALIZE")) {
-    bool same = (int64_t)ix->layout_univ.size() <= V;
+    bool same = (int64_t)ix->layout_univ.size() <= Vz;
     for (size_t t = 0; same && t < ix->layout_univ.size(); t++) same = ix->layout_univ[t] == ix->h_univ[t];
     for (size_t t = ix->layout_univ.size(); same && t < (size_t)V; t++) same = ix->h_univ[t] == 0;
+    if (same && V > (int64_t)ix->d_fslot.cap) same = false;  // new feature ids: the column map must grow
     if (same) {
       rownorm_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(ix->indptr.p, ix->ids.p, ix->tf.p, ix->d_perm.p, n,
-                                                                      ix->d_bb64.p, ix->d_univ.p, ix->d_B64.p,
-                                                                      ix->d_B32.p, nullptr);
+                                                                      ix->d_bb64.p, ix->d_B64.p, ix->d_B32.p);
       KV_CUDA(cudaGetLastError());
-      chunk_meta_kernel<<<(unsigned)((ix->n_chunks + 255) / 256), 256, 0, s>>>(ix->d_B32.p, n, ix->n_chunks, ix->d_cminB.p);
+      chunk_meta_kernel<<<(unsigned)((ix->n_chunks_pad + 255) / 256), 256, 0, s>>>(ix->d_B32.p, n, ix->n_chunks, ix->n_chunks_pad,
+                                                                                    ix->d_cminB.p);
       KV_CUDA(cudaGetLastError());
       KV_CUDA(cudaStreamSynchronize(s));
       ix->V = V;
@@ -500,254 +502,52 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
     }
   }
   ix->layout_valid = false;
-  // ---- on the host cores: (norm class, text) order of the rows ----
+  // ---- on the host cores: (norm class, text) order of the rows, then the column blocks ----
   std::vector<int> perm;
   sort_rows_by_text(ix->h_indptr, ix->h_ids, n, hB, perm);
-  ix->n_chunks = (n + CHUNK_ROWS - 1) / CHUNK_ROWS;
-  KV_CUDA(ix->d_chunkptr.ensure(ix->n_chunks + 1));
-  KV_CUDA(ix->d_sumptr.ensure(ix->n_chunks + 1));
-  KV_CUDA(ix->d_cminB.ensure(ix->n_chunks + 1));
-  ix->stream_len = ix->sum_len = 0;
-  ix->n_ovf = 0;
+  BlockLayout L;
+  build_blocks(ix->h_indptr.data(), ix->h_ids.data(), ix->h_tf.data(), perm.data(), n, V, ix->h_univ.data(),
+               ix->h_tfmax.data(), host_threads(), L);
+  ix->n_chunks = L.n_chunks;
+  ix->n_chunks_pad = L.n_chunks_pad;
+  ix->blk_words = L.total_words;
+  ix->n_entries = L.n_entries;
+  ix->n_rare_entries = L.n_rare_entries;
+  KV_CUDA(ix->d_blk.ensure(L.total_words + 64));
+  KV_CUDA(ix->d_binfo.ensure(L.n_chunks_pad));
+  KV_CUDA(ix->d_Uf.ensure(L.n_chunks_pad * NF));
+  KV_CUDA(ix->d_fslot.ensure(Vz));
+  KV_CUDA(ix->d_cminB.ensure(L.n_chunks_pad));
   if (n) {
     KV_CUDA(cudaMemcpyAsync(ix->d_perm.p, perm.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
     KV_CUDA(ix->d_invperm.ensure(n));
     invperm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ix->d_perm.p, n, ix->d_invperm.p);
     KV_CUDA(cudaGetLastError());
     rownorm_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(ix->indptr.p, ix->ids.p, ix->tf.p, ix->d_perm.p, n,
-                                                                    ix->d_bb64.p, ix->d_univ.p, ix->d_B64.p,
-                                                                    ix->d_B32.p, nullptr);
+                                                                    ix->d_bb64.p, ix->d_B64.p, ix->d_B32.p);
     KV_CUDA(cudaGetLastError());
-    chunk_meta_kernel<<<(unsigned)((ix->n_chunks + 255) / 256), 256, 0, s>>>(ix->d_B32.p, n, ix->n_chunks, ix->d_cminB.p);
-    KV_CUDA(cudaGetLastError());
-
-    // ---- scan stream + chunk summaries, built per chunk on the host cores ----
-    const int T = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), ix->n_chunks));
-    std::vector<int64_t> chunkptr((size_t)ix->n_chunks + 1, 0), sumptr((size_t)ix->n_chunks + 1, 0);
-    std::vector<std::vector<uint32_t>> part((size_t)T), spart((size_t)T);
-    std::vector<std::vector<std::pair<unsigned long long, uint32_t>>> povf((size_t)T);
-    std::vector<int64_t> chunk_len((size_t)ix->n_chunks, 0), sum_len((size_t)ix->n_chunks, 0), union_len((size_t)ix->n_chunks, 0);
-    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> punion((size_t)T);  // chunk unions (fid, max tf), per thread
-    parallel_for(ix->n_chunks, T, [&](int t, int64_t c0, int64_t c1) {
-      std::vector<std::pair<uint32_t, uint32_t>> u;                       // (fid, tf) of the whole chunk
-      std::vector<std::vector<std::pair<uint32_t, uint32_t>>> kept;       // stored entries per row
-      std::vector<uint32_t> &out = part[(size_t)t], &sout = spart[(size_t)t];
-      auto &ovf = povf[(size_t)t];
-      auto emit = [&](std::vector<uint32_t> &dst, unsigned long long key_pos, uint32_t f, uint32_t tfv) {
-        if (tfv >= TF_OVF) {
-          ovf.emplace_back((key_pos << 32) | f, tfv);
-          tfv = TF_OVF;
-        }
-        dst.push_back((f << 5) | tfv);
-      };
-      for (int64_t c = c0; c < c1; c++) {
-        const int64_t pos0 = c * CHUNK_ROWS, pos1 = std::min<int64_t>(n, pos0 + CHUNK_ROWS);
-        kept.resize((size_t)(pos1 - pos0));
-        u.clear();
-        for (int64_t pos = pos0; pos < pos1; pos++) {
-          auto &k = kept[(size_t)(pos - pos0)];
-          k.clear();
-          const int64_t r = perm[(size_t)pos];
-          for (int64_t p = ix->h_indptr[(size_t)r]; p < ix->h_indptr[(size_t)r + 1]; p++) {
-            uint32_t f = ix->h_ids[(size_t)p];
-            if (!ix->h_univ[f]) k.emplace_back(f, ix->h_tf[(size_t)p]);
-          }
-          u.insert(u.end(), k.begin(), k.end());
-        }
-        // longest prefix of stored entries shared by every row of the chunk
-        size_t lcp = kept[0].size();
-        for (size_t i = 1; i < kept.size() && lcp; i++) {
-          size_t m = std::min(lcp, kept[i].size()), j = 0;
-          while (j < m && kept[i][j] == kept[0][j]) j++;
-          lcp = j;
-        }
-        const size_t before = out.size();
-        for (size_t j = 0; j < lcp; j++) emit(out, OVF_CORE_BASE + (unsigned long long)c, kept[0][j].first, kept[0][j].second);
-        out.push_back(CORE_ENTRY);
-        for (size_t i = 0; i < kept.size(); i++) {
-          const size_t row_begin = out.size();
-          for (size_t j = lcp; j < kept[i].size(); j++)
-            emit(out, (unsigned long long)(pos0 + (int64_t)i), kept[i][j].first, kept[i][j].second);
-          if (out.size() == row_begin) out.push_back(PAD_ENTRY);
-          out.back() |= 0x80000000u;
-        }
-        chunk_len[(size_t)c] = (int64_t)(out.size() - before);
-        // union of the chunk's stored features with the max tf (summaries are emitted below)
-        std::sort(u.begin(), u.end());
-        const size_t ubefore = punion[(size_t)t].size();
-        for (size_t i = 0; i < u.size();) {
-          size_t j = i;
-          while (j + 1 < u.size() && u[j + 1].first == u[i].first) j++;
-          punion[(size_t)t].emplace_back(u[i].first, u[j].second);  // sorted: last of the run = max tf
-          i = j + 1;
-        }
-        union_len[(size_t)c] = (int64_t)(punion[(size_t)t].size() - ubefore);
-      }
-    });
-    // "summary-universal" features: present in >= 90 % of the chunk unions.  The bounds assume them present
-    // in EVERY chunk with their largest tf (a valid over-estimate), so the summaries need not store them.
-    {
-      std::unique_ptr<std::atomic<uint32_t>[]> cnt(new std::atomic<uint32_t>[(size_t)Vz]);
-      std::unique_ptr<std::atomic<uint32_t>[]> tfm(new std::atomic<uint32_t>[(size_t)Vz]);
-      parallel_for(Vz, T, [&](int, int64_t a0, int64_t a1) {
-        for (int64_t i = a0; i < a1; i++) { cnt[(size_t)i].store(0, std::memory_order_relaxed); tfm[(size_t)i].store(0, std::memory_order_relaxed); }
-      });
-      parallel_for(T, T, [&](int, int64_t t0, int64_t t1) {
-        for (int64_t t = t0; t < t1; t++)
-          for (const auto &e : punion[(size_t)t]) {
-            cnt[e.first].fetch_add(1, std::memory_order_relaxed);
-            uint32_t cur = tfm[e.first].load(std::memory_order_relaxed);
-            while (e.second > cur && !tfm[e.first].compare_exchange_weak(cur, e.second, std::memory_order_relaxed)) {}
-          }
-      });
-      ix->h_su.clear();
-      const uint32_t need = (uint32_t)std::max<int64_t>(2, (ix->n_chunks * 9 + 9) / 10);
-      for (int64_t f = 0; f < V; f++)
-        if (cnt[(size_t)f].load(std::memory_order_relaxed) >= need) ix->h_su.emplace_back((uint32_t)f, tfm[(size_t)f].load(std::memory_order_relaxed));
-    }
-    parallel_for(ix->n_chunks, T, [&](int t, int64_t c0, int64_t c1) {
-      std::vector<uint32_t> &sout = spart[(size_t)t];
-      auto &ovf = povf[(size_t)t];
-      const auto &src = punion[(size_t)t];
-      size_t off = 0;
-      for (int64_t c = c0; c < c1; c++) {
-        // summary pseudo-row: the union minus the summary-universal features
-        const size_t sbefore = sout.size();
-        for (size_t i = off; i < off + (size_t)union_len[(size_t)c]; i++) {
-          {
-            auto it = std::lower_bound(ix->h_su.begin(), ix->h_su.end(), std::make_pair(src[i].first, 0u));
-            if (it != ix->h_su.end() && it->first == src[i].first) continue;
-          }
-          uint32_t f = src[i].first, tfv = src[i].second;
-          if (tfv >= TF_OVF) {
-            ovf.emplace_back(((unsigned long long)(n + c) << 32) | f, tfv);
-            tfv = TF_OVF;
-          }
-          sout.push_back((f << 5) | tfv);
-        }
-        off += (size_t)union_len[(size_t)c];
-        if (sout.size() == sbefore) sout.push_back(PAD_ENTRY);
-        sout.back() |= 0x80000000u;
-        sum_len[(size_t)c] = (int64_t)(sout.size() - sbefore);
-      }
-    });
-    for (int64_t c = 0; c < ix->n_chunks; c++) {
-      chunkptr[(size_t)c + 1] = chunkptr[(size_t)c] + chunk_len[(size_t)c];
-      sumptr[(size_t)c + 1] = sumptr[(size_t)c] + sum_len[(size_t)c];
-    }
-    ix->stream_len = chunkptr[(size_t)ix->n_chunks];
-    ix->sum_len = sumptr[(size_t)ix->n_chunks];
-    KV_CUDA(ix->d_stream.ensure(ix->stream_len + 32));
-    KV_CUDA(ix->d_sum_stream.ensure(ix->sum_len + 32));
-    std::vector<std::pair<unsigned long long, uint32_t>> ovf_all;
-    for (int t = 0; t < T; t++) {  // thread t produced chunks [n_chunks*t/T, n_chunks*(t+1)/T)
-      const int64_t c0 = ix->n_chunks * t / T;
-      if (!part[(size_t)t].empty())
-        KV_CUDA(cudaMemcpyAsync(ix->d_stream.p + chunkptr[(size_t)c0], part[(size_t)t].data(), part[(size_t)t].size() * 4,
-                                cudaMemcpyHostToDevice, s));
-      if (!spart[(size_t)t].empty())
-        KV_CUDA(cudaMemcpyAsync(ix->d_sum_stream.p + sumptr[(size_t)c0], spart[(size_t)t].data(), spart[(size_t)t].size() * 4,
-                                cudaMemcpyHostToDevice, s));
-      ovf_all.insert(ovf_all.end(), povf[(size_t)t].begin(), povf[(size_t)t].end());
-    }
-    KV_CUDA(cudaMemcpyAsync(ix->d_chunkptr.p, chunkptr.data(), (size_t)(ix->n_chunks + 1) * 8, cudaMemcpyHostToDevice, s));
-    KV_CUDA(cudaMemcpyAsync(ix->d_sumptr.p, sumptr.data(), (size_t)(ix->n_chunks + 1) * 8, cudaMemcpyHostToDevice, s));
-    // ---- bound-pass layout: the chunk summaries again, in groups of SUM_GROUP with their shared part first ----
-    {
-      const int64_t n_groups = (ix->n_chunks + SUM_GROUP - 1) / SUM_GROUP;
-      std::vector<int64_t> uoff((size_t)ix->n_chunks, 0);  // offset of a chunk's union inside its thread's buffer
-      std::vector<int> uthr((size_t)ix->n_chunks, 0);
-      for (int t = 0; t < T; t++) {
-        int64_t off = 0;
-        for (int64_t c = ix->n_chunks * t / T; c < ix->n_chunks * (t + 1) / T; c++) {
-          uoff[(size_t)c] = off;
-          uthr[(size_t)c] = t;
-          off += union_len[(size_t)c];
-        }
-      }
-      const int T2 = (int)std::max<int64_t>(1, std::min<int64_t>(T, n_groups));
-      std::vector<std::vector<uint32_t>> gp((size_t)T2);
-      std::vector<std::vector<std::pair<unsigned long long, uint32_t>>> govf((size_t)T2);
-      std::vector<int64_t> glen((size_t)n_groups, 0), grpptr((size_t)n_groups + 1, 0);
-      auto is_su = [&](uint32_t f) {
-        auto it = std::lower_bound(ix->h_su.begin(), ix->h_su.end(), std::make_pair(f, 0u));
-        return it != ix->h_su.end() && it->first == f;
-      };
-      parallel_for(n_groups, T2, [&](int t, int64_t a, int64_t b) {
-        std::vector<std::pair<uint32_t, uint32_t>> core, tmp;
-        auto &out = gp[(size_t)t];
-        auto push = [&](unsigned long long key_pos, uint32_t f, uint32_t tfv) {
-          if (tfv >= TF_OVF) {
-            govf[(size_t)t].emplace_back((key_pos << 32) | f, tfv);
-            tfv = TF_OVF;
-          }
-          out.push_back((f << 5) | tfv);
-        };
-        for (int64_t g = a; g < b; g++) {
-          const int64_t c0 = g * SUM_GROUP, c1 = std::min<int64_t>(ix->n_chunks, c0 + SUM_GROUP);
-          auto span = [&](int64_t c) {
-            const auto &src = punion[(size_t)uthr[(size_t)c]];
-            return std::make_pair(src.begin() + (std::ptrdiff_t)uoff[(size_t)c],
-                                  src.begin() + (std::ptrdiff_t)(uoff[(size_t)c] + union_len[(size_t)c]));
-          };
-          // core = entries (fid, tf) present in every chunk union of the group (sorted ranges -> set_intersection)
-          core.assign(span(c0).first, span(c0).second);
-          for (int64_t c = c0 + 1; c < c1 && !core.empty(); c++) {
-            tmp.clear();
-            std::set_intersection(core.begin(), core.end(), span(c).first, span(c).second, std::back_inserter(tmp));
-            core.swap(tmp);
-          }
-          const size_t before = out.size();
-          for (auto &e : core)
-            if (!is_su(e.first)) push(OVF_GCORE_BASE + (unsigned long long)g, e.first, e.second);
-          out.push_back(CORE_ENTRY);
-          for (int64_t c = c0; c < c1; c++) {
-            const size_t row_begin = out.size();
-            auto sp = span(c);
-            for (auto it = sp.first; it != sp.second; ++it) {
-              if (is_su(it->first) || std::binary_search(core.begin(), core.end(), *it)) continue;
-              push((unsigned long long)(n + ix->n_chunks + c), it->first, it->second);
-            }
-            if (out.size() == row_begin) out.push_back(PAD_ENTRY);
-            out.back() |= 0x80000000u;
-          }
-          glen[(size_t)g] = (int64_t)(out.size() - before);
-        }
-      });
-      for (int64_t g = 0; g < n_groups; g++) grpptr[(size_t)g + 1] = grpptr[(size_t)g] + glen[(size_t)g];
-      ix->grp_len = grpptr[(size_t)n_groups];
-      KV_CUDA(ix->d_grp_stream.ensure(ix->grp_len + 32));
-      KV_CUDA(ix->d_grpptr.ensure(n_groups + 1));
-      for (int t = 0; t < T2; t++) {
-        const int64_t g0 = n_groups * t / T2;
-        if (!gp[(size_t)t].empty())
-          KV_CUDA(cudaMemcpyAsync(ix->d_grp_stream.p + grpptr[(size_t)g0], gp[(size_t)t].data(), gp[(size_t)t].size() * 4,
-                                  cudaMemcpyHostToDevice, s));
-        ovf_all.insert(ovf_all.end(), govf[(size_t)t].begin(), govf[(size_t)t].end());
-      }
-      KV_CUDA(cudaMemcpyAsync(ix->d_grpptr.p, grpptr.data(), (size_t)(n_groups + 1) * 8, cudaMemcpyHostToDevice, s));
-      KV_CUDA(cudaStreamSynchronize(s));  // gp goes out of scope
-    }
-    std::sort(ovf_all.begin(), ovf_all.end());
-    ix->n_ovf = (int)ovf_all.size();
-    KV_CUDA(ix->d_ovf_keys.ensure(std::max(1, ix->n_ovf))); KV_CUDA(ix->d_ovf_vals.ensure(std::max(1, ix->n_ovf)));
-    std::vector<unsigned long long> ok((size_t)ix->n_ovf);
-    std::vector<uint32_t> ov((size_t)ix->n_ovf);
-    for (int i = 0; i < ix->n_ovf; i++) { ok[(size_t)i] = ovf_all[(size_t)i].first; ov[(size_t)i] = ovf_all[(size_t)i].second; }
-    if (ix->n_ovf) {
-      KV_CUDA(cudaMemcpyAsync(ix->d_ovf_keys.p, ok.data(), (size_t)ix->n_ovf * 8, cudaMemcpyHostToDevice, s));
-      KV_CUDA(cudaMemcpyAsync(ix->d_ovf_vals.p, ov.data(), (size_t)ix->n_ovf * 4, cudaMemcpyHostToDevice, s));
-    }
-    KV_CUDA(cudaStreamSynchronize(s));  // the staging vectors go out of scope
-  } else {
-    KV_CUDA(ix->d_stream.ensure(32));
-    KV_CUDA(ix->d_sum_stream.ensure(32));
-    KV_CUDA(ix->d_grp_stream.ensure(32));
-    KV_CUDA(ix->d_grpptr.ensure(1));
-    KV_CUDA(cudaMemsetAsync(ix->d_grpptr.p, 0, sizeof(int64_t), s));
-    KV_CUDA(cudaMemsetAsync(ix->d_chunkptr.p, 0, sizeof(int64_t), s));
-    KV_CUDA(cudaMemsetAsync(ix->d_sumptr.p, 0, sizeof(int64_t), s));
-    KV_CUDA(cudaStreamSynchronize(s));
+  }
+  chunk_meta_kernel<<<(unsigned)((L.n_chunks_pad + 255) / 256), 256, 0, s>>>(ix->d_B32.p, n, L.n_chunks, L.n_chunks_pad, ix->d_cminB.p);
+  KV_CUDA(cudaGetLastError());
+  for (size_t t = 0; t < L.parts.size(); t++)
+    if (!L.parts[t].empty())
+      KV_CUDA(cudaMemcpyAsync(ix->d_blk.p + L.part_off[t], L.parts[t].data(), L.parts[t].size() * 4, cudaMemcpyHostToDevice, s));
+  KV_CUDA(cudaMemcpyAsync(ix->d_binfo.p, L.binfo.data(), (size_t)L.n_chunks_pad * sizeof(BlockInfo), cudaMemcpyHostToDevice, s));
+  KV_CUDA(cudaMemcpyAsync(ix->d_Uf.p, L.Uf.data(), (size_t)L.n_chunks_pad * NF * sizeof(__half), cudaMemcpyHostToDevice, s));
+  KV_CUDA(cudaMemcpyAsync(ix->d_fslot.p, L.fslot.data(), (size_t)Vz * sizeof(short), cudaMemcpyHostToDevice, s));
+  ix->n_ovf = (int)L.ovf.size();
+  KV_CUDA(ix->d_ovf_keys.ensure(std::max(1, ix->n_ovf))); KV_CUDA(ix->d_ovf_vals.ensure(std::max(1, ix->n_ovf)));
+  std::vector<unsigned long long> ok((size_t)ix->n_ovf);
+  std::vector<uint32_t> ov((size_t)ix->n_ovf);
+  for (int i = 0; i < ix->n_ovf; i++) { ok[(size_t)i] = L.ovf[(size_t)i].first; ov[(size_t)i] = L.ovf[(size_t)i].second; }
+  if (ix->n_ovf) {
+    KV_CUDA(cudaMemcpyAsync(ix->d_ovf_keys.p, ok.data(), (size_t)ix->n_ovf * 8, cudaMemcpyHostToDevice, s));
+    KV_CUDA(cudaMemcpyAsync(ix->d_ovf_vals.p, ov.data(), (size_t)ix->n_ovf * 4, cudaMemcpyHostToDevice, s));
+  }
+  KV_CUDA(cudaStreamSynchronize(s));  // the staging vectors go out of scope
+  {
+    int rc = make_map_f16_nf(&ix->map_u, ix->d_Uf.p, L.n_chunks_pad);
+    if (rc != KV_OK) return rc;
   }
   ix->V = V;
   ix->finalized = true;
@@ -769,42 +569,71 @@ static int score_impl(kv_index *ix, const uint32_t *q_ids, const uint32_t *q_tf,
   if (ix->nnz == 0 && q_nnz == 0 && q_oov_tf2 == 0.0)
     return kv_fail(KV_ERR_EMPTY_VOCAB, "empty vocabulary; perhaps the documents only contain stop words");
   KV_CUDA(cudaSetDevice(ix->device));
-  QueryPrep qp;
-  prep_query(ix, q_ids, q_tf, q_nnz, q_oov_tf2, qp);
-  int log_h = 6;
-  while ((1 << log_h) < 2 * (int)qp.fid.size() + 2) log_h++;
-  if (log_h > 24) return kv_fail(KV_ERR_INVALID, "kv_score: query has too many distinct features");
-  const int H = 1 << log_h;
-  const size_t tab_bytes = (size_t)H * (8 + 8 + 4);
-  KV_CUDA(ix->h_qtab.ensure((int64_t)tab_bytes));
-  KV_CUDA(ix->d_qtab.ensure((int64_t)tab_bytes));
-  double *tw = (double *)ix->h_qtab.p, *tdd = tw + H;
-  uint32_t *tk = (uint32_t *)(tdd + H);
-  for (int i = 0; i < H; i++) { tk[i] = KEY_EMPTY; tw[i] = 0; tdd[i] = 0; }
-  for (size_t i = 0; i < qp.fid.size(); i++) {
-    uint32_t t = qp.fid[i];
-    uint32_t h = (t * 0x9E3779B1u) >> (32 - log_h);
-    while (tk[h] != KEY_EMPTY) h = (h + 1) & (H - 1);
+  // per-query constants in float64 (features in CSR order)
+  const double idf0 = ix->jaccard ? 1.0 : (ix->corpus_fit ? 0.0 : std::log((double)(ix->n_total + 2) / 2.0) + 1.0);
+  double nq = q_oov_tf2 * idf0 * idf0, dotU = 0, corrU = 0, maxdot = 1.0, maxcorr = 1e-30;
+  std::vector<uint32_t> fid, tfq;
+  std::vector<double> fa, fd;
+  for (int64_t i = 0; i < q_nnz; i++) {
+    const uint32_t t = q_ids[i];
+    const double f = (double)q_tf[i];
+    if ((int64_t)t >= ix->V) { nq += f * f * idf0 * idf0; continue; }  // id issued after finalize: in no indexed row
     double a, d;
     idf_host(ix->n_total, ix->h_df[t], a, d, ix->jaccard, ix->corpus_fit);
+    nq += f * f * a;
+    if (ix->h_univ[t]) {
+      const double u = (double)ix->h_utf[t];
+      dotU += f * u * a;
+      corrU += u * u * d;
+    } else {
+      fid.push_back(t); tfq.push_back(q_tf[i]); fa.push_back(a); fd.push_back(d);
+      const double tm = (double)ix->h_tfmax[t];
+      maxdot += f * a * tm;
+      maxcorr += -d * tm * tm;
+    }
+  }
+  int log_h = 6;
+  while ((1 << log_h) < 2 * (int)fid.size() + 2) log_h++;
+  if (log_h > 13) return kv_fail(KV_ERR_INVALID, "kv_score: query has too many distinct features");
+  const int H = 1 << log_h;
+  // fixed point: the largest power-of-two scales that keep every row sum below 2^62
+  const int e_w = std::max(0, std::min(40, (int)std::floor(62.0 - std::log2(maxdot))));
+  const int e_c = std::max(0, std::min(40, (int)std::floor(62.0 - std::log2(maxcorr))));
+  const size_t tab_bytes = (size_t)H * (8 + 8 + 4);
+  KV_CUDA(ix->h_qtab.ensure((int64_t)tab_bytes));
+  KV_CUDA(ix->d_qtab1.ensure((int64_t)tab_bytes));
+  unsigned long long *tw = (unsigned long long *)ix->h_qtab.p, *tc = tw + H;
+  uint32_t *tk = (uint32_t *)(tc + H);
+  for (int i = 0; i < H; i++) { tk[i] = KEY_EMPTY; tw[i] = 0; tc[i] = 0; }
+  for (size_t i = 0; i < fid.size(); i++) {
+    const uint32_t t = fid[i];
+    uint32_t h = (t * 0x9E3779B1u) >> (32 - log_h);
+    while (tk[h] != KEY_EMPTY) h = (h + 1) & (H - 1);
     tk[h] = t;
-    tw[h] = (double)qp.tfq[i] * a;
-    tdd[h] = d;
+    tw[h] = (unsigned long long)std::llrint(std::ldexp((double)tfq[i] * fa[i], e_w));
+    tc[h] = (unsigned long long)std::llrint(std::ldexp(-fd[i], e_c));
   }
   cudaStream_t s = ix->stream;
-  KV_CUDA(cudaMemcpyAsync(ix->d_qtab.p, ix->h_qtab.p, tab_bytes, cudaMemcpyHostToDevice, s));
+  KV_CUDA(cudaMemcpyAsync(ix->d_qtab1.p, ix->h_qtab.p, tab_bytes, cudaMemcpyHostToDevice, s));
   KV_CUDA(ix->d_scores.ensure(ix->n_rows));
   ScoreParams P;
-  P.stream = ix->d_stream.p; P.chunkptr = ix->d_chunkptr.p; P.perm = ix->d_perm.p;
+  P.blk = ix->d_blk.p; P.binfo = ix->d_binfo.p; P.perm = ix->d_perm.p;
   P.n_chunks = ix->n_chunks; P.n_rows = ix->n_rows;
   P.B64 = ix->d_B64.p; P.ovf_keys = ix->d_ovf_keys.p; P.ovf_vals = ix->d_ovf_vals.p; P.n_ovf = ix->n_ovf;
-  P.qw = (const double *)ix->d_qtab.p; P.qd = P.qw + H; P.qkeys = (const uint32_t *)(P.qd + H);
-  P.log_h = log_h; P.table_in_smem = tab_bytes <= 40 * 1024;
-  P.nq = qp.nq; P.dotU = qp.dotU; P.corrU = qp.corrU; P.jaccard = ix->jaccard; P.out = ix->d_scores.p;
+  P.qw = (const unsigned long long *)ix->d_qtab1.p; P.qc = P.qw + H; P.qkeys = (const uint32_t *)(P.qc + H);
+  P.log_h = log_h;
+  P.w_unscale = std::ldexp(1.0, -e_w); P.c_unscale = std::ldexp(1.0, -e_c);
+  P.nq = nq; P.dotU = dotU; P.corrU = corrU; P.jaccard = ix->jaccard; P.out = ix->d_scores.p;
+  const size_t smem = tab_bytes + 8 * 32 * 24;
+  static bool attr_set[64] = {false};
+  if (!attr_set[ix->device & 63]) {
+    KV_CUDA(cudaFuncSetAttribute(tfidf_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set[ix->device & 63] = true;
+  }
   int blocks = (int)std::min<int64_t>((ix->n_chunks + 7) / 8, (int64_t)ix->sm_count * 8);
   if (blocks < 1) blocks = 1;
   KV_CUDA(cudaEventRecord(ix->ev[1], s));
-  tfidf_score_kernel<<<blocks, 256, P.table_in_smem ? tab_bytes : 0, s>>>(P);
+  tfidf_score_kernel<<<blocks, 256, smem, s>>>(P);
   KV_CUDA(cudaGetLastError());
   KV_CUDA(cudaEventRecord(ix->ev[2], s));
   if (out_scores)
@@ -823,11 +652,11 @@ int kv_score(kv_index *ix, const uint32_t *q_ids, const uint32_t *q_tf, int64_t 
   return score_impl(ix, q_ids, q_tf, q_nnz, q_oov_tf2, out_scores);
 }
 
-// ---- batched top-k, in two halves: prepare_batch (host work + H2D) and run_batch (device only) ----
+// ---- batched top-k, in two halves: prepare_batch (host work + H2D + table kernels) and run_batch (device only) ----
 static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
                          const double *q_oov, int64_t n_q) {
   if (!ix->finalized) return kv_fail(KV_ERR_STATE, "kv_topk: index not finalized");
-  if (n_q >= (1LL << 31)) return kv_fail(KV_ERR_INVALID, "kv_topk: too many queries in one call");
+  if (n_q >= (1LL << 31) - TILE_Q) return kv_fail(KV_ERR_INVALID, "kv_topk: too many queries in one call");
   KV_CUDA(cudaSetDevice(ix->device));
   cudaStream_t s = ix->stream;
   ix->batch_valid = false;
@@ -836,165 +665,272 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
   for (int64_t q = 0; q < n_q; q++)
     if (q_indptr[q + 1] < q_indptr[q] || (q_indptr[q + 1] > q_indptr[q] && (!q_ids || !q_tf)))
       return kv_fail(KV_ERR_INVALID, "kv_topk: bad query CSR");
-
-  // ---- host: per-query constants (float64), text order of the queries, tile tables ----
-  KV_CUDA(ix->h_qconst.ensure(6 * n_q));
-  KV_CUDA(ix->h_qperm.ensure(2 * n_q));
-  std::vector<QueryPrep> qp((size_t)n_q);
+  const int64_t base = q_indptr[0], nnz = q_indptr[n_q] - base;
   const int T = host_threads();
+
+  // ---- host: classification of the queries, text order, pinned staging of the CSR ----
+  // null: no feature of the query is in the index (every score is 0).  irregular: more features than a query table
+  // holds, or term frequencies so large that the 64-bit fixed-point sums or the fp16 bound weights could overflow --
+  // such a query takes the float64 full-scan path (K1a + selection).
+  const double amax = ix->jaccard ? 1.0 : std::pow(std::log((double)(ix->n_total + 2)) + 1.0, 2.0);
+  std::vector<uint8_t> flag((size_t)n_q, 0);
   parallel_for(n_q, n_q >= 2048 ? T : 1, [&](int, int64_t a, int64_t b) {
-    for (int64_t q = a; q < b; q++)
-      prep_query(ix, q_ids + q_indptr[q], q_tf + q_indptr[q], q_indptr[q + 1] - q_indptr[q], q_oov ? q_oov[q] : 0.0,
-                 qp[(size_t)q]);
+    for (int64_t q = a; q < b; q++) {
+      bool known = false;
+      int feats = 0;
+      double s_dot = 0, s_corr = 0, wmax = 0;
+      for (int64_t p = q_indptr[q]; p < q_indptr[q + 1]; p++) {
+        const uint32_t t = q_ids[p];
+        if ((int64_t)t >= ix->V) continue;
+        known = true;
+        if (ix->h_univ[t]) continue;
+        feats++;
+        const double tm = (double)ix->h_tfmax[t], f = (double)q_tf[p];
+        s_dot += f * tm;
+        s_corr += tm * tm;
+        wmax = std::max(wmax, f);
+      }
+      if (!known) flag[(size_t)q] = 1;
+      else if (feats > QFEATS || s_dot * amax >= 1073741824.0 || s_corr * 32.0 >= 1073741824.0 || wmax * amax > 60000.0)
+        flag[(size_t)q] = 2;
+    }
   });
-  // queries with similar text share a tile: smaller feature tables, and tile-wide pruning works
+  // queries with similar text share a scan group and a bound tile (their candidates are largely the same chunks)
   std::vector<int> order((size_t)n_q);
   for (int64_t q = 0; q < n_q; q++) order[(size_t)q] = (int)q;
-  // first key: class of the query norm (queries with much out-of-corpus mass have low scores and low
-  // k-th-score thresholds; mixing them with strong queries would block the tile-wide pruning)
-  std::vector<short> qcls((size_t)n_q);
-  for (int64_t q = 0; q < n_q; q++)
-    qcls[(size_t)q] = qp[(size_t)q].nq > 0 ? (short)std::floor(std::log2(qp[(size_t)q].nq) * 2.0) : (short)-1000;
   stable_sort_indices(order, [&](int a, int b) {
-    if (qcls[(size_t)a] != qcls[(size_t)b]) return qcls[(size_t)a] < qcls[(size_t)b];
     return cmp_seq(q_ids + q_indptr[a], q_indptr[a + 1] - q_indptr[a], q_ids + q_indptr[b], q_indptr[b + 1] - q_indptr[b]) < 0;
   }, T);  // == std::stable_sort, on all host threads
-  float *c_nq = ix->h_qconst.p, *c_dotU = c_nq + n_q, *c_corrU = c_dotU + n_q, *c_ninf = c_corrU + n_q;
-  float *c_dotS = c_ninf + n_q, *c_corrS = c_dotS + n_q;
+  KV_CUDA(ix->h_qperm.ensure(2 * n_q));
+  KV_CUDA(ix->h_flags.ensure(n_q));
+  KV_CUDA(ix->h_q_indptr.ensure(n_q + 1));
+  KV_CUDA(ix->h_q_ids.ensure(std::max<int64_t>(nnz, 1)));
+  KV_CUDA(ix->h_q_tf.ensure(std::max<int64_t>(nnz, 1)));
+  KV_CUDA(ix->h_q_oov.ensure(n_q));
   int *qperm = ix->h_qperm.p, *null_list = qperm + n_q;
   int64_t n_null = 0;
-  std::vector<char> skip((size_t)n_q, 0);  // by sorted slot: not part of any tile table
   for (int64_t i = 0; i < n_q; i++) {
     const int64_t q = order[(size_t)i];
-    const QueryPrep &p = qp[(size_t)q];
     qperm[i] = (int)q;
-    c_dotU[i] = (float)p.dotU;
-    c_corrU[i] = (float)p.corrU;
-    c_ninf[i] = -INFINITY;
-    c_dotS[i] = (float)(p.dotS * (1.0 + 1e-6));  // bounds may only err upwards
-    c_corrS[i] = (float)p.corrS;
-    int nx = 0;
-    for (uint32_t f : p.tfq) nx += f > 1;
-    const bool null_q = p.nq <= 0.0 || (p.fid.empty() && p.dotU == 0.0);  // every score is 0
-    const bool irregular = (int)p.fid.size() > TILE_MAX_FEATURES || nx > TXCAP;
-    c_nq[i] = (null_q || irregular) ? 0.f : (float)p.nq;  // nq == 0 switches the lane off in the kernel
-    if (null_q) {
+    ix->h_flags.p[i] = flag[(size_t)q];
+    if (flag[(size_t)q] == 1) {
       null_list[n_null++] = (int)q;
-      skip[(size_t)i] = 1;
-    } else if (irregular) {  // too many features for a tile: full float64 scan + selection instead
+    } else if (flag[(size_t)q] == 2) {
       const int64_t a = q_indptr[q], b = q_indptr[q + 1];
       ix->irr_q.push_back(q);
       ix->irr_ids.insert(ix->irr_ids.end(), q_ids + a, q_ids + b);
       ix->irr_tf.insert(ix->irr_tf.end(), q_tf + a, q_tf + b);
       ix->irr_indptr.push_back((int64_t)ix->irr_ids.size());
       ix->irr_oov.push_back(q_oov ? q_oov[q] : 0.0);
-      skip[(size_t)i] = 1;
     }
   }
-  // tiles: consecutive sorted queries, closed when 128 queries are in or the feature table is full (tile_builder.cuh:
-  // built on all host threads when no table cap is hit, else by the sequential rule -- identical bytes either way)
-  std::vector<TileDesc> tiles;
-  std::vector<unsigned char> tables;
-  {
-    const TileCtx cx{ix->n_total, ix->h_df.data(), ix->jaccard, ix->corpus_fit};
-    if (getenv("KAKVEDA_B200_SERIAL_TILES") || !build_tiles_parallel(cx, qp, order, skip, T, tiles, tables))
-      build_tiles_serial(cx, qp, order, skip, tiles, tables);
-  }
-  const int64_t n_tiles = (int64_t)tiles.size();
-  KV_CUDA(ix->h_tables.ensure(n_tiles * (int64_t)Tile::table_bytes));
-  KV_CUDA(ix->h_tiles.ensure(n_tiles));
-  memcpy(ix->h_tables.p, tables.data(), (size_t)n_tiles * Tile::table_bytes);
-  memcpy(ix->h_tiles.p, tiles.data(), (size_t)n_tiles * sizeof(TileDesc));
+  parallel_for(n_q + 1, n_q >= 65536 ? T : 1, [&](int, int64_t a, int64_t b) {
+    for (int64_t q = a; q < b; q++) {
+      ix->h_q_indptr.p[q] = q_indptr[q] - base;
+      if (q < n_q) ix->h_q_oov.p[q] = q_oov ? q_oov[q] : 0.0;
+    }
+  });
+  parallel_for(nnz, nnz >= (1 << 20) ? T : 1, [&](int, int64_t a, int64_t b) {
+    if (b > a) {
+      memcpy(ix->h_q_ids.p + a, q_ids + base + a, (size_t)(b - a) * 4);
+      memcpy(ix->h_q_tf.p + a, q_tf + base + a, (size_t)(b - a) * 4);
+    }
+  });
 
-  KV_CUDA(ix->d_tables.ensure(n_tiles * (int64_t)Tile::table_bytes));
-  KV_CUDA(ix->d_tiles.ensure(n_tiles));
-  KV_CUDA(ix->d_qconst.ensure(6 * n_q));
+  const int64_t n_tiles = (n_q + TILE_Q - 1) / TILE_Q, n_q_pad = n_tiles * TILE_Q;
+  KV_CUDA(ix->d_q_indptr.ensure(n_q + 1));
+  KV_CUDA(ix->d_q_ids.ensure(std::max<int64_t>(nnz, 1)));
+  KV_CUDA(ix->d_q_tf.ensure(std::max<int64_t>(nnz, 1)));
+  KV_CUDA(ix->d_q_oov.ensure(n_q));
   KV_CUDA(ix->d_qperm.ensure(2 * n_q));
+  KV_CUDA(ix->d_flags.ensure(n_q));
+  KV_CUDA(ix->d_qconst.ensure(7 * n_q));
+  KV_CUDA(ix->d_qtab.ensure(n_q * (int64_t)QTAB_BYTES));
+  KV_CUDA(ix->d_rtab.ensure(n_tiles * (int64_t)RTAB_BYTES));
+  KV_CUDA(ix->d_Wf.ensure(n_q_pad * NF));
   KV_CUDA(cudaEventRecord(ix->ev[0], s));
-  KV_CUDA(cudaMemcpyAsync(ix->d_tables.p, ix->h_tables.p, (size_t)n_tiles * Tile::table_bytes, cudaMemcpyHostToDevice, s));
-  KV_CUDA(cudaMemcpyAsync(ix->d_tiles.p, ix->h_tiles.p, (size_t)n_tiles * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
-  KV_CUDA(cudaMemcpyAsync(ix->d_qconst.p, ix->h_qconst.p, (size_t)6 * n_q * sizeof(float), cudaMemcpyHostToDevice, s));
+  KV_CUDA(cudaMemcpyAsync(ix->d_q_indptr.p, ix->h_q_indptr.p, (size_t)(n_q + 1) * 8, cudaMemcpyHostToDevice, s));
+  if (nnz) {
+    KV_CUDA(cudaMemcpyAsync(ix->d_q_ids.p, ix->h_q_ids.p, (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
+    KV_CUDA(cudaMemcpyAsync(ix->d_q_tf.p, ix->h_q_tf.p, (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
+  }
+  KV_CUDA(cudaMemcpyAsync(ix->d_q_oov.p, ix->h_q_oov.p, (size_t)n_q * 8, cudaMemcpyHostToDevice, s));
   KV_CUDA(cudaMemcpyAsync(ix->d_qperm.p, ix->h_qperm.p, (size_t)2 * n_q * sizeof(int), cudaMemcpyHostToDevice, s));
+  KV_CUDA(cudaMemcpyAsync(ix->d_flags.p, ix->h_flags.p, (size_t)n_q, cudaMemcpyHostToDevice, s));
   KV_CUDA(cudaEventRecord(ix->ev[1], s));
+  // ---- device: per-query constants and tables, per-tile rare-feature tables ----
+  KV_CUDA(cudaMemsetAsync(ix->d_Wf.p, 0, (size_t)n_q_pad * NF * sizeof(__half), s));
+  PrepParams P;
+  P.q_indptr = ix->d_q_indptr.p; P.q_ids = ix->d_q_ids.p; P.q_tf = ix->d_q_tf.p; P.q_oov = ix->d_q_oov.p;
+  P.qperm = ix->d_qperm.p; P.flags = ix->d_flags.p;
+  P.n_q = n_q; P.V = ix->V; P.n_total = ix->n_total;
+  P.a64 = ix->d_a64.p; P.d64 = ix->d_d64.p; P.univ = ix->d_univ.p; P.utf = ix->d_utf.p; P.tfmax = ix->d_tfmax.p;
+  P.fslot = ix->d_fslot.p; P.jaccard = ix->jaccard; P.corpus_fit = ix->corpus_fit;
+  P.q_nq = ix->d_qconst.p; P.q_dotU = P.q_nq + n_q; P.q_corrU = P.q_nq + 2 * n_q; P.q_dotS = P.q_nq + 3 * n_q;
+  P.q_corrS = P.q_nq + 4 * n_q; P.q_dotX = P.q_nq + 5 * n_q;
+  P.qtab = ix->d_qtab.p; P.Wf = ix->d_Wf.p; P.rtab = ix->d_rtab.p;
+  prep_queries_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, s>>>(P);
+  KV_CUDA(cudaGetLastError());
+  static bool attr_set[64] = {false};
+  const int prep_smem = RT_SLOTS * 4 * 6;
+  if (!attr_set[ix->device & 63]) {
+    KV_CUDA(cudaFuncSetAttribute(prep_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
+    attr_set[ix->device & 63] = true;
+  }
+  prep_tiles_kernel<<<(unsigned)n_tiles, TILE_Q, prep_smem, s>>>(P);
+  KV_CUDA(cudaGetLastError());
+  {
+    int rc = make_map_f16_nf(&ix->map_w, ix->d_Wf.p, n_q_pad);
+    if (rc != KV_OK) return rc;
+  }
   KV_CUDA(cudaStreamSynchronize(s));  // the pinned staging buffers may be rewritten by the next call
   ix->batch_q = n_q;
   ix->batch_tiles = n_tiles;
   ix->batch_null = n_null;
-  ix->batch_h2d_bytes = n_tiles * (int64_t)(Tile::table_bytes + sizeof(TileDesc)) + 6 * n_q * (int64_t)sizeof(float) +
-                        2 * n_q * (int64_t)sizeof(int);
+  ix->batch_h2d_bytes = (n_q + 1) * 8 + nnz * 8 + n_q * 8 + 2 * n_q * (int64_t)sizeof(int) + n_q;
   ix->batch_valid = true;
   cudaEventElapsedTime(&ix->last_ms[0], ix->ev[0], ix->ev[1]);
   return KV_OK;
 }
 
-// Device-only half: scan + merge (+ fallback scans for irregular queries) of the uploaded batch.
+// Device-only half: bounds + scans + merge (+ fallback scans for irregular queries) of the uploaded batch.
 static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
   if (!ix->batch_valid) return kv_fail(KV_ERR_STATE, "kv_topk_resident: no query batch uploaded");
   if (k < 1 || k > 32) return kv_fail(KV_ERR_INVALID, "kv_topk: k must be 1..32");
   KV_CUDA(cudaSetDevice(ix->device));
   cudaStream_t s = ix->stream;
   const int64_t n_q = ix->batch_q, n_tiles = ix->batch_tiles;
-  // launch geometry: tiles x row-splits.  Without pruning every CTA streams its whole row range, so
-  // aim at >= 8 waves of resident CTAs; with pruning a CTA owns a tile's whole row range unless
-  // there are too few tiles to fill the GPU.
+  const int64_t n_groups = (n_q + GROUP_Q - 1) / GROUP_Q;
+  const int64_t n_blocks = (ix->n_chunks + B_BN - 1) / B_BN;
+  // Pruned mode: bound pass 0 -> seed scan -> bound pass 1 -> scan of the candidates.  Exhaustive mode (small
+  // indexes, KAKVEDA_B200_NO_PRUNE=1): every chunk is a candidate of every query.
   const char *env = getenv("KAKVEDA_B200_NO_PRUNE");
-  const int prune = (env && env[0] == '1') ? 0 : (ix->n_chunks >= 64 ? 1 : 0);
-  const int ctas_per_sm = 3;
-  int64_t want = (int64_t)ix->sm_count * ctas_per_sm * 8;
-  int64_t n_splits = (want + n_tiles - 1) / n_tiles;
-  n_splits = std::max<int64_t>(1, std::min<int64_t>(n_splits, std::max<int64_t>(1, ix->n_chunks / (2 * SUM_GROUP))));
-  n_splits = std::min<int64_t>(n_splits, 2048);
-  ix->last_tiles = n_tiles; ix->last_splits = n_splits; ix->last_ctas = n_tiles * n_splits;
+  const int prune = (env && env[0] == '1') ? 0 : (ix->n_chunks >= 4 * B_BN ? 1 : 0);
+  int64_t n_bsplits, n_ssplits;
+  if (prune) {
+    n_bsplits = std::max<int64_t>(1, std::min<int64_t>((ix->sm_count + n_tiles - 1) / n_tiles, n_blocks));
+    n_ssplits = std::max<int64_t>(1, std::min<int64_t>((4LL * ix->sm_count + n_groups * n_bsplits - 1) / (n_groups * n_bsplits), 8));
+  } else {
+    n_bsplits = std::max<int64_t>(1, std::min<int64_t>((8LL * ix->sm_count + n_groups - 1) / n_groups,
+                                                        std::min<int64_t>(1024, std::max<int64_t>(1, ix->n_chunks / 4))));
+    n_ssplits = 1;
+  }
+  const int64_t n_lists = n_groups * n_bsplits, n_parts = n_bsplits * n_ssplits;
+  const int64_t n_ssplits_a = std::max<int64_t>(1, std::min<int64_t>((4LL * ix->sm_count + n_groups - 1) / n_groups, 8));
+  ix->last_tiles = n_tiles; ix->last_splits = n_parts; ix->last_ctas = n_lists * n_ssplits;
   if (n_q > ix->d_gthr.cap && (ix->gthr_exported || ix->n_peers))
     return kv_fail(KV_ERR_STATE, "kv_topk: the query batch outgrew the threshold array shared with the peer GPUs; exchange it again "
                                  "(kv_index_thresholds_export / kv_index_thresholds_peers)");
   KV_CUDA(ix->d_gthr.ensure(n_q));
   const int n_peers = (ix->n_peers > 0 && n_q <= ix->peer_cap) ? ix->n_peers : 0;
-  KV_CUDA(ix->d_part_s.ensure(n_splits * n_q * k));
-  KV_CUDA(ix->d_part_r.ensure(n_splits * n_q * k));
+  const int64_t parts_alloc = std::max(n_parts, n_ssplits_a);
+  KV_CUDA(ix->d_part_s.ensure(parts_alloc * n_q * k));
+  KV_CUDA(ix->d_part_r.ensure(parts_alloc * n_q * k));
   KV_CUDA(ix->d_stats.ensure(8));
-  if (prune) KV_CUDA(ix->d_ubuf.ensure(n_tiles * ix->n_chunks));
-
-  KV_CUDA(cudaEventRecord(ix->ev[1], s));
-  if (ix->n_rows > 0) {
-    // global lower bounds of the k-th score start at -inf (staged as the 4th constants column)
-    KV_CUDA(cudaMemcpyAsync(ix->d_gthr.p, ix->d_qconst.p + 3 * n_q, (size_t)n_q * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    KV_CUDA(cudaMemsetAsync(ix->d_stats.p, 0, 8 * sizeof(unsigned long long), s));
-    TopkParams P;
-    P.stream = ix->d_stream.p; P.chunkptr = ix->d_chunkptr.p; P.sum_stream = ix->d_sum_stream.p; P.sumptr = ix->d_sumptr.p;
-    P.chunk_minB = ix->d_cminB.p; P.perm = ix->d_perm.p;
-    P.grp_stream = ix->d_grp_stream.p; P.grpptr = ix->d_grpptr.p;
-    P.n_chunks = ix->n_chunks; P.n_rows = ix->n_rows;
-    P.row_base = ix->row_base; P.B32 = ix->d_B32.p; P.ovf_keys = ix->d_ovf_keys.p; P.ovf_vals = ix->d_ovf_vals.p;
-    P.n_ovf = ix->n_ovf; P.tables = ix->d_tables.p; P.tiles = ix->d_tiles.p;
-    P.q_nq = ix->d_qconst.p; P.q_dotU = P.q_nq + n_q; P.q_corrU = P.q_dotU + n_q;
-    P.q_dotS = P.q_nq + 4 * n_q; P.q_corrS = P.q_nq + 5 * n_q;
-    P.q_excl = ix->has_excl ? ix->d_excl_sorted.p : nullptr;
-    P.gthr = ix->d_gthr.p; P.ubuf = ix->d_ubuf.p; P.stats = ix->d_stats.p;
-    P.n_q = n_q; P.k = k; P.n_splits = (int)n_splits; P.prune = prune; P.jaccard = ix->jaccard;
-    for (int i = 0; i < 7; i++) P.peer_gthr[i] = i < n_peers ? ix->peer_gthr[i] : nullptr;
-    P.n_peers = n_peers;
-    P.share = (n_splits > 1 || n_peers > 0) ? 1 : 0;
-    P.part_scores = ix->d_part_s.p; P.part_rows = ix->d_part_r.p;
-    const size_t smem = Tile::smem_bytes(k);
-    static bool attr_set[64] = {false};
-    if (!attr_set[ix->device & 63]) {
-      KV_CUDA(cudaFuncSetAttribute(tfidf_topk_kernel<TG, TLOGH, TXCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)Tile::smem_bytes(32)));
-      attr_set[ix->device & 63] = true;
+  const int n_seed = (int)n_bsplits * B_SEEDS_PER_QUERY;
+  const int64_t chunks_per_split = ((n_blocks + n_bsplits - 1) / n_bsplits + 1) * B_BN;
+  const int max_pages = (int)(chunks_per_split / PAGE_RECS + 2);
+  if (prune) {
+    KV_CUDA(ix->d_seeds.ensure(n_q * n_seed));
+    KV_CUDA(ix->d_direct.ensure(n_groups * GROUP_Q * n_seed));
+    KV_CUDA(ix->d_list_count.ensure(n_groups + n_lists));
+    KV_CUDA(ix->d_list_pages.ensure(n_lists * max_pages));
+    const int64_t want_pages = std::min<int64_t>(n_lists * max_pages, 131072 + n_lists);
+    if (want_pages > ix->pool_pages) {
+      KV_CUDA(ix->d_pool.ensure(want_pages * PAGE_RECS));
+      ix->pool_pages = want_pages;
     }
-    dim3 grid((unsigned)n_tiles, (unsigned)n_splits);
-    tfidf_topk_kernel<TG, TLOGH, TXCAP><<<grid, 256, smem, s>>>(P);
+    KV_CUDA(ix->d_pool_ctl.ensure(2));
+  }
+  static bool attr_set[64] = {false};
+  if (!attr_set[ix->device & 63]) {
+    KV_CUDA(cudaFuncSetAttribute(tfidf_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(32)));
+    KV_CUDA(cudaFuncSetAttribute(tfidf_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set[ix->device & 63] = true;
+  }
+  if (prune && bound_smem_bytes(max_pages) > 232448)
+    return kv_fail(KV_ERR_INVALID, "kv_topk: index too large for one bound-kernel row range (max_pages %d)", max_pages);
+
+  int64_t launches = 0;
+  KV_CUDA(cudaEventRecord(ix->ev[1], s));
+  for (auto &e : ix->evk) KV_CUDA(cudaEventRecord(e, s));
+  if (ix->n_rows > 0) {
+    // global lower bounds of the k-th score start at -inf
+    const float *qc = ix->d_qconst.p;
+    KV_CUDA(cudaMemsetAsync(ix->d_stats.p, 0, 8 * sizeof(unsigned long long), s));
+    fill_int_kernel<<<(unsigned)((n_q + 255) / 256), 256, 0, s>>>(ix->d_gthr.p, n_q, (int)0xFF800000);
     KV_CUDA(cudaGetLastError());
+    launches++;
+    ScanParams SP;
+    SP.blk = ix->d_blk.p; SP.binfo = ix->d_binfo.p; SP.B32 = ix->d_B32.p; SP.perm = ix->d_perm.p;
+    SP.n_chunks = ix->n_chunks; SP.n_rows = ix->n_rows; SP.row_base = ix->row_base;
+    SP.ovf_keys = ix->d_ovf_keys.p; SP.ovf_vals = ix->d_ovf_vals.p; SP.n_ovf = ix->n_ovf;
+    SP.qtab = ix->d_qtab.p; SP.q_nq = qc; SP.q_dotU = qc + n_q; SP.q_corrU = qc + 2 * n_q;
+    SP.q_excl = ix->has_excl ? ix->d_excl_sorted.p : nullptr;
+    SP.gthr = ix->d_gthr.p;
+    for (int i = 0; i < 7; i++) SP.peer_gthr[i] = i < n_peers ? ix->peer_gthr[i] : nullptr;
+    SP.n_peers = n_peers;
+    SP.stats = ix->d_stats.p; SP.n_q = n_q; SP.k = k; SP.jaccard = ix->jaccard;
+    SP.part_scores = ix->d_part_s.p; SP.part_rows = ix->d_part_r.p;
+    SP.list_count = nullptr; SP.list_pages = nullptr; SP.max_pages = max_pages; SP.pool = nullptr; SP.direct = nullptr;
+    SP.direct_stride = 0;
+    const size_t s_smem = scan_smem_bytes(k);
+    if (prune) {
+      KV_CUDA(cudaMemsetAsync(ix->d_pool_ctl.p, 0, 2 * sizeof(unsigned int), s));
+      BoundParams BP;
+      BP.blk = ix->d_blk.p; BP.binfo = ix->d_binfo.p; BP.chunk_minB = ix->d_cminB.p;
+      BP.ovf_keys = ix->d_ovf_keys.p; BP.ovf_vals = ix->d_ovf_vals.p; BP.n_ovf = ix->n_ovf;
+      BP.n_chunks = ix->n_chunks; BP.n_q = n_q; BP.rtab = ix->d_rtab.p;
+      BP.q_nq = qc; BP.q_dotS = qc + 3 * n_q; BP.q_corrS = qc + 4 * n_q; BP.q_dotX = qc + 5 * n_q;
+      BP.gthr = ix->d_gthr.p; BP.n_bsplits = (int)n_bsplits; BP.jaccard = ix->jaccard;
+      BP.seeds = ix->d_seeds.p;
+      BP.list_count = ix->d_list_count.p + n_groups; BP.list_pages = ix->d_list_pages.p; BP.max_pages = max_pages;
+      BP.pool = ix->d_pool.p; BP.pool_next = ix->d_pool_ctl.p; BP.pool_pages = (unsigned int)ix->pool_pages;
+      BP.overflow = (int *)(ix->d_pool_ctl.p + 1); BP.stats = ix->d_stats.p;
+      const size_t b_smem = bound_smem_bytes(max_pages);
+      const dim3 bgrid((unsigned)n_tiles, (unsigned)n_bsplits);
+      // pass 0: seeds
+      KV_CUDA(cudaEventRecord(ix->evk[0], s));
+      BP.pass = 0;
+      tfidf_bound_kernel<<<bgrid, B_THREADS, b_smem, s>>>(ix->map_w, ix->map_u, BP);
+      KV_CUDA(cudaGetLastError());
+      seeds_to_lists_kernel<<<(unsigned)((n_groups * GROUP_Q * n_seed + 255) / 256), 256, 0, s>>>(ix->d_seeds.p, n_q, n_seed,
+                                                                                                 ix->d_direct.p, ix->d_list_count.p);
+      KV_CUDA(cudaGetLastError());
+      KV_CUDA(cudaEventRecord(ix->evk[1], s));
+      // seed scan: gives every query a lower bound of its k-th score
+      SP.list_mode = 1; SP.list_count = ix->d_list_count.p; SP.direct = ix->d_direct.p; SP.direct_stride = GROUP_Q * n_seed;
+      SP.n_bsplits = 1; SP.n_ssplits = (int)n_ssplits_a;
+      tfidf_scan_kernel<<<dim3((unsigned)n_groups, (unsigned)n_ssplits_a), S_WARPS * 32, s_smem, s>>>(SP);
+      KV_CUDA(cudaGetLastError());
+      KV_CUDA(cudaEventRecord(ix->evk[2], s));
+      // pass 1: candidate lists
+      BP.pass = 1;
+      tfidf_bound_kernel<<<bgrid, B_THREADS, b_smem, s>>>(ix->map_w, ix->map_u, BP);
+      KV_CUDA(cudaGetLastError());
+      KV_CUDA(cudaEventRecord(ix->evk[3], s));
+      SP.list_mode = 0; SP.list_count = ix->d_list_count.p + n_groups; SP.list_pages = ix->d_list_pages.p;
+      SP.pool = ix->d_pool.p; SP.direct = nullptr;
+      launches += 4;
+    } else {
+      SP.list_mode = 2;
+    }
+    SP.n_bsplits = (int)n_bsplits; SP.n_ssplits = (int)n_ssplits;
+    tfidf_scan_kernel<<<dim3((unsigned)n_lists, (unsigned)n_ssplits), S_WARPS * 32, s_smem, s>>>(SP);
+    KV_CUDA(cudaGetLastError());
+    KV_CUDA(cudaEventRecord(ix->evk[4], s));
     KV_CUDA(cudaEventRecord(ix->ev[2], s));
-    merge_topk_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, s>>>(ix->d_part_s.p, ix->d_part_r.p, (int)n_splits,
+    merge_topk_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, s>>>(ix->d_part_s.p, ix->d_part_r.p, (int)n_parts,
                                                                          n_q, k, ix->d_qperm.p, d_out_s, d_out_r);
     KV_CUDA(cudaGetLastError());
+    KV_CUDA(cudaEventRecord(ix->evk[5], s));
+    launches += 2;
     if (ix->batch_null) {
       fill_null_kernel<<<(unsigned)((ix->batch_null * k + 255) / 256), 256, 0, s>>>(ix->d_qperm.p + n_q, (int)ix->batch_null, k,
                                                                                     ix->n_rows, ix->row_base,
                                                                                     ix->has_excl ? ix->d_excl_orig.p : nullptr, d_out_s, d_out_r);
       KV_CUDA(cudaGetLastError());
+      launches++;
     }
     for (size_t i = 0; i < ix->irr_q.size(); i++) {
       const int64_t q = ix->irr_q[i], a = ix->irr_indptr[i], b = ix->irr_indptr[i + 1];
@@ -1003,8 +939,10 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
       select_topk_kernel<<<1, 1024, 0, s>>>(ix->d_scores.p, ix->n_rows, ix->row_base, k,
                                             ix->has_excl ? (int64_t)ix->h_excl_orig[(size_t)q] : -1, d_out_s + q * k, d_out_r + q * k);
       KV_CUDA(cudaGetLastError());
+      launches += 2;
     }
     KV_CUDA(cudaMemcpyAsync(ix->last_stats, ix->d_stats.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    if (prune) KV_CUDA(cudaMemcpyAsync(&ix->last_stats[6], ix->d_pool_ctl.p, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
   } else {
     KV_CUDA(cudaEventRecord(ix->ev[2], s));
     std::vector<float> es((size_t)(n_q * k), -INFINITY);
@@ -1013,7 +951,21 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
     KV_CUDA(cudaMemcpyAsync(d_out_r, er.data(), er.size() * 8, cudaMemcpyHostToDevice, s));
     KV_CUDA(cudaStreamSynchronize(s));
   }
+  ix->last_launches = launches;
   KV_CUDA(cudaEventRecord(ix->ev[3], s));
+  return KV_OK;
+}
+
+// after the stream is synchronised: timings of the batch and the candidate-pool check
+static int finish_batch(kv_index *ix) {
+  for (int i = 1; i < 4; i++) cudaEventElapsedTime(&ix->last_ms[i], ix->ev[i], ix->ev[i + 1]);
+  for (int i = 0; i < 5; i++) cudaEventElapsedTime(&ix->last_kernel_ms[i], ix->evk[i], ix->evk[i + 1]);
+  const unsigned int *ctl = (const unsigned int *)&ix->last_stats[6];
+  if (ix->n_rows > 0 && ctl[1] != 0) {
+    ix->last_stats[6] = 0;
+    return kv_fail(KV_ERR_NOMEM, "kv_topk: the candidate pool (%lld pages) is exhausted; split the query batch",
+                   (long long)ix->pool_pages);
+  }
   return KV_OK;
 }
 
@@ -1047,8 +999,7 @@ static int topk_impl(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_id
     memcpy(h_scores, ix->h_out_s.p, (size_t)n_q * k * sizeof(float));
     memcpy(h_rows, ix->h_out_r.p, (size_t)n_q * k * sizeof(int64_t));
   }
-  for (int i = 1; i < 4; i++) cudaEventElapsedTime(&ix->last_ms[i], ix->ev[i], ix->ev[i + 1]);
-  return KV_OK;
+  return finish_batch(ix);
 }
 
 int kv_query_upload(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
@@ -1102,11 +1053,8 @@ int kv_rescore_pairs(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_id
   std::vector<int64_t> ip((size_t)n_q + 1);
   for (int64_t q = 0; q <= n_q; q++) ip[(size_t)q] = q_indptr[q] - q_indptr[0];
   parallel_for(n_q, n_q >= 2048 ? host_threads() : 1, [&](int, int64_t a, int64_t b) {
-    QueryPrep qp;
-    for (int64_t q = a; q < b; q++) {
-      prep_query(ix, q_ids + q_indptr[q], q_tf + q_indptr[q], q_indptr[q + 1] - q_indptr[q], q_oov_tf2 ? q_oov_tf2[q] : 0.0, qp);
-      cst[(size_t)q] = qp.nq;
-    }
+    for (int64_t q = a; q < b; q++)
+      cst[(size_t)q] = host_query_norm(ix, q_ids + q_indptr[q], q_tf + q_indptr[q], q_indptr[q + 1] - q_indptr[q], q_oov_tf2 ? q_oov_tf2[q] : 0.0);
   });
   KV_CUDA(ix->d_rq_indptr.ensure(n_q + 1)); KV_CUDA(ix->d_rq_ids.ensure(std::max<int64_t>(nnz, 1)));
   KV_CUDA(ix->d_rq_tf.ensure(std::max<int64_t>(nnz, 1))); KV_CUDA(ix->d_rq_const.ensure(n_q));
@@ -1168,8 +1116,7 @@ int kv_topk_resident_host(kv_index *ix, int k, float *out_scores, int64_t *out_r
   KV_CUDA(cudaMemcpyAsync(out_rows, ix->d_out_r.p, (size_t)n_q * k * sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
   KV_CUDA(cudaEventRecord(ix->ev[4], ix->stream));
   KV_CUDA(cudaStreamSynchronize(ix->stream));
-  for (int i = 1; i < 4; i++) cudaEventElapsedTime(&ix->last_ms[i], ix->ev[i], ix->ev[i + 1]);
-  return KV_OK;
+  return finish_batch(ix);
 }
 
 int kv_index_thresholds_export(kv_index *ix, int64_t capacity, void *handle_out) {
@@ -1219,8 +1166,7 @@ int kv_topk_resident(kv_index *ix, int k, void *d_scores, void *d_rows) {
   if (rc != KV_OK) return rc;
   KV_CUDA(cudaEventRecord(ix->ev[4], ix->stream));
   KV_CUDA(cudaStreamSynchronize(ix->stream));
-  for (int i = 1; i < 4; i++) cudaEventElapsedTime(&ix->last_ms[i], ix->ev[i], ix->ev[i + 1]);
-  return KV_OK;
+  return finish_batch(ix);
 }
 
 int kv_topk(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
@@ -1237,21 +1183,35 @@ int kv_topk_device(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids,
 
 int kv_merge_topk_device(int device, const void *d_scores_in, const void *d_rows_in, int n_lists, int64_t n_q, int k,
                          void *d_scores_out, void *d_rows_out) {
+  return kv_merge_topk_device_on(device, d_scores_in, d_rows_in, n_lists, n_q, k, d_scores_out, d_rows_out, nullptr, 1);
+}
+
+// stream: the CUDA stream (cudaStream_t) the input lists were produced on -- e.g. the stream an NCCL all-gather was
+// enqueued on -- or NULL for the legacy default stream; sync != 0 waits for the merge before returning
+int kv_merge_topk_device_on(int device, const void *d_scores_in, const void *d_rows_in, int n_lists, int64_t n_q, int k,
+                            void *d_scores_out, void *d_rows_out, void *stream, int sync) {
   if (n_lists < 1 || n_lists > 2048 || n_q < 0 || k < 1 || k > 255 || !d_scores_in || !d_rows_in || !d_scores_out || !d_rows_out)
     return kv_fail(KV_ERR_INVALID, "kv_merge_topk_device: bad arguments");
   if (n_q == 0) return KV_OK;
   KV_CUDA(cudaSetDevice(device));
-  merge_topk_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256>>>((const float *)d_scores_in, (const long long *)d_rows_in,
-                                                                 n_lists, n_q, k, nullptr, (float *)d_scores_out,
-                                                                 (long long *)d_rows_out);
+  cudaStream_t s = (cudaStream_t)stream;
+  merge_topk_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, s>>>((const float *)d_scores_in, (const long long *)d_rows_in,
+                                                                       n_lists, n_q, k, nullptr, (float *)d_scores_out,
+                                                                       (long long *)d_rows_out);
   KV_CUDA(cudaGetLastError());
-  KV_CUDA(cudaDeviceSynchronize());
+  if (sync) KV_CUDA(cudaStreamSynchronize(s));
   return KV_OK;
 }
 
 int kv_index_last_timing(const kv_index *ix, float ms[4]) {
   if (!ix || !ms) return kv_fail(KV_ERR_INVALID, "kv_index_last_timing: bad arguments");
   for (int i = 0; i < 4; i++) ms[i] = ix->last_ms[i];
+  return KV_OK;
+}
+
+int kv_index_last_kernel_ms(const kv_index *ix, float ms[5]) {
+  if (!ix || !ms) return kv_fail(KV_ERR_INVALID, "kv_index_last_kernel_ms: bad arguments");
+  for (int i = 0; i < 5; i++) ms[i] = ix->last_kernel_ms[i];
   return KV_OK;
 }
 
@@ -1263,17 +1223,22 @@ int kv_index_last_score_ms(const kv_index *ix, float *ms) {
 
 int kv_index_layout(const kv_index *ix, int64_t bytes[4], int64_t counts[17]) {
   if (!ix || !bytes || !counts) return kv_fail(KV_ERR_INVALID, "kv_index_layout: bad arguments");
-  bytes[0] = ix->stream_len * 4;
+  bytes[0] = ix->blk_words * 4;
   bytes[1] = ix->n_rows * 4;
-  bytes[2] = (ix->n_chunks + 1) * 8;
-  bytes[3] = (ix->sum_len + ix->grp_len) * 4 + (ix->n_chunks + 1) * 12;
-  counts[0] = ix->stream_len; counts[1] = ix->n_univ; counts[2] = ix->n_rows;
+  bytes[2] = ix->n_chunks_pad * (int64_t)sizeof(BlockInfo);
+  bytes[3] = ix->n_chunks_pad * (int64_t)(NF * sizeof(__half) + sizeof(float));
+  counts[0] = ix->n_entries; counts[1] = ix->n_univ; counts[2] = ix->n_rows;
   counts[3] = ix->last_ctas; counts[4] = ix->last_tiles; counts[5] = ix->last_splits;
   counts[6] = ix->batch_h2d_bytes; counts[7] = ix->n_ovf;
-  counts[8] = ix->n_chunks; counts[9] = (int64_t)ix->last_stats[0]; counts[10] = (int64_t)ix->last_stats[1];
-  counts[11] = (int64_t)ix->last_stats[2];
-  counts[12] = (int64_t)ix->last_stats[3];
-  for (int i = 0; i < 4; i++) counts[13 + i] = (int64_t)ix->last_stats[4 + i];
+  counts[8] = ix->n_chunks;
+  counts[9] = (int64_t)ix->last_stats[0];   // (query, chunk) pairs scored (seed scan + candidate scan)
+  counts[10] = (int64_t)ix->last_stats[1];  // candidate records scanned
+  counts[11] = (int64_t)ix->last_stats[2];  // (query, chunk) pairs whose bound passed
+  counts[12] = (int64_t)ix->last_stats[3];  // candidate records written
+  counts[13] = ix->last_launches;
+  counts[14] = ix->n_rare_entries;
+  counts[15] = (int64_t)(ix->last_stats[6] & 0xFFFFFFFFull);  // pool pages used
+  counts[16] = ix->pool_pages;
   return KV_OK;
 }
 

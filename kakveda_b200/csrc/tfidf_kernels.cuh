@@ -1,5 +1,6 @@
-// Device code of the TF-IDF cosine index: finalize kernels, K1a (float64 full scan), K1b (query
-// batch, fused top-k, block-max pruning), K5 (list merge).  Included by tfidf_index.cu only.
+// Device code of the TF-IDF cosine index: finalize kernels, query preparation, K1a (one query, float64 scores of
+// every row), K1b-S (exact scan of candidate (query, chunk) pairs with fused top-k), K5 (list merge), K6 (float64
+// re-scoring).  The bound kernel K1b-B (tcgen05) lives in bound_kernel.cuh.  Included by tfidf_index.cu only.
 //
 // Math (restating sklearn text.py:1650-1739 + pairwise.py:1742-1752 as called
 // by services/shared/similarity.py:14-20).  The reference refits TF-IDF on [query]+corpus per
@@ -12,45 +13,58 @@
 //   |q|^2    = sum_{t in q} (tf_q(t) idf_q(t))^2   (out-of-vocabulary features: df = 0)
 //   score    = dot / sqrt(|q|^2 (B_c + corr)),  0 when either side has no feature.
 //
-// Scan layout in HBM (built by finalize; "position" = index of a row in text-sorted order):
-//   * rows are sorted by their feature-id sequence (= token order), so rows with similar text are
-//     neighbours; perm[position] is the original row;
-//   * features present in EVERY local row with one common tf ("universal": the field names of
-//     signature_text, fingerprint.py:60-65) are folded into per-query constants;
-//   * the remaining entries of all rows form one self-delimiting uint32 stream
-//         [31] last entry of its row   [30:5] feature id   [4:0] tf (31 = see overflow table)
-//     (a row without entries carries one sentinel entry); chunkptr[] gives the stream offset of
-//     every CHUNK_ROWS-th position -- the unit of work distribution and of pruning.  Entries keep
-//     the text order of the features, and the longest prefix shared by ALL rows of a chunk is
-//     stored once at the head of the chunk ("core", closed by a marker entry): the scan evaluates
-//     it once and restarts every row from that state -- each row is still summed in its own
-//     entry order, so the result is bit-identical to an unfactored scan;
-//   * per chunk a summary pseudo-row (union of the chunk's features with the max tf, in the same
-//     entry format) and the smallest row norm: evaluating it like a row yields an upper bound of
-//     every score in the chunk (block-max pruning, exact); features that every chunk summary contains
-//     with one tf are kept out of the summaries and enter the bounds as per-query constants;
-//   * B32/B64: row norms B_c by position.
+// Scan layout in HBM (built by finalize; "position" = index of a row in (norm class, text) order):
+//   * rows are sorted by (norm class, feature-id sequence = token order): rows with similar text are neighbours;
+//     perm[position] is the original row; a CHUNK is 32 consecutive positions (one row per lane);
+//   * features present in EVERY local row with one common tf ("universal": the field names of signature_text,
+//     fingerprint.py:60-65) are folded into per-query constants;
+//   * per chunk one feature-major COLUMN BLOCK: the distinct (feature, tf) pairs of its rows, each with the 32-bit
+//     mask of the rows that hold it:  words[E] = [31] every valid row holds it  [30:5] feature id  [4:0] tf (31 =
+//     see overflow table), masks[E].  A query is scored against a chunk by probing the E words in its own hash table
+//     and adding each hit's weight to the rows of its mask -- a third of the entries a row-major stream needs, and
+//     the per-row sums are INTEGERS (fixed point, see below), so the order of the additions is irrelevant: rows
+//     with identical text get identical bits wherever they sit, and the (score desc, row asc) order of
+//     services/gfkb/app.py:89 is reproduced for duplicate rows;
+//   * entries of the NF = 256 features found in most chunks ("frequent") come last in a block; for them a dense
+//     fp16 matrix Uf[chunk][256] holds the largest tf in the chunk -- the tensor-core part of the chunk bounds;
+//   * B32/B64: row norms B_c by position, chunk_minB: smallest positive norm of a chunk.
+//
+// Fixed point: a query's weights are w(t) = round(tf_q a(t) 2^32) (64-bit) and c(t) = round(-d(t) 2^24); a row's sums
+// are exact integer sums of tf_c w(t) and tf_c^2 c(t).  Relative resolution 2^-32 per term (float32 has 2^-24).
 #pragma once
 #include "kv_cuda.cuh"
 
+#include <cuda_fp16.h>
+
 namespace kvk {
 
-constexpr int CHUNK_ROWS = 64;
-constexpr int SUM_GROUP = 16;  // chunk summaries per group in the bound pass (their shared features are evaluated once)
-constexpr unsigned long long OVF_GCORE_BASE = 0xD0000000ULL;  // overflow-key position of a summary-group core: BASE + group
+constexpr int CHUNK_ROWS = 32;
+constexpr int NF = 256;  // features evaluated densely by the bound kernel
 constexpr uint32_t FID_BITS = 26;
 constexpr uint32_t FID_MASK = (1u << FID_BITS) - 1;
 constexpr uint32_t FID_NONE = FID_MASK;  // sentinel feature id (never in a table)
 constexpr uint32_t KEY_EMPTY = 0xFFFFFFFFu;
-constexpr uint32_t KEY_MULTI = 0x80000000u;  // table key flag: some query of the tile has tf_q > 1
+constexpr uint32_t W_ALL = 0x80000000u;  // block word flag: every valid row of the chunk holds the entry
 constexpr uint32_t TF_OVF = 31;
 constexpr uint32_t FULL = 0xFFFFFFFFu;
-constexpr uint32_t PAD_ENTRY = (FID_NONE << 5) | 1u;
-constexpr uint32_t FID_CORE = FID_MASK - 1;  // marker entry: end of the chunk's shared prefix ("core")
-constexpr uint32_t CORE_ENTRY = (FID_CORE << 5) | 1u;
-constexpr unsigned long long OVF_CORE_BASE = 0xC0000000ULL;  // overflow-key position of a chunk core: BASE + chunk
-constexpr float PRUNE_SLACK = 1.00002f;   // bound vs threshold comparisons tolerate fp32 rounding
+constexpr uint32_t PAD_WORD = (FID_NONE << 5) | 1u;
+constexpr int QKEYS = 128;   // hash slots of a query's own table (K1b-S)
+constexpr int QFEATS = 64;   // features a query may hold in it (more: float64 full-scan path)
+constexpr int QTAB_BYTES = QKEYS * 4 + QFEATS * 16;
+constexpr int GROUP_Q = 32;  // queries per scan group (one candidate list, one K1b-S CTA)
+constexpr int TILE_Q = 128;  // queries per bound tile (4 groups; the M of the bound GEMM)
+constexpr int RT_SLOTS = 2048;  // rare-feature table of a bound tile
+constexpr int RT_CAP = 1500;    // features it accepts (the rest enters the bounds as per-query constants)
+constexpr int RT_MULTI = 512;   // of those, features shared by several queries of the tile (128-bit membership masks)
+constexpr int RTAB_BYTES = RT_SLOTS * 12 + RT_MULTI * 16;
+constexpr float PRUNE_SLACK = 1.0005f;  // bounds: fp16 round-up of weights, fp32 tensor-core sums, constants rounded outwards
 constexpr float FILTER_SLACK = 0.999996f;
+constexpr int PAGE_RECS = 1024;  // candidate records per pool page
+
+struct BlockInfo {
+  uint32_t off4;  // offset of the block in 16-byte units
+  uint16_t n_entries, n_rare;  // entries; of those, leading entries of non-frequent features
+};
 
 // ----------------------------------------------------------------------------------------
 // finalize kernels
@@ -89,11 +103,10 @@ __global__ void idf_kernel(const uint32_t *__restrict__ df, const uint32_t *__re
   T.utf[t] = u ? tfmin[t] : 0;
 }
 
-// one warp per position: B_c and the number of entries the row keeps in the stream
+// one warp per position: B_c
 __global__ void rownorm_kernel(const int64_t *__restrict__ indptr, const uint32_t *__restrict__ ids,
                                const uint16_t *__restrict__ tf, const int *__restrict__ perm, int64_t n_rows,
-                               const double *__restrict__ bb64, const uint8_t *__restrict__ univ, double *B64,
-                               float *B32, int64_t *keep) {
+                               const double *__restrict__ bb64, double *B64, float *B32) {
   int64_t pos = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (pos >= n_rows) return;
@@ -101,34 +114,41 @@ __global__ void rownorm_kernel(const int64_t *__restrict__ indptr, const uint32_
   // B_c is summed in entry order by one lane-strided pass + a fixed shuffle tree: rows with equal
   // text get the same bits
   double b = 0.0;
-  int k = 0;
   for (int64_t p = indptr[r] + lane; p < indptr[r + 1]; p += 32) {
     uint32_t t = ids[p];
     double f = (double)tf[p];
     b += f * f * bb64[t];
-    k += univ[t] ? 0 : 1;
   }
-  for (int o = 16; o; o >>= 1) {
-    b += __shfl_xor_sync(FULL, b, o);
-    k += __shfl_xor_sync(FULL, k, o);
-  }
+  for (int o = 16; o; o >>= 1) b += __shfl_xor_sync(FULL, b, o);
   if (lane == 0) {
     B64[pos] = b;
     B32[pos] = (float)b;
-    if (keep) keep[pos] = k > 0 ? k : 1;
   }
 }
 
-__global__ void chunk_meta_kernel(const float *__restrict__ B32, int64_t n_rows, int64_t n_chunks, float *chunk_minB) {
+// chunk_minB[c] for c < n_chunks; +inf for the padding chunks up to n_pad (and for chunks without a positive norm:
+// rows without features always score 0, they do not loosen a bound)
+__global__ void chunk_meta_kernel(const float *__restrict__ B32, int64_t n_rows, int64_t n_chunks, int64_t n_pad,
+                                  float *chunk_minB) {
   int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (c >= n_chunks) return;
-  int64_t r = c * CHUNK_ROWS;
-  {
-    float m = INFINITY;  // rows without features (B == 0) always score 0: they do not loosen the bound
+  if (c >= n_pad) return;
+  float m = INFINITY;
+  if (c < n_chunks) {
+    const int64_t r = c * CHUNK_ROWS;
     for (int64_t i = r; i < r + CHUNK_ROWS && i < n_rows; i++)
       if (B32[i] > 0.f) m = fminf(m, B32[i]);
-    chunk_minB[c] = m;
   }
+  chunk_minB[c] = m;
+}
+
+__global__ void fill_int_kernel(int *p, int64_t n, int v) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void invperm_kernel(const int *__restrict__ perm, int64_t n, int *invperm) {
+  const int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (pos < n) invperm[perm[pos]] = (int)pos;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -136,9 +156,10 @@ __global__ void chunk_meta_kernel(const float *__restrict__ B32, int64_t n_rows,
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t hash_fid(uint32_t fid, int log_h) { return (fid * 0x9E3779B1u) >> (32 - log_h); }
 
+// tf of a block entry whose 5-bit field overflowed: sorted table keyed by (chunk << 32 | entry index)
 __device__ uint32_t ovf_lookup(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ vals,
-                               int n, int64_t pos, uint32_t fid) {
-  unsigned long long key = ((unsigned long long)pos << 32) | fid;
+                               int n, int64_t chunk, uint32_t entry) {
+  unsigned long long key = ((unsigned long long)chunk << 32) | entry;
   int lo = 0, hi = n - 1;
   while (lo <= hi) {
     int mid = (lo + hi) >> 1;
@@ -149,23 +170,33 @@ __device__ uint32_t ovf_lookup(const unsigned long long *__restrict__ keys, cons
   return TF_OVF;  // unreachable for a consistent index
 }
 
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t v;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(v));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 // ----------------------------------------------------------------------------------------
-// K1a: one query against every row, float64 (the drop-in SimilarityEngine.score path)
+// K1a: one query against every row, float64 (the drop-in SimilarityEngine.score path).  One warp per chunk: the
+// lanes probe the block's entries in the query table, every hit adds its fixed-point weight to the rows of its
+// mask; lane = row.
 // ----------------------------------------------------------------------------------------
 struct ScoreParams {
-  const uint32_t *stream;
-  const int64_t *chunkptr;
+  const uint32_t *blk;
+  const BlockInfo *binfo;
   const int *perm;
   int64_t n_chunks, n_rows;
   const double *B64;
   const unsigned long long *ovf_keys;
   const uint32_t *ovf_vals;
   int n_ovf;
-  // query table (global memory): qw[H] = tf_q * a(t), qd[H] = d(t), keys[H]
+  // query table (global memory): keys[H], then w[H] = round(tf_q a(t) 2^e), c[H] = round(-d(t) 2^e2)  (64-bit)
   const uint32_t *qkeys;
-  const double *qw, *qd;
+  const unsigned long long *qw, *qc;
   int log_h;
-  int table_in_smem;
+  double w_unscale, c_unscale;  // 2^-e, 2^-e2
   double nq, dotU, corrU;
   int jaccard;
   double *out;  // by ORIGINAL row
@@ -174,159 +205,289 @@ struct ScoreParams {
 __global__ void __launch_bounds__(256) tfidf_score_kernel(ScoreParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int H = 1 << P.log_h;
-  const uint32_t *keys = P.qkeys;
-  const double *qw = P.qw, *qd = P.qd;
-  if (P.table_in_smem) {
-    double *s_w = (double *)smem_raw;
-    double *s_d = s_w + H;
-    uint32_t *s_k = (uint32_t *)(s_d + H);
-    for (int i = threadIdx.x; i < H; i += blockDim.x) {
-      s_k[i] = P.qkeys[i];
-      s_w[i] = P.qw[i];
-      s_d[i] = P.qd[i];
-    }
-    __syncthreads();
-    keys = s_k; qw = s_w; qd = s_d;
+  unsigned long long *s_w = (unsigned long long *)smem_raw;
+  unsigned long long *s_c = s_w + H;
+  uint32_t *s_k = (uint32_t *)(s_c + H);
+  // per-warp hit buffer: up to 32 hits of one probe round
+  struct Hit { unsigned long long w, c; uint32_t m, pad; };
+  Hit *s_hits = (Hit *)(s_k + H) + (threadIdx.x >> 5) * 32;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    s_k[i] = P.qkeys[i];
+    s_w[i] = P.qw[i];
+    s_c[i] = P.qc[i];
   }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
+  const uint32_t lt = lanemask_lt();
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t c = warp; c < P.n_chunks; c += n_warps) {
-    const int64_t p0 = P.chunkptr[c], p1 = P.chunkptr[c + 1];
+    const BlockInfo bi = P.binfo[c];
+    const int E = bi.n_entries, E4 = (E + 3) & ~3;
+    const uint32_t *words = P.blk + (size_t)bi.off4 * 4, *masks = words + E4;
     const int64_t pos0 = c * CHUNK_ROWS;
-    int row_in = 0;
-    // Per-row sums are accumulated strictly in entry order (warp-uniform accumulators), so rows with
-    // identical text get bit-identical scores wherever they sit in the stream -- the GFKB handler's
-    // stable sort (services/gfkb/app.py:89) then orders duplicate rows exactly like the reference.
-    double du = 0.0, dv = 0.0, mine = 0.0;
-    double cu = 0.0, cv = 0.0;  // sums over the chunk's shared prefix
-    bool in_core = true;        // until the marker (or the first row end) is seen
-    for (int64_t p = p0; p < p1; p += 32) {
-      const uint32_t e = (p + lane < p1) ? P.stream[p + lane] : PAD_ENTRY;
-      const uint32_t fid = (e >> 5) & FID_MASK;
-      const uint32_t lastmask = __ballot_sync(FULL, (e >> 31) != 0);
-      const uint32_t coremask = __ballot_sync(FULL, fid == FID_CORE);
-      const int my_row_off = __popc(lastmask & ((1u << lane) - 1u));
-      double wu = 0.0, wv = 0.0;
+    const int rows = (int)min((int64_t)CHUNK_ROWS, P.n_rows - pos0);
+    const uint32_t valid = rows == 32 ? FULL : ((1u << rows) - 1u);
+    unsigned long long acc_w = 0, acc_c = 0;
+    for (int e0 = 0; e0 < E; e0 += 32) {
+      const int e = e0 + lane;
+      const uint32_t w = e < E ? __ldg(words + e) : PAD_WORD;
+      const uint32_t fid = (w >> 5) & FID_MASK;
       bool hit = false;
-      if (fid < FID_CORE) {
-        uint32_t h = hash_fid(fid, P.log_h);
+      uint32_t h = 0;
+      if (fid != FID_NONE) {
+        h = hash_fid(fid, P.log_h);
         for (;;) {
-          uint32_t k = keys[h];
+          const uint32_t k = s_k[h];
           if (k == KEY_EMPTY) break;
-          if (k == fid) {
-            uint32_t tf = e & 31u;
-            if (tf == TF_OVF) {
-              // entries before the marker belong to the core (marker and core sit in the first groups of the chunk)
-              bool core_entry = in_core && (coremask == 0 || lane < (__ffs(coremask) - 1));  // every chunk has a marker
-              tf = ovf_lookup(P.ovf_keys, P.ovf_vals, P.n_ovf,
-                              core_entry ? (int64_t)(OVF_CORE_BASE + c) : pos0 + row_in + my_row_off, fid);
-            }
-            double f = (double)tf;
-            wu = f * qw[h];
-            wv = f * f * qd[h];
-            hit = true;
-            break;
-          }
+          if (k == fid) { hit = true; break; }
           h = (h + 1) & (H - 1);
         }
       }
-      const uint32_t hitmask = __ballot_sync(FULL, hit);
-      uint32_t ev = hitmask | lastmask | coremask;
-      while (ev) {
-        const int j = __ffs(ev) - 1;
-        ev &= ev - 1;
-        if ((hitmask >> j) & 1u) {
-          du += __shfl_sync(FULL, wu, j);
-          dv += __shfl_sync(FULL, wv, j);
-        }
-        if ((coremask >> j) & 1u) { cu = du; cv = dv; in_core = false; }
-        if ((lastmask >> j) & 1u) {
-          in_core = false;
-          const double dot = P.dotU + du;
-          double sc;
-          if (P.jaccard) {
-            const double den = P.nq + P.B64[pos0 + row_in] - dot;
-            sc = (den > 0.0 && dot != 0.0) ? dot / den : 0.0;
-          } else {
-            const double den = P.nq * (P.B64[pos0 + row_in] + P.corrU + dv);
-            sc = (den > 0.0 && dot != 0.0) ? dot / sqrt(den) : 0.0;
-          }
-          if ((row_in & 31) == lane) mine = sc;
-          row_in++;
-          du = cu; dv = cv;
-          if ((row_in & 31) == 0) P.out[P.perm[pos0 + row_in - 32 + lane]] = mine;
-        }
+      const uint32_t hm = __ballot_sync(FULL, hit);
+      if (hm == 0) continue;
+      if (hit) {
+        uint32_t tf = w & 31u;
+        if (tf == TF_OVF) tf = ovf_lookup(P.ovf_keys, P.ovf_vals, P.n_ovf, c, (uint32_t)e);
+        Hit r;
+        r.m = (w & W_ALL) ? valid : __ldg(masks + e);
+        r.w = s_w[h] * (unsigned long long)tf;
+        r.c = s_c[h] * (unsigned long long)tf * (unsigned long long)tf;
+        r.pad = 0;
+        s_hits[__popc(hm & lt)] = r;
       }
+      __syncwarp();
+      const int nh = __popc(hm);
+      for (int i = 0; i < nh; i++) {
+        const Hit r = s_hits[i];
+        if ((r.m >> lane) & 1u) { acc_w += r.w; acc_c += r.c; }
+      }
+      __syncwarp();
     }
-    if ((row_in & 31) != 0 && lane < (row_in & 31)) P.out[P.perm[pos0 + (row_in & ~31) + lane]] = mine;
+    if (lane < rows) {
+      const double dot = P.dotU + (double)acc_w * P.w_unscale;
+      const double corr = P.corrU - (double)acc_c * P.c_unscale;
+      const double B = P.B64[pos0 + lane];
+      double sc;
+      if (P.jaccard) {
+        const double den = P.nq + B - dot;
+        sc = (den > 0.0 && dot != 0.0) ? dot / den : 0.0;
+      } else {
+        const double den = P.nq * (B + corr);
+        sc = (den > 0.0 && dot != 0.0) ? dot / sqrt(den) : 0.0;
+      }
+      P.out[P.perm[pos0 + lane]] = sc;
+    }
   }
 }
 
 // ----------------------------------------------------------------------------------------
-// K1b: query batch against every row with fused top-k and block-max pruning
+// query batch preparation (device): per-query constants, the query's own hash table (K1b-S), its row of the dense
+// weight matrix Wf (K1b-B), and per 128-query tile the table of its non-frequent features (K1b-B's join)
 // ----------------------------------------------------------------------------------------
-struct TileDesc {
-  int q_begin, q_count, n_extras, pad;
+struct QFeat {
+  uint32_t w_lo, w_hi;  // round(tf_q a(t) 2^32)
+  uint32_t cq;          // round(-d(t) 2^24)
+  uint32_t tfq;
 };
 
-struct TopkParams {
-  const uint32_t *stream;
-  const int64_t *chunkptr;
-  const uint32_t *sum_stream;  // chunk summaries (pseudo-rows)
-  const int64_t *sumptr;
-  const uint32_t *grp_stream;  // the same summaries in groups of SUM_GROUP: shared core + per-chunk residuals
-  const int64_t *grpptr;
-  const float *chunk_minB;
+struct PrepParams {
+  const int64_t *q_indptr;  // [n_q + 1] by ORIGINAL query (device)
+  const uint32_t *q_ids, *q_tf;
+  const double *q_oov;      // [n_q] or NULL
+  const int *qperm;         // sorted slot -> original query
+  const uint8_t *flags;     // by sorted slot: 0 regular, 1 null (every score is 0), 2 irregular (float64 full-scan path)
+  int64_t n_q, V, n_total;
+  const double *a64, *d64;
+  const uint8_t *univ;
+  const uint32_t *utf, *tfmax;
+  const short *fslot;       // feature -> column of the dense matrices, -1: not a frequent feature
+  int jaccard, corpus_fit;
+  float *q_nq, *q_dotU, *q_corrU, *q_dotS, *q_corrS, *q_dotX;  // [n_q] by sorted slot
+  unsigned char *qtab;      // [n_q][QTAB_BYTES]
+  __half *Wf;               // [n_q_pad][NF], zeroed by the caller
+  unsigned char *rtab;      // [n_tiles][RTAB_BYTES]
+};
+
+__global__ void prep_queries_kernel(PrepParams P) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= P.n_q) return;
+  uint32_t *keys = (uint32_t *)(P.qtab + (size_t)i * QTAB_BYTES);
+  QFeat *feats = (QFeat *)(keys + QKEYS);
+  for (int j = 0; j < QKEYS; j++) keys[j] = KEY_EMPTY;
+  const int q = P.qperm[i];
+  const double idf0 = P.jaccard ? 1.0 : (P.corpus_fit ? 0.0 : log((double)(P.n_total + 2) / 2.0) + 1.0);
+  double nq = (P.q_oov ? P.q_oov[q] : 0.0) * idf0 * idf0;
+  double dotU = 0.0, corrU = 0.0, corrS = 0.0;
+  int cnt = 0;
+  const bool regular = P.flags[i] == 0;
+  for (int64_t p = P.q_indptr[q]; p < P.q_indptr[q + 1]; p++) {
+    const uint32_t t = P.q_ids[p];
+    const double f = (double)P.q_tf[p];
+    if ((int64_t)t >= P.V) { nq += f * f * idf0 * idf0; continue; }  // id issued after finalize: in no indexed row
+    const double a = P.a64[t], d = P.d64[t];
+    nq += f * f * a;
+    if (P.univ[t]) {
+      const double u = (double)P.utf[t];
+      dotU += f * u * a;
+      corrU += u * u * d;
+    } else if (regular && cnt < QFEATS) {
+      const double tm = (double)P.tfmax[t];
+      corrS += tm * tm * d;
+      uint32_t h = hash_fid(t, 7);
+      while (keys[h] != KEY_EMPTY) h = (h + 1) & (QKEYS - 1);
+      keys[h] = (t << 6) | (uint32_t)cnt;
+      const unsigned long long w = (unsigned long long)__double2ll_rn(f * a * 4294967296.0);
+      QFeat qf;
+      qf.w_lo = (uint32_t)w; qf.w_hi = (uint32_t)(w >> 32);
+      qf.cq = (uint32_t)__double2ll_rn(-d * 16777216.0);
+      qf.tfq = P.q_tf[p];
+      feats[cnt++] = qf;
+      const int fs = P.fslot[t];
+      if (fs >= 0) P.Wf[(size_t)i * NF + fs] = __float2half_ru(__double2float_ru(f * a));
+    }
+  }
+  P.q_nq[i] = regular ? (float)nq : 0.f;  // nq == 0 switches the query off in the kernels
+  P.q_dotU[i] = (float)dotU;
+  P.q_corrU[i] = (float)corrU;
+  P.q_dotS[i] = __double2float_ru(dotU * (1.0 + 1e-6));  // bounds may only err upwards
+  P.q_corrS[i] = __double2float_rd(corrU + corrS);       // ... and their denominators downwards
+  P.q_dotX[i] = 0.f;
+}
+
+// one CTA (128 threads = the tile's queries) per tile: the tile's rare-feature table.  Slot = (feature, largest
+// tf_q a(t) over the tile's queries holding it, the query or the index of a 128-bit membership mask).
+__global__ void __launch_bounds__(TILE_Q) prep_tiles_kernel(PrepParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t *s_keys = (uint32_t *)smem_raw;          // [RT_SLOTS]
+  uint32_t *s_w = s_keys + RT_SLOTS;                 // float bits
+  uint32_t *s_m = s_w + RT_SLOTS;                    // [RT_SLOTS][4]
+  __shared__ int s_cnt, s_multi;
+  __shared__ float s_dotX[TILE_Q];
+  const int tile = blockIdx.x, qi = threadIdx.x;
+  for (int j = qi; j < RT_SLOTS; j += TILE_Q) {
+    s_keys[j] = KEY_EMPTY;
+    s_w[j] = 0;
+    s_m[4 * j] = s_m[4 * j + 1] = s_m[4 * j + 2] = s_m[4 * j + 3] = 0;
+  }
+  if (qi == 0) { s_cnt = 0; s_multi = 0; }
+  s_dotX[qi] = 0.f;
+  __syncthreads();
+  const int64_t i = (int64_t)tile * TILE_Q + qi;
+  if (i < P.n_q && P.flags[i] == 0) {
+    const int q = P.qperm[i];
+    int cnt = 0;
+    for (int64_t p = P.q_indptr[q]; p < P.q_indptr[q + 1]; p++) {
+      const uint32_t t = P.q_ids[p];
+      if ((int64_t)t >= P.V || P.univ[t]) continue;
+      if (cnt++ >= QFEATS) break;
+      if (P.fslot[t] >= 0) continue;
+      const float w = __double2float_ru((double)P.q_tf[p] * P.a64[t]);
+      uint32_t h = hash_fid(t, 11);
+      bool placed = false;
+      for (int probes = 0; probes < RT_SLOTS; probes++) {
+        uint32_t k = s_keys[h];
+        if (k == KEY_EMPTY) {
+          if (s_cnt >= RT_CAP) break;  // table full: this feature enters the bounds as a constant
+          k = atomicCAS(&s_keys[h], KEY_EMPTY, t);
+          if (k == KEY_EMPTY) { atomicAdd(&s_cnt, 1); k = t; }
+        }
+        if (k == t) { placed = true; break; }
+        h = (h + 1) & (RT_SLOTS - 1);
+      }
+      if (placed) {
+        atomicMax(&s_w[h], __float_as_uint(w));
+        atomicOr(&s_m[4 * h + (qi >> 5)], 1u << (qi & 31));
+      } else {
+        s_dotX[qi] += __fmul_ru(w, (float)P.tfmax[t]);  // assumed present everywhere with its largest tf
+      }
+    }
+  }
+  __syncthreads();
+  uint32_t *o_keys = (uint32_t *)(P.rtab + (size_t)tile * RTAB_BYTES);
+  float *o_w = (float *)(o_keys + RT_SLOTS);
+  uint32_t *o_q = (uint32_t *)(o_w + RT_SLOTS);
+  uint32_t *o_multi = o_q + RT_SLOTS;  // [RT_MULTI][4]
+  for (int j = qi; j < RT_SLOTS; j += TILE_Q) {
+    const uint32_t k = s_keys[j];
+    uint32_t qinfo = 0xFFFFFFFFu;
+    float w = __uint_as_float(s_w[j]);
+    if (k != KEY_EMPTY) {
+      const uint32_t m0 = s_m[4 * j], m1 = s_m[4 * j + 1], m2 = s_m[4 * j + 2], m3 = s_m[4 * j + 3];
+      const int pc = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+      if (pc == 1) {
+        qinfo = m0 ? (uint32_t)(__ffs(m0) - 1) : m1 ? (uint32_t)(31 + __ffs(m1)) : m2 ? (uint32_t)(63 + __ffs(m2)) : (uint32_t)(95 + __ffs(m3));
+      } else {
+        const int mi = atomicAdd(&s_multi, 1);
+        if (mi < RT_MULTI) {
+          o_multi[4 * mi] = m0; o_multi[4 * mi + 1] = m1; o_multi[4 * mi + 2] = m2; o_multi[4 * mi + 3] = m3;
+          qinfo = 0x80000000u | (uint32_t)mi;
+        } else {  // no mask slot left: constant for every member query (the key stays: probe chains must not break)
+          const float x = __fmul_ru(w, (float)P.tfmax[k]);
+          const uint32_t mm[4] = {m0, m1, m2, m3};
+          for (int g = 0; g < 4; g++)
+            for (uint32_t b = mm[g]; b; b &= b - 1) atomicAdd(&s_dotX[g * 32 + __ffs(b) - 1], x * 1.000001f);
+          w = 0.f;
+        }
+      }
+    }
+    o_keys[j] = k;
+    o_w[j] = w;
+    o_q[j] = qinfo;
+  }
+  __syncthreads();
+  if (i < P.n_q) P.q_dotX[i] = s_dotX[qi] * 1.00001f;
+}
+
+// ----------------------------------------------------------------------------------------
+// K1b-S: exact scan of candidate (query, chunk) pairs with fused top-k.  One CTA = one scan group (32 queries, their
+// tables and top-k lists in shared memory) x one range of the group's candidate records {chunk, query mask}.  A warp
+// takes a record, stages the chunk's column block into shared memory with a bulk-async copy (TMA, mbarrier
+// completion; double buffered, so the next block lands while this one is scored) and scores it for each query of the
+// mask: lanes probe 32 block entries at a time in the query's table, hits add their fixed-point weights to the rows
+// of their masks, lane = row.  Survivors of the division-free pre-test enter the query's sorted list under a lock.
+// ----------------------------------------------------------------------------------------
+struct ScanParams {
+  const uint32_t *blk;
+  const BlockInfo *binfo;
+  const float *B32;
   const int *perm;
   int64_t n_chunks, n_rows, row_base;
-  const float *B32;
   const unsigned long long *ovf_keys;
   const uint32_t *ovf_vals;
   int n_ovf;
-  const unsigned char *tables;  // [n_tiles][table_bytes]
-  const TileDesc *tiles;
-  const float *q_nq, *q_dotU, *q_corrU;  // [n_q] (sorted query order)
-  const float *q_dotS, *q_corrS;         // [n_q] start values of chunk bounds (universal + summary-universal features)
-  const int *q_excl;                     // [n_q] or NULL: local ORIGINAL row a query must not match (self-join), -1 = none
-  int *gthr;                             // [n_q] float bits: lower bound of the global k-th score
-  int *peer_gthr[7];                     // the same array on the other GPUs of a row-sharded GFKB (peer memory over
-  int n_peers;                           //   NVLink): a raised bound is pushed to every shard, so all of them prune with it
-  int share;                             // thresholds are exchanged (several row splits and/or peers)
-  float *ubuf;                           // [n_tiles][n_chunks] chunk upper bounds (scratch)
-  unsigned long long *stats;             // [0] chunks scanned, [1] chunks pruned, [2] summaries evaluated
+  const unsigned char *qtab;              // [n_q][QTAB_BYTES]
+  const float *q_nq, *q_dotU, *q_corrU;   // [n_q] (sorted query order)
+  const int *q_excl;                      // [n_q] or NULL: local ORIGINAL row a query must not match (self-join), -1 = none
+  int *gthr;                              // [n_q] float bits: lower bound of the global k-th score
+  int *peer_gthr[7];                      // the same array on the other GPUs of a row-sharded GFKB (peer memory over
+  int n_peers;                            //   NVLink): a raised bound is pushed to every shard, so all of them prune with it
+  // candidate lists: list l = group * n_bsplits + bsplit.  mode 0: paged pool, 1: fixed stride (seed lists),
+  // 2: every chunk of the list's chunk range x every query of the group (exhaustive)
+  int list_mode;
+  const uint32_t *list_count;   // [n_lists]
+  const uint32_t *list_pages;   // [n_lists][max_pages]
+  int max_pages;
+  const uint2 *pool;            // {chunk, query mask}
+  const uint2 *direct;          // mode 1: [n_lists][direct_stride]
+  int direct_stride;
+  int n_bsplits, n_ssplits;
+  unsigned long long *stats;    // [0] (query, chunk) pairs scored, [1] records
   int64_t n_q;
-  int k, n_splits, prune, jaccard;
-  float *part_scores;  // [n_splits][n_q][k]
+  int k, jaccard;
+  float *part_scores;  // [n_bsplits * n_ssplits][n_q][k]
   long long *part_rows;
 };
 
-template <int G, int LOGH, int XCAP>
-struct TileLayout {
-  static constexpr int H = 1 << LOGH;
-  static constexpr int QT = 32 * G;
-  static constexpr size_t off_keys = 0;
-  static constexpr size_t off_ad = off_keys + sizeof(uint32_t) * H;
-  static constexpr size_t off_masks = off_ad + sizeof(float2) * H;
-  // XCAP (<= 32) extra entries for features some query of the tile holds with tf_q > 1: (weight (t-1) a(t), chain flag)
-  // + the membership masks of the queries with that tf_q
-  static constexpr size_t off_xad = off_masks + sizeof(uint32_t) * H * G;
-  static constexpr size_t off_xmask = off_xad + sizeof(float2) * XCAP;
-  static constexpr size_t table_bytes = off_xmask + sizeof(uint32_t) * XCAP * G;  // multiple of 16
-  static size_t smem_bytes(int k) { return table_bytes + (size_t)QT * k * 8 + (size_t)QT * 8 + 288; }
+constexpr int S_WARPS = 8;
+constexpr int S_BUF_ENTRIES = 256;  // a staged block holds up to this many entries (larger blocks are read in place)
+constexpr int S_BUF_BYTES = S_BUF_ENTRIES * 8;
+
+struct ScanHit {
+  uint32_t m, c_lo, w_lo, w_hi;  // c fits 32 bits for tf <= 2 ... kept 64-bit via c_hi below
+  uint32_t c_hi, pad0, pad1, pad2;
 };
 
-template <int G>
-struct Lanes {  // per-lane state of the G queries a lane owns (query g*32+lane of the tile)
-  float nq[G], dotU[G], corrU[G];
-  float filt[G], fq[G];  // filter threshold (a score) and the factor of the division-free pre-test
-  int krow[G];
-  bool valid[G];
-  int jaccard;           // 0: TF-IDF cosine, 1: token-set Jaccard (warp-uniform)
-};
-
-// score of one (query, row) pair from the accumulated sums.  Cosine: dot / sqrt(|q|^2 (B + corr)).
-// Jaccard (a = 1, d = 0, B = |row|, nq = |query|): dot / (|query| + |row| - dot) -- exact small integers.
 __device__ __forceinline__ float pair_score(int jaccard, float dot, float nq, float t) {
   if (jaccard) {
     const float den = nq + t - dot;
@@ -335,215 +496,111 @@ __device__ __forceinline__ float pair_score(int jaccard, float dot, float nq, fl
   const float den = nq * t;
   return den > 0.f ? __fdiv_rn(dot, __fsqrt_rn(den)) : 0.f;
 }
-// upper bound from a summary (max dot, min norm): +inf when the denominator bound is not positive
-__device__ __forceinline__ float bound_score(int jaccard, float dot, float nq, float t) {
-  if (jaccard) {
-    const float den = nq + t - dot;
-    return den > 0.f ? __fdiv_rn(dot, den) : INFINITY;
-  }
-  const float den = nq * t;
-  return den > 0.f ? __fdiv_rn(dot, __fsqrt_rn(den)) : INFINITY;
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk asynchronous copy global -> shared (TMA engine), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
 }
 
-template <int G>
-__device__ __forceinline__ void set_filter(Lanes<G> &L, int g, float ks, int kr) {
-  L.filt[g] = ks;
-  L.krow[g] = kr;
-  // pre-test without division: cosine  dot^2 >= fq * (B + corr);  Jaccard  dot >= fq * (|q| + |row| - dot)
-  L.fq[g] = ks > 0.f ? (L.jaccard ? ks * FILTER_SLACK : ks * ks * L.nq[g] * FILTER_SLACK) : -1.f;
-}
-
-// shared-memory loads through 32-bit shared-window addresses (the tile table is read-only once it is staged): keeps
-// the address arithmetic of the event loop to one multiply-add per load
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
-  uint32_t v;
-  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ float2 lds_f2(uint32_t a) {
-  float2 v;
-  asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
-  uint4 v;
-  asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-  return v;
-}
-// values the compiler must keep in a register instead of re-deriving them inside the event loop
-__device__ __forceinline__ uint32_t pinned_lanemask_eq() {
-  uint32_t v;
-  asm volatile("mov.u32 %0, %%lanemask_eq;" : "=r"(v));
-  return v;
-}
-__device__ __forceinline__ uint32_t pinned_shared_addr(const void *p) {
-  uint32_t v;
-  asm volatile("mov.u32 %0, %1;" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-  return v;
-}
-
-// Walk the entries [p0,p1) of one chunk (or of one summary pseudo-row).  For every row end the
-// functor gets the per-lane sums (dot, corr include the folded universal features).
-//
-// Lanes probe 32 stream entries in parallel; the warp then walks the hit / row-end events in stream order (sums
-// must follow each row's own entry order).  A feature for which some query of the tile has tf_q > 1 carries the
-// KEY_MULTI flag and the index of its first EXTRA entry: the primary slot adds the tf_q = 1 part for every query
-// that has the feature, each extra entry adds (t - 1) a(t) tf_c for the queries whose tf_q equals t.
-template <int G, int LOGH, int XCAP, bool HAS_CORE, class RowFn>
-__device__ __forceinline__ void scan_entries(const uint32_t *__restrict__ stream, int64_t p0, int64_t p1,
-                                             int64_t ovf_pos0, int64_t ovf_core_key, uint32_t tbl, uint32_t lanebit,
-                                             const unsigned long long *ovf_keys, const uint32_t *ovf_vals, int n_ovf,
-                                             const float (&dot0)[G], const float (&corr0)[G], RowFn &&on_row) {
-  // tbl: shared-window address of the tile table (TileLayout); lanebit: 1 << lane.
-  // HAS_CORE: the range starts with the chunk's shared prefix, closed by a marker entry; the sums
-  // reached at the marker are the state every row of the chunk restarts from.
-  // Sums are kept for all G groups of the tile -- a group that sits a chunk out is simply not looked at by the row
-  // functor (a predicated-off add costs the same issue slot as a skipped one).
-  using TL = TileLayout<G, LOGH, XCAP>;
-  constexpr int H = 1 << LOGH;
-  static_assert(G == 4, "the event loop loads the four membership words of a slot as one uint4");
-  const int lane = threadIdx.x & 31;
-  float dot[G], corr[G], dotc[G], corrc[G];
-#pragma unroll
-  for (int g = 0; g < G; g++) { dot[g] = dotc[g] = dot0[g]; corr[g] = corrc[g] = corr0[g]; }
-  int row_in = 0;
-  bool in_core = HAS_CORE;
-  for (int64_t p = p0; p < p1; p += 32) {
-    const uint32_t e = (p + lane < p1) ? stream[p + lane] : PAD_ENTRY;
-    const uint32_t fid = (e >> 5) & FID_MASK;
-    int w = -1;  // (slot << 11) | (first extra << 6) | (multi << 5) | tf  when this lane's entry is in the tile table
-    if (fid < FID_CORE) {
-      uint32_t h = hash_fid(fid, LOGH);
-      for (;;) {
-        const uint32_t key = lds_u32(tbl + (uint32_t)TL::off_keys + h * 4u);
-        if (key == KEY_EMPTY) break;
-        if ((key & FID_MASK) == fid) {
-          w = (int)((h << 11) | (((key >> FID_BITS) & 31u) << 6) | ((key >> 31) << 5) | (e & 31u));
-          break;
-        }
-        h = (h + 1) & (H - 1);
-      }
-    }
-    const uint32_t lastmask = __ballot_sync(FULL, (e >> 31) != 0);
-    const uint32_t ev_all = __ballot_sync(FULL, w >= 0) | lastmask;
-    // the core marker (once per chunk) splits its batch in two: events before it close the shared prefix
-    uint32_t ev_first = ev_all, ev_second = 0;
-    bool split = false;
-    if (HAS_CORE) {
-      const uint32_t coremask = __ballot_sync(FULL, fid == FID_CORE);
-      if (coremask) {
-        const int cj = __ffs(coremask) - 1;
-        ev_first = ev_all & ((1u << cj) - 1u);
-        ev_second = ev_all & ~((2u << cj) - 1u);
-        split = true;
-      }
-    }
-#pragma unroll 1
-    for (int pass = 0; pass < 2; pass++) {
-      uint32_t ev = pass == 0 ? ev_first : ev_second;
-      while (ev) {
-        const int j = __ffs(ev) - 1;
-        ev &= ev - 1;
-        const int wj = __shfl_sync(FULL, w, j);
-        if (wj >= 0) {
-          const uint32_t slot = (uint32_t)wj >> 11;
-          uint32_t tf = wj & 31;
-          if (tf == TF_OVF) {
-            uint32_t fj = __shfl_sync(FULL, fid, j);
-            tf = ovf_lookup(ovf_keys, ovf_vals, n_ovf, in_core ? ovf_core_key : ovf_pos0 + row_in, fj);
-          }
-          const uint4 mm = lds_u4(tbl + (uint32_t)TL::off_masks + slot * 16u);
-          const float2 ad = lds_f2(tbl + (uint32_t)TL::off_ad + slot * 8u);
-          const float f = (float)tf;
-          const float u = f * ad.x, v = f * f * ad.y;
-          if (mm.x & lanebit) { dot[0] += u; corr[0] += v; }
-          if (mm.y & lanebit) { dot[1] += u; corr[1] += v; }
-          if (mm.z & lanebit) { dot[2] += u; corr[2] += v; }
-          if (mm.w & lanebit) { dot[3] += u; corr[3] += v; }
-          if (wj & 32) {  // rare: the queries with tf_q = t > 1 get the remaining (t - 1) parts
-            uint32_t x = ((uint32_t)wj >> 6) & 31u;
-            for (;;) {
-              const float2 xa = lds_f2(tbl + (uint32_t)TL::off_xad + x * 8u);
-              const uint4 xm = lds_u4(tbl + (uint32_t)TL::off_xmask + x * 16u);
-              const float u2 = f * xa.x;
-              if (xm.x & lanebit) dot[0] += u2;
-              if (xm.y & lanebit) dot[1] += u2;
-              if (xm.z & lanebit) dot[2] += u2;
-              if (xm.w & lanebit) dot[3] += u2;
-              if (xa.y == 0.f) break;  // last extra entry of this feature
-              x++;
-            }
-          }
-        }
-        if ((lastmask >> j) & 1u) {
-          on_row(row_in, dot, corr);
-#pragma unroll
-          for (int g = 0; g < G; g++) { dot[g] = dotc[g]; corr[g] = corrc[g]; }
-          row_in++;
-        }
-      }
-      if (!split) break;
-      if (pass == 0) {
-#pragma unroll
-        for (int g = 0; g < G; g++) { dotc[g] = dot[g]; corrc[g] = corr[g]; }
-        in_core = false;
-      }
-    }
-  }
-}
-
-template <int G, int LOGH, int XCAP>
-__global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
-  using TL = TileLayout<G, LOGH, XCAP>;
-  constexpr int QT = TL::QT;
+__global__ void __launch_bounds__(S_WARPS * 32, 2) tfidf_scan_kernel(ScanParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const uint32_t tbl = pinned_shared_addr(smem_raw);  // tile table (keys, (a,d), membership masks, extras)
-  const uint32_t lanebit = pinned_lanemask_eq();
-  float *s_lscore = (float *)(smem_raw + TL::table_bytes);  // [QT][k]
-  int *s_lrow = (int *)(s_lscore + QT * P.k);               // [QT][k]
-  int *s_cnt = s_lrow + QT * P.k;                           // [QT]
-  int *s_lock = s_cnt + QT;                                 // [QT]
-  float *s_thrmin = (float *)(s_lock + QT);                 // [1] min over the tile of the k-th scores
-  unsigned int *s_stat = (unsigned int *)(s_thrmin + 1);    // [4]
-  long long *s_next = (long long *)(s_stat + 5);            // [N_LEVELS + 1] chunk cursors, one per bound level (8-byte aligned: s_thrmin sits on a 16-byte boundary)
-
-  const int tile = blockIdx.x, split = blockIdx.y;
-  const TileDesc td = P.tiles[tile];
   const int k = P.k;
-  {
-    const uint4 *src = (const uint4 *)(P.tables + (size_t)tile * TL::table_bytes);
-    uint4 *dst = (uint4 *)smem_raw;
-    for (int i = threadIdx.x; i < (int)(TL::table_bytes / 16); i += blockDim.x) dst[i] = src[i];
-    for (int i = threadIdx.x; i < QT * k; i += blockDim.x) {
+  uint32_t *s_keys = (uint32_t *)smem_raw;                                  // [GROUP_Q][QKEYS]
+  QFeat *s_feats = (QFeat *)(s_keys + GROUP_Q * QKEYS);                     // [GROUP_Q][QFEATS]
+  unsigned char *s_buf = (unsigned char *)(s_feats + GROUP_Q * QFEATS);     // [S_WARPS][2][S_BUF_BYTES]
+  ScanHit *s_hits = (ScanHit *)(s_buf + S_WARPS * 2 * S_BUF_BYTES);         // [S_WARPS][32]
+  uint64_t *s_bar = (uint64_t *)(s_hits + S_WARPS * 32);                    // [S_WARPS][2]
+  float *s_lscore = (float *)(s_bar + S_WARPS * 2);                         // [GROUP_Q][k]
+  int *s_lrow = (int *)(s_lscore + GROUP_Q * k);                            // [GROUP_Q][k]
+  int *s_cnt = s_lrow + GROUP_Q * k;                                        // [GROUP_Q]
+  int *s_lock = s_cnt + GROUP_Q;                                            // [GROUP_Q]
+  float *s_nq = (float *)(s_lock + GROUP_Q);                                // [GROUP_Q] per-query constants
+  float *s_dotU = s_nq + GROUP_Q, *s_corrU = s_dotU + GROUP_Q;
+  int *s_excl = (int *)(s_corrU + GROUP_Q);
+  unsigned int *s_next = (unsigned int *)(s_excl + GROUP_Q);                // [1] next record of this CTA's range
+  unsigned int *s_stat = s_next + 1;                                        // [2]
+
+  const int list = blockIdx.x, ssplit = blockIdx.y;
+  const int group = list / P.n_bsplits, bsplit = list - group * P.n_bsplits;
+  const int64_t q0 = (int64_t)group * GROUP_Q;
+  const int q_count = (int)min((int64_t)GROUP_Q, P.n_q - q0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = lanemask_lt();
+
+  // record range of this CTA
+  uint32_t n_rec;
+  int64_t c_lo = 0;
+  if (P.list_mode == 2) {
+    c_lo = P.n_chunks * bsplit / P.n_bsplits;
+    n_rec = (uint32_t)(P.n_chunks * (bsplit + 1) / P.n_bsplits - c_lo);
+  } else {
+    n_rec = P.list_count[list];
+    if (P.list_mode == 1) n_rec = min(n_rec, (uint32_t)P.direct_stride);
+  }
+  const uint32_t r_lo = (uint32_t)((unsigned long long)n_rec * ssplit / P.n_ssplits);
+  const uint32_t r_hi = (uint32_t)((unsigned long long)n_rec * (ssplit + 1) / P.n_ssplits);
+
+  {  // stage the group's query tables and constants
+    const uint4 *src = (const uint4 *)(P.qtab + (size_t)q0 * QTAB_BYTES);
+    for (int i = threadIdx.x; i < q_count * (QTAB_BYTES / 16); i += blockDim.x) {
+      const int q = i / (QTAB_BYTES / 16), o = i - q * (QTAB_BYTES / 16);
+      const uint4 v = src[i];
+      if (o < QKEYS / 4) ((uint4 *)(s_keys + q * QKEYS))[o] = v;
+      else ((uint4 *)(s_feats + q * QFEATS))[o - QKEYS / 4] = v;
+    }
+    for (int i = threadIdx.x; i < GROUP_Q * k; i += blockDim.x) {
       s_lscore[i] = -INFINITY;
       s_lrow[i] = 0x7fffffff;
     }
-    for (int i = threadIdx.x; i < QT; i += blockDim.x) { s_cnt[i] = 0; s_lock[i] = 0; }
-    if (threadIdx.x < 4) s_stat[threadIdx.x] = 0;
-    if (threadIdx.x == 0) *s_thrmin = -INFINITY;
+    if (threadIdx.x < GROUP_Q) {
+      const int qi = threadIdx.x;
+      const bool ok = qi < q_count;
+      s_cnt[qi] = 0;
+      s_lock[qi] = 0;
+      s_nq[qi] = ok ? P.q_nq[q0 + qi] : 0.f;
+      s_dotU[qi] = ok ? P.q_dotU[q0 + qi] : 0.f;
+      s_corrU[qi] = ok ? P.q_corrU[q0 + qi] : 0.f;
+      s_excl[qi] = (ok && P.q_excl) ? P.q_excl[q0 + qi] : -1;
+    }
+    if (threadIdx.x == 0) { *s_next = r_lo; s_stat[0] = s_stat[1] = 0; }
+    if (lane == 0) {
+      mbar_init(&s_bar[warp * 2], 1);
+      mbar_init(&s_bar[warp * 2 + 1], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  Lanes<G> L;
-  L.jaccard = P.jaccard;
-#pragma unroll
-  for (int g = 0; g < G; g++) {
-    int qi = g * 32 + lane;
-    L.valid[g] = qi < td.q_count;
-    int q = td.q_begin + (L.valid[g] ? qi : 0);
-    L.nq[g] = P.q_nq[q];
-    L.dotU[g] = P.q_dotU[q];
-    L.corrU[g] = P.q_corrU[q];
-    if (L.nq[g] <= 0.f) L.valid[g] = false;  // null query (every score is 0): answered on the host side
-    set_filter<G>(L, g, L.valid[g] ? __int_as_float(P.gthr[q]) : INFINITY, 0x7fffffff);
-  }
-
-  // Publish a lower bound of a query's global k-th score: locally (the CTAs scanning other row ranges) and, when it
-  // raises the local value, on every peer GPU (fire-and-forget system-scope reductions over NVLink peer memory).
-  // Valid for all shards: k rows with at least this score exist somewhere in the GFKB.
+  // Publish a lower bound of a query's global k-th score: locally (the CTAs scanning other candidate ranges and the
+  // bound kernel) and, when it raises the local value, on every peer GPU (fire-and-forget system-scope reductions
+  // over NVLink peer memory).  Valid for all shards: k rows with at least this score exist somewhere in the GFKB.
   auto publish_threshold = [&](int64_t q, float ks) {
     const int v = __float_as_int(ks);
+    if (v <= 0) return;  // only positive scores order like their bit patterns
     const int old = atomicMax(&P.gthr[q], v);
     if (old < v) {
 #pragma unroll
@@ -552,231 +609,224 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
     }
   };
 
-  // pick up thresholds raised meanwhile by other warps of the CTA (shared lists) and by the CTAs
-  // scanning other row ranges for the same queries (global lower bounds of the k-th score)
-  auto refresh_filters = [&]() {
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-      int qi = g * 32 + lane;
-      if (!L.valid[g]) continue;
-      if (s_cnt[qi] == k) {
-        float ks = s_lscore[qi * k + k - 1];
-        int kr = s_lrow[qi * k + k - 1];
-        if (ks > L.filt[g] || (ks == L.filt[g] && kr < L.krow[g])) set_filter<G>(L, g, ks, kr);
-      }
-      if (P.share) {
-        float gs = __int_as_float(*(volatile int *)&P.gthr[td.q_begin + qi]);
-        if (gs > L.filt[g]) set_filter<G>(L, g, gs, 0x7fffffff);
-      }
+  auto fetch = [&](uint32_t r, int64_t &chunk, uint32_t &mask) {
+    if (P.list_mode == 2) {
+      chunk = c_lo + r;
+      mask = q_count == 32 ? FULL : ((1u << q_count) - 1u);
+    } else {
+      uint2 rec;
+      if (P.list_mode == 1) rec = P.direct[(size_t)list * P.direct_stride + r];
+      else rec = P.pool[(size_t)P.list_pages[(size_t)list * P.max_pages + (r / PAGE_RECS)] * PAGE_RECS + (r % PAGE_RECS)];
+      chunk = rec.x;
+      mask = rec.y;
     }
   };
+  auto grab = [&]() -> uint32_t {
+    uint32_t r = 0;
+    if (lane == 0) r = atomicAdd(s_next, 1u);
+    return __shfl_sync(FULL, r, 0);
+  };
 
-  auto process_chunk = [&](int64_t c, uint32_t gmask) {
-    const int64_t pos0 = c * CHUNK_ROWS;
-    refresh_filters();
-    scan_entries<G, LOGH, XCAP, true>(P.stream, P.chunkptr[c], P.chunkptr[c + 1], pos0, (int64_t)(OVF_CORE_BASE + c), tbl, lanebit,
-                                P.ovf_keys, P.ovf_vals, P.n_ovf, L.dotU, L.corrU,
-                          [&](int row_in, const float *dot, const float *corr) {
-      const float Bc = P.B32[pos0 + row_in];
-#pragma unroll
-      for (int g = 0; g < G; g++) {
-        if (!((gmask >> g) & 1u)) continue;
-        const float t = Bc + corr[g];
-        const float lhs = L.jaccard ? dot[g] : dot[g] * dot[g];
-        const float rhs = L.fq[g] * (L.jaccard ? (L.nq[g] + t - dot[g]) : t);
-        if (L.valid[g] && lhs >= rhs) {
-          const float s = pair_score(L.jaccard, dot[g], L.nq[g], t);
-          const int row = P.perm[pos0 + row_in];
-          const int qi = g * 32 + lane;
-          // self-join: a query never matches the row it was taken from (looked up only on this rare path)
-          const bool banned = P.q_excl != nullptr && P.q_excl[td.q_begin + qi] == row;
-          if (!banned && (s > L.filt[g] || (s == L.filt[g] && row < L.krow[g]))) {
-            while (atomicCAS(&s_lock[qi], 0, 1) != 0) {}
-            __threadfence_block();
-            float *ls = s_lscore + qi * k;
-            int *lr = s_lrow + qi * k;
-            int cnt = s_cnt[qi];
-            int pos = -1;
-            if (cnt < k) {
-              pos = cnt;
-              s_cnt[qi] = ++cnt;
-            } else if (s > ls[k - 1] || (s == ls[k - 1] && row < lr[k - 1])) {
-              pos = k - 1;
+  unsigned char *my_buf = s_buf + warp * 2 * S_BUF_BYTES;
+  uint64_t *my_bar = s_bar + warp * 2;
+  ScanHit *my_hits = s_hits + warp * 32;
+  uint32_t phases = 0;  // bit b: parity the next wait on buffer b expects
+
+  // start the copy of a record's block (if it fits the staging buffer); returns whether it was staged
+  auto issue = [&](int64_t chunk, int b) -> bool {
+    const BlockInfo bi = P.binfo[chunk];
+    const int E4 = (bi.n_entries + 3) & ~3;
+    if (E4 == 0 || E4 > S_BUF_ENTRIES) return false;
+    if (lane == 0) {
+      mbar_expect_tx(&my_bar[b], (uint32_t)E4 * 8u);
+      bulk_copy_g2s(my_buf + b * S_BUF_BYTES, P.blk + (size_t)bi.off4 * 4, (uint32_t)E4 * 8u, &my_bar[b]);
+    }
+    return true;
+  };
+
+  unsigned int pairs_done = 0, recs_done = 0;
+  uint32_t r_cur = grab();
+  int64_t chunk_cur = 0, chunk_nxt = 0;
+  uint32_t mask_cur = 0, mask_nxt = 0;
+  bool staged_cur = false, staged_nxt = false;
+  int b = 0;
+  if (r_cur < r_hi) {
+    fetch(r_cur, chunk_cur, mask_cur);
+    staged_cur = mask_cur ? issue(chunk_cur, b) : false;
+  }
+  while (r_cur < r_hi) {
+    const uint32_t r_nxt = grab();
+    if (r_nxt < r_hi) {
+      fetch(r_nxt, chunk_nxt, mask_nxt);
+      staged_nxt = mask_nxt ? issue(chunk_nxt, b ^ 1) : false;
+    }
+    if (mask_cur) {
+      const BlockInfo bi = P.binfo[chunk_cur];
+      const int E = bi.n_entries, E4 = (E + 3) & ~3;
+      const uint32_t *words, *masks;
+      if (staged_cur) {
+        mbar_wait(&my_bar[b], (phases >> b) & 1u);
+        phases ^= 1u << b;
+        words = (const uint32_t *)(my_buf + b * S_BUF_BYTES);
+      } else {
+        words = P.blk + (size_t)bi.off4 * 4;
+      }
+      masks = words + E4;
+      const int64_t pos0 = chunk_cur * CHUNK_ROWS;
+      const int rows = (int)min((int64_t)CHUNK_ROWS, P.n_rows - pos0);
+      const uint32_t valid = rows == 32 ? FULL : ((1u << rows) - 1u);
+      const float Bc = lane < rows ? P.B32[pos0 + lane] : 0.f;
+      recs_done++;
+      for (uint32_t qm = mask_cur; qm; qm &= qm - 1) {
+        const int qi = __ffs(qm) - 1;
+        const float nq = s_nq[qi];
+        if (!(nq > 0.f)) continue;  // null / irregular query: answered elsewhere
+        pairs_done++;
+        const uint32_t *keys = s_keys + qi * QKEYS;
+        const QFeat *feats = s_feats + qi * QFEATS;
+        unsigned long long acc_w = 0, acc_c = 0;
+        for (int e0 = 0; e0 < E; e0 += 32) {
+          const int e = e0 + lane;
+          const uint32_t w = e < E ? words[e] : PAD_WORD;
+          const uint32_t fid = (w >> 5) & FID_MASK;
+          int idx = -1;
+          if (fid != FID_NONE) {
+            uint32_t h = hash_fid(fid, 7);
+            for (;;) {
+              const uint32_t key = keys[h];
+              if (key == KEY_EMPTY) break;
+              if ((key >> 6) == fid) { idx = (int)(key & 63u); break; }
+              h = (h + 1) & (QKEYS - 1);
             }
-            if (pos >= 0) {
-              while (pos > 0 && (ls[pos - 1] < s || (ls[pos - 1] == s && lr[pos - 1] > row))) {
-                ls[pos] = ls[pos - 1];
-                lr[pos] = lr[pos - 1];
-                pos--;
+          }
+          const uint32_t hm = __ballot_sync(FULL, idx >= 0);
+          if (hm == 0) continue;
+          if (idx >= 0) {
+            uint32_t tf = w & 31u;
+            if (tf == TF_OVF) tf = ovf_lookup(P.ovf_keys, P.ovf_vals, P.n_ovf, chunk_cur, (uint32_t)e);
+            const QFeat f = feats[idx];
+            const unsigned long long ww = (((unsigned long long)f.w_hi << 32) | f.w_lo) * (unsigned long long)tf;
+            const unsigned long long cc = (unsigned long long)f.cq * (unsigned long long)tf * (unsigned long long)tf;
+            ScanHit hrec;
+            hrec.m = (w & W_ALL) ? valid : masks[e];
+            hrec.w_lo = (uint32_t)ww; hrec.w_hi = (uint32_t)(ww >> 32);
+            hrec.c_lo = (uint32_t)cc; hrec.c_hi = (uint32_t)(cc >> 32);
+            hrec.pad0 = hrec.pad1 = hrec.pad2 = 0;
+            my_hits[__popc(hm & lt)] = hrec;
+          }
+          __syncwarp();
+          const int nh = __popc(hm);
+          for (int i = 0; i < nh; i++) {
+            const uint4 h0 = *(const uint4 *)&my_hits[i];
+            const uint32_t chi = my_hits[i].c_hi;
+            if ((h0.x >> lane) & 1u) {
+              acc_w += ((unsigned long long)h0.w << 32) | h0.z;
+              acc_c += ((unsigned long long)chi << 32) | h0.y;
+            }
+          }
+          __syncwarp();
+        }
+        // fused epilogue: pre-test without division, exact score for survivors, insertion under the query's lock
+        if (lane < rows) {
+          const float dot = s_dotU[qi] + __ull2float_rn(acc_w) * (1.f / 4294967296.f);
+          const float corr = s_corrU[qi] - __ull2float_rn(acc_c) * (1.f / 16777216.f);
+          const float t = Bc + corr;
+          // current filter: the list's k-th score once it is full, and the global lower bound of the k-th score
+          float filt = __int_as_float(*(volatile int *)&P.gthr[q0 + qi]);
+          int krow = 0x7fffffff;
+          if (*(volatile int *)&s_cnt[qi] == k) {
+            const float ks = *(volatile float *)&s_lscore[qi * k + k - 1];
+            const int kr = *(volatile int *)&s_lrow[qi * k + k - 1];
+            if (ks > filt || (ks == filt && kr < krow)) { filt = ks; krow = kr; }
+          }
+          bool pass;
+          if (filt > 0.f) {
+            const float fq = P.jaccard ? filt * FILTER_SLACK : filt * filt * nq * FILTER_SLACK;
+            const float lhs = P.jaccard ? dot : dot * dot;
+            const float rhs = fq * (P.jaccard ? (nq + t - dot) : t);
+            pass = lhs >= rhs;
+          } else {
+            pass = true;
+          }
+          if (pass) {
+            const float s = pair_score(P.jaccard, dot, nq, t);
+            const int row = P.perm[pos0 + lane];
+            if (row != s_excl[qi] && (s > filt || (s == filt && row < krow))) {
+              while (atomicCAS(&s_lock[qi], 0, 1) != 0) {}
+              __threadfence_block();
+              float *ls = s_lscore + qi * k;
+              int *lr = s_lrow + qi * k;
+              int cnt = s_cnt[qi];
+              int pos = -1;
+              if (cnt < k) {
+                pos = cnt;
+                s_cnt[qi] = ++cnt;
+              } else if (s > ls[k - 1] || (s == ls[k - 1] && row < lr[k - 1])) {
+                pos = k - 1;
               }
-              ls[pos] = s;
-              lr[pos] = row;
+              if (pos >= 0) {
+                while (pos > 0 && (ls[pos - 1] < s || (ls[pos - 1] == s && lr[pos - 1] > row))) {
+                  ls[pos] = ls[pos - 1];
+                  lr[pos] = lr[pos - 1];
+                  pos--;
+                }
+                ls[pos] = s;
+                lr[pos] = row;
+                if (cnt == k) publish_threshold(q0 + qi, ls[k - 1]);
+              }
+              __threadfence_block();
+              atomicExch(&s_lock[qi], 0);
             }
-            if (cnt == k) {
-              float ks = ls[k - 1];
-              int kr = lr[k - 1];
-              if (ks > L.filt[g] || (ks == L.filt[g] && kr < L.krow[g])) set_filter<G>(L, g, ks, kr);
-              if (pos >= 0 && P.share) publish_threshold(td.q_begin + qi, ks);
-            }
-            __threadfence_block();
-            atomicExch(&s_lock[qi], 0);
           }
         }
-      }
-    });
-  };
-
-  long long t_ph1 = 0, t_re = 0, t_scan = 0, t_wait = 0;  // per-warp cycle counters (profiling aid)
-  constexpr int N_LEVELS = 24;  // bound levels of the visit order
-  // chunks of this split
-  const int64_t n_groups = (P.n_chunks + SUM_GROUP - 1) / SUM_GROUP;
-  const int64_t g_lo = n_groups * split / P.n_splits, g_hi = n_groups * (split + 1) / P.n_splits;
-  const int64_t c_lo = min(P.n_chunks, g_lo * SUM_GROUP), c_hi = min(P.n_chunks, g_hi * SUM_GROUP);
-
-  if (!P.prune) {
-    unsigned done = 0;
-    for (int64_t c = c_lo + warp; c < c_hi; c += n_warps, done++) process_chunk(c, FULL);
-    if (lane == 0) atomicAdd(&s_stat[0], done);
-  } else {
-    // ---- phase 1: an upper bound of every score in each chunk, from the chunk's summary pseudo-row ----
-    float *ub = P.ubuf + (size_t)tile * P.n_chunks;
-    long long t0 = clock64();
-    for (int64_t gg = g_lo + warp; gg < g_hi; gg += n_warps) {
-      float sd[G], sc0[G];  // start of a bound: universal features + the features (nearly) every chunk summary has
-#pragma unroll
-      for (int g = 0; g < G; g++) {
-        const int q = td.q_begin + (L.valid[g] ? g * 32 + lane : 0);
-        sd[g] = P.q_dotS[q];
-        sc0[g] = P.q_corrS[q];
-      }
-      // one group = SUM_GROUP chunk summaries: the features they all share are evaluated once (core), then
-      // every chunk's residual -> its bound
-      scan_entries<G, LOGH, XCAP, true>(P.grp_stream, P.grpptr[gg], P.grpptr[gg + 1], P.n_rows + P.n_chunks + gg * SUM_GROUP,
-                                  (int64_t)(OVF_GCORE_BASE + gg), tbl, lanebit,
-                                  P.ovf_keys, P.ovf_vals, P.n_ovf, sd, sc0,
-                                  [&](int row_in, const float *dot, const float *corr) {
-        const int64_t c = gg * SUM_GROUP + row_in;
-        const float Bmin = P.chunk_minB[c];
-        float best = -INFINITY;
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-          if (!L.valid[g]) continue;
-          const float b = bound_score(L.jaccard, dot[g], L.nq[g], Bmin + corr[g]);
-          best = fmaxf(best, b);
-        }
-        for (int o = 16; o; o >>= 1) best = fmaxf(best, __shfl_xor_sync(FULL, best, o));
-        if (lane == 0) ub[c] = best;
-      });
-    }
-    t_ph1 = clock64() - t0;
-    if (threadIdx.x <= N_LEVELS) s_next[threadIdx.x] = (long long)c_lo;
-    t0 = clock64();
-    __syncthreads();
-    t_wait += clock64() - t0;
-    // ---- phase 2: visit chunks by descending bound level; a warp stops once no remaining chunk can beat the
-    //      weakest k-th score of the tile.  Every level has its own chunk cursor, so warps move on to the next
-    //      level on their own (no barrier, no idle tail per level); each warp derives the tile-wide threshold
-    //      from the shared lists itself ----
-    auto tile_threshold = [&]() {  // weakest k-th score over the tile's queries (-inf while some query lacks k candidates)
-      refresh_filters();
-      float m = INFINITY;
-#pragma unroll
-      for (int g = 0; g < G; g++)
-        if (L.valid[g]) m = fminf(m, L.filt[g]);
-      for (int o = 16; o; o >>= 1) m = fminf(m, __shfl_xor_sync(FULL, m, o));
-      return m;
-    };
-    for (int lev = 0; lev <= N_LEVELS; lev++) {
-      const float hi = lev == 0 ? INFINITY : 1.0f - (lev - 1) * (1.0f / (N_LEVELS - 1));
-      const float lo = lev == N_LEVELS ? -INFINITY : 1.0f - lev * (1.0f / (N_LEVELS - 1));
-      float thr_min = tile_threshold();
-      if (hi * PRUNE_SLACK < thr_min) break;  // every remaining bound is below every k-th score
-      for (;;) {
-        long long nb = 0;
-        if (lane == 0) nb = atomicAdd((unsigned long long *)&s_next[lev], 32ULL);  // warps grab 32 chunks at a time
-        const int64_t base = __shfl_sync(FULL, nb, 0);
-        if (base >= c_hi) break;
-        const int64_t c = base + lane;
-        const float b = c < c_hi ? ub[c] : -INFINITY;
-        const bool in_level = c < c_hi && b >= lo && (b < hi || lev == 0);  // level 0 takes +inf bounds too
-        uint32_t m = __ballot_sync(FULL, in_level && b * PRUNE_SLACK >= thr_min);
-        const bool visited = m != 0;
-        if (lane == 0) {
-          atomicAdd(&s_stat[0], (unsigned)__popc(m));
-        }
-        while (m) {
-          const int j = __ffs(m) - 1;
-          m &= m - 1;
-          const int64_t cc = base + j;
-          // the stored bound is the max over the tile; re-evaluate it per query against each query's own
-          // current threshold (much sharper): scan the chunk only if some query could still place a row
-          refresh_filters();
-          const float Bmin = P.chunk_minB[cc];
-          long long t1 = clock64();
-          uint32_t may = 0;  // bit g: this lane's query of group g could still place a row of the chunk
-          float sd[G], sc0[G];
-#pragma unroll
-          for (int g = 0; g < G; g++) {
-            const int q = td.q_begin + (L.valid[g] ? g * 32 + lane : 0);
-            sd[g] = P.q_dotS[q];
-            sc0[g] = P.q_corrS[q];
-          }
-          scan_entries<G, LOGH, XCAP, false>(P.sum_stream, P.sumptr[cc], P.sumptr[cc + 1], P.n_rows + cc, 0, tbl, lanebit,
-                                       P.ovf_keys, P.ovf_vals, P.n_ovf, sd, sc0,
-                                [&](int, const float *dot, const float *corr) {
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-              if (!L.valid[g]) continue;
-              const float b2 = bound_score(L.jaccard, dot[g], L.nq[g], Bmin + corr[g]);
-              if (b2 * PRUNE_SLACK >= L.filt[g]) may |= 1u << g;
-            }
-          });
-          uint32_t gmask = 0;
-#pragma unroll
-          for (int g = 0; g < G; g++)
-            if (__any_sync(FULL, (may >> g) & 1u)) gmask |= 1u << g;
-          long long t2 = clock64();
-          t_re += t2 - t1;
-          if (gmask) {
-            process_chunk(cc, gmask);
-            t_scan += clock64() - t2;
-            if (lane == 0) atomicAdd(&s_stat[3], (unsigned)__popc(gmask));
-          } else if (lane == 0) {
-            atomicAdd(&s_stat[1], 1u);
-          }
-        }
-        if (visited) thr_min = tile_threshold();
+        __syncwarp();
       }
     }
-    t0 = clock64();
-    __syncthreads();
-    t_wait += clock64() - t0;
-    if (threadIdx.x == 0) s_stat[2] = (unsigned)(c_hi - c_lo);
-    if (lane == 0 && P.stats) {
-      atomicAdd(&P.stats[4], (unsigned long long)t_ph1);
-      atomicAdd(&P.stats[5], (unsigned long long)t_re);
-      atomicAdd(&P.stats[6], (unsigned long long)t_scan);
-      atomicAdd(&P.stats[7], (unsigned long long)t_wait);
-    }
+    __syncwarp();  // every lane is done with buffer b before a later copy may overwrite it
+    r_cur = r_nxt;
+    chunk_cur = chunk_nxt;
+    mask_cur = mask_nxt;
+    staged_cur = staged_nxt;
+    b ^= 1;
+  }
+  if (lane == 0) {
+    atomicAdd(&s_stat[0], pairs_done);
+    atomicAdd(&s_stat[1], recs_done);
   }
   __syncthreads();
-  // publish this CTA's partial lists (already ordered) and raise the global lower bounds
-  for (int i = threadIdx.x; i < td.q_count * k; i += blockDim.x) {
-    int qi = i / k, j = i - qi * k;
-    int64_t q = td.q_begin + qi;
-    size_t o = ((size_t)split * P.n_q + q) * k + j;
-    bool used = j < s_cnt[qi];
+  // publish this CTA's partial lists (already ordered)
+  const int part = bsplit * P.n_ssplits + ssplit;
+  for (int i = threadIdx.x; i < q_count * k; i += blockDim.x) {
+    const int qi = i / k, j = i - qi * k;
+    const size_t o = ((size_t)part * P.n_q + (q0 + qi)) * k + j;
+    const bool used = j < s_cnt[qi];
     P.part_scores[o] = used ? s_lscore[i] : -INFINITY;
     P.part_rows[o] = used ? (long long)(P.row_base + s_lrow[i]) : -1LL;
-    if (j == k - 1 && used) publish_threshold(q, s_lscore[i]);
   }
   if (threadIdx.x == 0 && P.stats) {
-    // s_stat[0]: chunks that passed the tile-wide test, s_stat[1]: of those, rejected per query
-    atomicAdd(&P.stats[0], (unsigned long long)(s_stat[0] - s_stat[1]));
-    atomicAdd(&P.stats[1], (unsigned long long)((c_hi - c_lo) - (long long)(s_stat[0] - s_stat[1])));
-    atomicAdd(&P.stats[2], (unsigned long long)s_stat[2] + s_stat[0]);
-    atomicAdd(&P.stats[3], (unsigned long long)s_stat[3]);
+    atomicAdd(&P.stats[0], (unsigned long long)s_stat[0]);
+    atomicAdd(&P.stats[1], (unsigned long long)s_stat[1]);
   }
+}
+
+static inline size_t scan_smem_bytes(int k) {
+  return (size_t)GROUP_Q * QTAB_BYTES + (size_t)S_WARPS * 2 * S_BUF_BYTES + (size_t)S_WARPS * 32 * sizeof(ScanHit) +
+         (size_t)S_WARPS * 2 * 8 + (size_t)GROUP_Q * k * 8 + (size_t)GROUP_Q * 4 * 6 + 16;
+}
+
+// seeds of the first bound pass -> fixed-stride candidate lists: query slot i holds n_seed chunk ids (-1: none)
+__global__ void seeds_to_lists_kernel(const int *__restrict__ seeds, int64_t n_q, int n_seed, uint2 *direct,
+                                      uint32_t *list_count) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t n_groups = (n_q + GROUP_Q - 1) / GROUP_Q;
+  if (i < n_groups) list_count[i] = (uint32_t)(GROUP_Q * n_seed);
+  if (i >= n_groups * GROUP_Q * n_seed) return;
+  const int64_t q = i / n_seed;
+  const int c = q < n_q ? seeds[i] : -1;
+  uint2 rec;
+  rec.x = c >= 0 ? (uint32_t)c : 0u;
+  rec.y = c >= 0 ? (1u << (q % GROUP_Q)) : 0u;
+  direct[i] = rec;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -785,7 +835,7 @@ __global__ void __launch_bounds__(256, 3) tfidf_topk_kernel(TopkParams P) {
 // multiply-add, no folded constants), so the bits depend only on the row's text, the query and the global
 // statistics -- not on which segment or shard holds the row or which features that shard folded as universal.
 // Rows with identical text therefore tie EXACTLY everywhere, and the (score desc, row asc) order of
-// services/gfkb/app.py:89 is reproduced across segments.  Same formula as K1a (values agree to ~1e-16 relative).
+// services/gfkb/app.py:89 is reproduced across segments.  Same formula as K1a (values agree to ~1e-12 relative).
 // Used by the batched match path: K1b selects candidates in float32, K6 gives them float64 scores.
 // ----------------------------------------------------------------------------------------
 struct RescoreParams {
@@ -856,11 +906,6 @@ __global__ void __launch_bounds__(256) rescore_kernel(RescoreParams P) {
     }
     P.out[pair] = sc;
   }
-}
-
-__global__ void invperm_kernel(const int *__restrict__ perm, int64_t n, int *invperm) {
-  const int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (pos < n) invperm[perm[pos]] = (int)pos;
 }
 
 // ----------------------------------------------------------------------------------------

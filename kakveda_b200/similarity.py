@@ -340,16 +340,23 @@ class GfkbIndex:
         _capi.check(_capi.load().kv_index_last_score_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def last_kernel_ms(self) -> Tuple[float, float, float, float, float]:
+        """CUDA-event ms of the last batch's kernels: bound pass 0 (seeds), seed scan, bound pass 1 (candidate lists),
+        candidate scan, merge."""
+        ms = (C.c_float * 5)()
+        _capi.check(_capi.load().kv_index_last_kernel_ms(self._h, ms))
+        return tuple(ms)
+
     def layout(self) -> dict:
         b = (C.c_int64 * 4)()
         c = (C.c_int64 * 17)()
         _capi.check(_capi.load().kv_index_layout(self._h, b, c))
-        return {"stream_bytes": b[0], "norm_bytes": b[1], "chunkptr_bytes": b[2], "summary_bytes": b[3],
+        return {"block_bytes": b[0], "norm_bytes": b[1], "directory_bytes": b[2], "dense_bytes": b[3],
                 "entries": c[0], "universal_features": c[1], "rows": c[2], "last_ctas": c[3], "last_tiles": c[4],
                 "last_splits": c[5], "last_upload_bytes": c[6], "tf_overflow_entries": c[7], "chunks": c[8],
-                "chunks_scanned": c[9], "chunks_pruned": c[10], "summaries_evaluated": c[11],
-                "groups_active": c[12], "cycles_bound_pass": c[13], "cycles_bound_requery": c[14],
-                "cycles_scan": c[15], "cycles_barrier": c[16]}
+                "pairs_scored": c[9], "records_scanned": c[10], "pairs_passed_bound": c[11],
+                "records_written": c[12], "kernel_launches": c[13], "rare_entries": c[14],
+                "pool_pages_used": c[15], "pool_pages": c[16]}
 
     def close(self) -> None:
         if self._h is not None:
@@ -379,15 +386,15 @@ class SimilarityEngine:
     device: int = 0
     _lock: threading.Lock = field(default_factory=threading.Lock, repr=False, compare=False)
     _index: Optional[GfkbIndex] = field(default=None, repr=False, compare=False)
-    _sig: Tuple[int, int] = field(default=(0, 0), repr=False, compare=False)
+    _rows: List[str] = field(default_factory=list, repr=False, compare=False)
 
     def _sync_index(self, corpus: Sequence[str]) -> GfkbIndex:
-        n = len(corpus)
-        sig = (n, hash(tuple(corpus)))
-        if self._index is not None and sig == self._sig:
+        # Identity of the cached corpus is decided by comparing the row strings themselves (a shallow copy of the last
+        # corpus is kept) -- exact, no hash that could collide; the comparison is a C-level list compare.
+        n, old_n = len(corpus), len(self._rows)
+        if self._index is not None and n == old_n and (corpus is self._rows or list(corpus) == self._rows):
             return self._index
-        old_n = self._sig[0]
-        if self._index is not None and 0 < old_n < n and hash(tuple(corpus[:old_n])) == self._sig[1]:
+        if self._index is not None and 0 < old_n < n and list(corpus[:old_n]) == self._rows:
             self._index.add_texts(corpus[old_n:])
         else:
             if self._index is not None:
@@ -395,7 +402,7 @@ class SimilarityEngine:
             self._index = GfkbIndex(device=self.device)
             self._index.add_texts(corpus)
         self._index.finalize()
-        self._sig = sig
+        self._rows = list(corpus)
         return self._index
 
     def score(self, query: str, corpus: List[str]) -> List[float]:
