@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=50_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary kernels (dense / Jaccard / hash / K1a) of the 1-GPU run")
     ap.add_argument("--shard", default="rows", choices=["rows", "queries", "rows-text"],
                     help="rows: corpus rows sharded over the GPUs by row index (BASELINE configs[2]); rows-text: sharded by ranges of "
                          "the global text order (tighter chunks per shard); queries: index replicated, queries split")
@@ -61,7 +62,7 @@ def workload_config(a, world):
         "parallelism": ("corpus rows sharded over %d GPU(s); queries replicated; pruning bounds pushed to peer GPUs over NVLink during the scan; 1 all-gather of partial top-k" % world)
                        if getattr(a, "shard", "rows").startswith("rows") else
                        ("index replicated on %d GPU(s); query batch split; 1 all-gather of the results" % world),
-        "l2": "inputs larger than L2 (scan stream >> 126 MB); no explicit flush",
+        "l2": "inputs larger than L2 (column blocks + dense bound matrix >> 126 MB); no explicit flush",
     }
 
 
@@ -125,7 +126,31 @@ def _ref_one(qtext):
     return time.perf_counter() - t
 
 
-def cpu_reference_rate(a, n_queries, procs):
+def _standalone_synth(seed, count, dup_of_seed=0, dup_rows=0):
+    """Synthetic rows from oracle/_build/libkvsynth.so (the generator alone, g++-built by __graft_entry__.build()):
+    the reference arm creates its inputs without loading the product's CUDA library."""
+    import ctypes as C
+
+    import numpy as np
+
+    so = ROOT / "oracle" / "_build" / "libkvsynth.so"
+    if not so.exists():
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", str(ROOT / "oracle" / "synth_shim.cpp"),
+                        "-o", str(so)], check=True)
+    lib = C.CDLL(str(so))
+    lib.kv_synth_signatures.restype = C.c_int
+    lib.kv_synth_signatures.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_char_p, C.c_int64,
+                                        C.POINTER(C.c_int64)]
+    off = np.zeros(count + 1, dtype=np.int64)
+    cap = max(1, count * 320)
+    buf = C.create_string_buffer(cap)
+    rc = lib.kv_synth_signatures(seed, 0, count, dup_of_seed, dup_rows, buf, cap, off.ctypes.data_as(C.POINTER(C.c_int64)))
+    assert rc == 0, "kv_synth_signatures failed"
+    raw = buf.raw
+    return [raw[off[i]:off[i + 1]].decode("ascii") for i in range(count)]
+
+
+def cpu_reference_rate(a, n_queries, procs, standalone=False):
     """Queries/s of the reference path on this box's host cores, scaled to the a.rows-entry GFKB.
 
     Sample: n_queries queries scored (SimilarityEngine.score semantics: TF-IDF refit per query) against
@@ -134,11 +159,15 @@ def cpu_reference_rate(a, n_queries, procs):
     parallel (the reference itself is single-threaded Python)."""
     import multiprocessing as mp
 
-    from kakveda_b200 import synth
-
     rows = min(a.cpu_sample_rows, a.rows)
-    _SAMPLE["corpus"] = synth.corpus(rows)
-    qs = synth.queries(n_queries, a.rows)
+    if standalone:
+        _SAMPLE["corpus"] = _standalone_synth(0xC0FFEE, rows)
+        qs = _standalone_synth(0xFACADE, n_queries, 0xC0FFEE, a.rows)
+    else:
+        from kakveda_b200 import synth
+
+        _SAMPLE["corpus"] = synth.corpus(rows)
+        qs = synth.queries(n_queries, a.rows)
     from oracle import tfidf_oracle as O
     O.score_sklearn(qs[0], _SAMPLE["corpus"][:64])  # import scikit-learn / page it in before the clock starts
     t0 = time.perf_counter()
@@ -192,9 +221,9 @@ def run_reference(a):
     procs = max(1, min(cores, 64))
     per_step = max(procs, a.cpu_sample_queries)
     for _ in range(max(0, min(a.warmup, 1))):
-        cpu_reference_rate(a, procs, procs)
+        cpu_reference_rate(a, procs, procs, standalone=True)
     t0 = time.perf_counter()
-    vals = [cpu_reference_rate(a, per_step, procs) for _ in range(max(1, a.steps))]
+    vals = [cpu_reference_rate(a, per_step, procs, standalone=True) for _ in range(max(1, a.steps))]
     total = time.perf_counter() - t0
     v = sum(x["value"] for x in vals) / len(vals)
     sample = ("%d queries x first %d rows per step with sklearn TfidfVectorizer refit per query "
@@ -264,7 +293,7 @@ def run_ours(a):
     shard.set_resident(qfb)   # inputs resident in HBM before the timed region
 
     # ---- device-resident timing: W warm-up + K timed steps ----
-    scan_ms, merge_ms = [], []
+    scan_ms, merge_ms, kern_ms, exch_ms = [], [], [], []
     for _ in range(a.warmup):
         shard.topk_resident(a.k)
     sampler = ClockSampler(local)
@@ -277,12 +306,53 @@ def run_ours(a):
         s, r = shard.topk_resident(a.k)
         ms = shard.index.last_timing_ms()
         scan_ms.append(ms[1]); merge_ms.append(ms[2])
+        kern_ms.append(shard.index.last_kernel_ms())
+        exch_ms.append(getattr(shard, "last_exchange_ms", (0.0, 0.0)))
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     step_ms = max_over_ranks(e0.elapsed_time(e1) / a.steps)
     lay = shard.index.layout()
     checksum = int(r.sum().item()) if r.numel() else 0
+    kavg = [sum(x[i] for x in kern_ms) / len(kern_ms) for i in range(5)]   # bound0, seed scan, bound1, scan, merge
+    local_kernels_ms = sum(kavg)
+    # per-rank attribution of a step (max/min over ranks): own kernels, all-gather, global merge
+    kmax, kmin = max_over_ranks(local_kernels_ms), -max_over_ranks(-local_kernels_ms)
+    gather_ms = max_over_ranks(sum(x[0] for x in exch_ms) / len(exch_ms))
+    gmerge_ms = max_over_ranks(sum(x[1] for x in exch_ms) / len(exch_ms))
+
+    # ---- parity inside the bench run: sampled queries of THIS batch re-scored by the float64 full scan (K1a) ----
+    # For 64 sampled queries every rank checks, on its own rows: (a) each returned (score, row) pair it owns agrees with
+    # the float64 score at rtol 1e-5, (b) no row of its shard outside the returned set beats the returned k-th score.
+    n_check = min(64, a.queries)
+    ok_pairs = bad = 0
+    s_h, r_h = s.cpu().numpy(), r.cpu().numpy()
+    row_map = shard.row_map.cpu().numpy() if getattr(shard, "row_map", None) is not None else None
+    base = shard.index.row_base if hasattr(shard.index, "row_base") else 0
+    for qi in np.linspace(0, a.queries - 1, n_check).astype(np.int64):
+        a0, a1 = int(qfb.indptr[qi]), int(qfb.indptr[qi + 1])
+        sc = shard.index.score_features(qfb.ids[a0:a1], qfb.tf[a0:a1], float(qfb.oov[qi]))
+        gids = row_map if row_map is not None else (np.arange(len(sc), dtype=np.int64) + base)
+        pos = {int(g): i for i, g in enumerate(r_h[qi]) if g >= 0}
+        mine = np.nonzero(np.isin(gids, np.fromiter(pos.keys(), dtype=np.int64, count=len(pos))))[0]
+        for li in mine:
+            want, got = sc[li], float(s_h[qi, pos[int(gids[li])]])
+            if abs(want - got) <= 1e-5 * abs(want) + 1e-7:
+                ok_pairs += 1
+            else:
+                bad += 1
+        rest = sc.copy()
+        rest[mine] = -1.0
+        kth = float(s_h[qi, a.k - 1]) if r_h[qi, a.k - 1] >= 0 else -1.0
+        if rest.size and rest.max() > kth * (1 + 1e-5) + 1e-7:
+            bad += 1
+    bad_total = int(max_over_ranks(float(bad)))
+    ok_total = ok_pairs
+    if world > 1:
+        t = torch.tensor([ok_pairs], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        ok_total = int(t.item())
+    assert bad_total == 0, f"in-run parity check failed on {bad_total} item(s)"
 
     # ---- end to end from host text ----
     e2e_steps = max(1, a.e2e_steps)
@@ -297,7 +367,7 @@ def run_ours(a):
     d2h = a.queries * a.k * 12
     assert int(er.sum()) == checksum, "end-to-end result differs from the resident-path result"
 
-    # ---- roofline of the dominant kernel (tfidf_topk_kernel), SURVEY section 8(d) accounting ----
+    # ---- roofline of the path, SURVEY section 8(d) accounting ----
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -305,45 +375,51 @@ def run_ours(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     rows_local = lay["rows"]
-    bytes_per_row = (lay["stream_bytes"] + lay["norm_bytes"] + lay["chunkptr_bytes"]) / max(1, rows_local)
+    bytes_per_row = (lay["block_bytes"] + lay["norm_bytes"] + lay["directory_bytes"]) / max(1, rows_local)
     tiles = lay["last_tiles"]
-    scan_s = (sum(scan_ms) / len(scan_ms)) / 1e3
+    names = ["tfidf_bound_kernel(pass 0: seeds)", "tfidf_scan_kernel(seeds)", "tfidf_bound_kernel(pass 1: candidate lists)",
+             "tfidf_scan_kernel(candidates)", "merge_topk_kernel"]
+    dom = max(range(5), key=lambda i: kavg[i])
+    path_s = local_kernels_ms / 1e3
     compulsory = tiles * rows_local * bytes_per_row + lay["last_upload_bytes"] + a.queries * a.k * 12 * lay["last_splits"]
-    achieved = compulsory / scan_s / 1e9
-    traffic = ncu_issue = issue_view = None
-    try:  # dram__bytes_read+write of exactly this launch, from the committed ncu capture (same workload only)
-        tr = json.loads((ROOT / "profiles" / "r1h_topk_traffic.json").read_text())
+    achieved = compulsory / path_s / 1e9
+    traffic = ncu_note = None
+    try:  # dram bytes of exactly these launches, from the committed ncu capture (same workload only)
+        tr = json.loads((ROOT / "profiles" / "r2_path_traffic.json").read_text())
         if (tr["rows"], tr["queries"], tr["k"], tr["n_gpus"]) == (a.rows, a.queries, a.k, world):
-            traffic, ncu_issue = tr["traffic_bytes_per_launch"], tr["issue_active_pct"]
-            # what actually binds this kernel: warp-instruction issue (148 SMs x 4 schedulers x 1 instruction / clock)
-            sm_hz = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
-            issue_peak = 148 * 4 * sm_hz
-            issue_view = {"warp_instructions_per_launch": tr["warp_instructions"], "achieved_per_s": tr["warp_instructions"] / scan_s,
-                          "peak_per_s": issue_peak, "frac": tr["warp_instructions"] / scan_s / issue_peak,
-                          "note": "instruction count from the committed ncu capture of this launch, time measured live"}
+            traffic, ncu_note = tr["traffic_bytes_per_step"], tr.get("note")
     except Exception:
         pass
+    pairs_all = a.queries * lay["chunks"]
     roofline = {
-        "bound": "hbm", "kernel": "tfidf_topk_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic, "ncu_issue_active_pct": ncu_issue, "issue_slots": issue_view,
+        "bound": "hbm", "kernel": "GFKB match path = " + " + ".join(names[:4]), "dominant_kernel": names[dom],
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "traffic_source": ("profiles/r2_path_traffic.json (ncu capture of this workload, committed; not re-measured in this run)" if traffic else None),
+        "ncu_note": ncu_note,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-        "algorithmic_bytes_per_launch": compulsory, "bytes_per_row": bytes_per_row,
-        "query_tile": 128, "query_tiles": tiles, "row_splits": lay["last_splits"],
-        "chunks": lay["chunks"], "chunks_scanned_per_tile": lay["chunks_scanned"] / max(1, tiles),
-        "chunks_pruned_frac": lay["chunks_pruned"] / max(1, lay["chunks_pruned"] + lay["chunks_scanned"]),
-        "active_groups_per_scanned_chunk": lay["groups_active"] / max(1, lay["chunks_scanned"]),
-        "warp_cycles": {kk: lay["cycles_" + kk] for kk in ("bound_pass", "bound_requery", "scan", "barrier")},
-        "kernel_ms": scan_s * 1e3, "merge_ms": sum(merge_ms) / len(merge_ms),
-        "unbatched_rate_gbs": a.queries * rows_local * bytes_per_row / scan_s / 1e9,
-        "note": "algorithmic bytes = query_tiles x rows x bytes_per_row (SURVEY 8(d): each 128-query tile would stream every "
-                "row once); block-max pruning skips ~91% of the chunks and L2 serves most re-reads, so measured DRAM traffic "
-                "is ~10x lower; the kernel is bound by instruction issue / shared-memory lookups (ncu issue-active 63%), "
-                "not by HBM -- see DESIGN.md section 6",
+        "algorithmic_bytes_per_step": compulsory, "bytes_per_row": bytes_per_row,
+        "query_tile": 128, "query_tiles": tiles, "partial_lists_per_query": lay["last_splits"],
+        "chunks": lay["chunks"], "chunk_rows": 32,
+        "kernel_ms": {"bound_pass0": kavg[0], "seed_scan": kavg[1], "bound_pass1": kavg[2], "candidate_scan": kavg[3], "merge": kavg[4],
+                      "sum": local_kernels_ms},
+        "dominant_kernel_frac": compulsory / (kavg[dom] / 1e3) / 1e9 / peak,
+        "pairs_passed_bound_frac": lay["pairs_passed_bound"] / max(1, pairs_all),
+        "pairs_scored_per_query": lay["pairs_scored"] / max(1, a.queries),
+        "candidate_records": lay["records_written"], "pool_pages_used": lay["pool_pages_used"],
+        "unbatched_rate_gbs": a.queries * rows_local * bytes_per_row / path_s / 1e9,
+        "note": "algorithmic bytes = query_tiles x rows x bytes_per_row (SURVEY 8(d): each 128-query tile would stream every row "
+                "once), divided by the SUM of the path's kernel times of one step (CUDA events on the launching stream, rank 0). "
+                "The path does not stream: tensor-core chunk bounds (exact block-max pruning) leave ~0.1% of the (query, chunk) "
+                "pairs to the exact scan, so measured DRAM traffic is far below the algorithmic bytes -- see DESIGN.md section 6",
     }
+    rank_stats = {"kernels_ms_max": kmax, "kernels_ms_min": kmin, "all_gather_ms": gather_ms, "global_merge_ms": gmerge_ms,
+                  "step_ms": step_ms, "unattributed_ms": step_ms - kmax - gather_ms - gmerge_ms}
+    parity = {"sampled_queries": int(n_check), "pairs_checked": int(ok_total), "failed": int(bad_total),
+              "check": "returned (score,row) pairs vs float64 full scan (K1a) at rtol 1e-5 + no unreturned row of a shard beats the k-th score"}
 
     # ---- secondary kernels of the path (rank 0): the HBM-bound single-query scan and the hash match ----
     secondary = None
-    if rank == 0 and world == 1:   # single-GPU runs only: keeps the multi-GPU scaling runs short
+    if rank == 0 and world == 1 and not a.no_secondary:   # single-GPU runs only: keeps the multi-GPU scaling runs short
         from kakveda_b200 import HashIndex
         ix = shard.index
         sc_ms = []
@@ -351,7 +427,7 @@ def run_ours(a):
             a0, a1 = int(qfb.indptr[i]), int(qfb.indptr[i + 1])
             ix.score_features(qfb.ids[a0:a1], qfb.tf[a0:a1], float(qfb.oov[i]))
             sc_ms.append(ix.last_score_ms())
-        sc_bytes = lay["stream_bytes"] + lay["chunkptr_bytes"] + rows_local * (8 + 4 + 8)
+        sc_bytes = lay["block_bytes"] + lay["directory_bytes"] + rows_local * (8 + 4 + 8)
         sc_s = min(sc_ms[1:]) / 1e3
         rng = np.random.default_rng(11)
         n_hash = 64_000_000  # 512 MB of fingerprints: larger than L2
@@ -448,7 +524,7 @@ def run_ours(a):
                                               "frac_of_bf16_sustained_peak": 2.0 * dn * dn * dd / (min(ams) / 1e3) / 1e12 / tsust,
                                               "rows_per_s": dn / (min(ams) / 1e3),
                                               "note": "BASELINE configs[3]: every row's 32 nearest other rows; full N x N (symmetry not exploited); parity unpinned"},
-            "k3_jaccard_1M_sets_2048_queries": {"kernel": "tfidf_topk_kernel (Jaccard mode)", "rows": jn, "queries": jq, "ms": min(jms),
+            "k3_jaccard_1M_sets_2048_queries": {"kernel": "tfidf_bound_kernel + tfidf_scan_kernel (Jaccard mode)", "rows": jn, "queries": jq, "ms": min(jms),
                                                 "queries_per_s": jq / (min(jms) / 1e3), "avg_tokens_per_row": jentries / jn,
                                                 "bytes_per_row": 4.0 * jentries / jn + 4.0,
                                                 "note": "random Zipf token sets have no text structure to prune on: close to an exhaustive scan; "
@@ -485,8 +561,8 @@ def run_ours(a):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
             "e2e": {"value": a.queries / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s * 1e3},
-            "gpu_launches": (2 if world == 1 else 3) * a.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
+            "gpu_launches": int(lay["kernel_launches"] + (1 if world > 1 else 0)) * a.steps,
+            "roofline": roofline, "rank_stats": rank_stats, "parity_in_run": parity, "cpu_baseline": cpu, "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

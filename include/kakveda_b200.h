@@ -207,9 +207,12 @@ int kv_index_thresholds_peers(kv_index *ix, const void *handles, int n_peers, in
 int kv_merge_topk_device(int device, const void *d_scores_in, const void *d_rows_in, int n_lists,
                          int64_t n_q, int k, void *d_scores_out, void *d_rows_out);
 /* The same on a caller-given CUDA stream (a cudaStream_t, e.g. the stream the all-gather that produced the lists
- * was enqueued on; NULL = legacy default stream); sync = 0 returns without waiting for the kernel. */
+ * was enqueued on; NULL = legacy default stream); sync = 0 returns without waiting for the kernel.  stride_s /
+ * stride_r: float32 / int64 elements between the starts of consecutive lists (n_q*k when contiguous; larger when
+ * scores and rows travel in ONE packed all-gather buffer per rank). */
 int kv_merge_topk_device_on(int device, const void *d_scores_in, const void *d_rows_in, int n_lists,
-                            int64_t n_q, int k, void *d_scores_out, void *d_rows_out, void *stream, int sync);
+                            int64_t n_q, int k, int64_t stride_s, int64_t stride_r, void *d_scores_out,
+                            void *d_rows_out, void *stream, int sync);
 
 /* Timing of the last kv_topk / kv_topk_device call on this handle, CUDA-event
  * milliseconds on its stream:

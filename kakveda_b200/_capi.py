@@ -64,8 +64,8 @@ SIGNATURES = {
     "kv_index_thresholds_peers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64]),
     "kv_merge_topk_device": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
                                        C.c_void_p]),
-    "kv_merge_topk_device_on": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
-                                          C.c_void_p, C.c_void_p, C.c_int]),
+    "kv_merge_topk_device_on": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "kv_index_last_timing": (C.c_int, [C.c_void_p, c_f32p]),
     "kv_index_last_kernel_ms": (C.c_int, [C.c_void_p, c_f32p]),
     "kv_index_last_score_ms": (C.c_int, [C.c_void_p, c_f32p]),

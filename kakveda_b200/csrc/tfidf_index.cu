@@ -79,6 +79,7 @@ struct kv_index {
   int n_ovf = 0;
   int64_t blk_words = 0, n_chunks = 0, n_chunks_pad = 0, n_entries = 0, n_rare_entries = 0;
   std::vector<uint32_t> h_df, h_tfmax;
+  std::vector<short> h_fslot;
   std::vector<uint8_t> h_univ;
   std::vector<uint32_t> h_utf;
   int64_t n_univ = 0;
@@ -485,8 +486,12 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
     bool same = (int64_t)ix->layout_univ.size() <= Vz;
     for (size_t t = 0; same && t < ix->layout_univ.size(); t++) same = ix->layout_univ[t] == ix->h_univ[t];
     for (size_t t = ix->layout_univ.size(); same && t < (size_t)V; t++) same = ix->h_univ[t] == 0;
-    if (same && V > (int64_t)ix->d_fslot.cap) same = false;  // new feature ids: the column map must grow
     if (same) {
+      if ((int64_t)ix->h_fslot.size() < Vz) {  // new feature ids (rows of another segment): none of them is a dense column
+        ix->h_fslot.resize((size_t)Vz, (short)-1);
+        KV_CUDA(ix->d_fslot.ensure(Vz));
+        KV_CUDA(cudaMemcpyAsync(ix->d_fslot.p, ix->h_fslot.data(), (size_t)Vz * sizeof(short), cudaMemcpyHostToDevice, s));
+      }
       rownorm_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(ix->indptr.p, ix->ids.p, ix->tf.p, ix->d_perm.p, n,
                                                                       ix->d_bb64.p, ix->d_B64.p, ix->d_B32.p);
       KV_CUDA(cudaGetLastError());
@@ -534,7 +539,8 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
       KV_CUDA(cudaMemcpyAsync(ix->d_blk.p + L.part_off[t], L.parts[t].data(), L.parts[t].size() * 4, cudaMemcpyHostToDevice, s));
   KV_CUDA(cudaMemcpyAsync(ix->d_binfo.p, L.binfo.data(), (size_t)L.n_chunks_pad * sizeof(BlockInfo), cudaMemcpyHostToDevice, s));
   KV_CUDA(cudaMemcpyAsync(ix->d_Uf.p, L.Uf.data(), (size_t)L.n_chunks_pad * NF * sizeof(__half), cudaMemcpyHostToDevice, s));
-  KV_CUDA(cudaMemcpyAsync(ix->d_fslot.p, L.fslot.data(), (size_t)Vz * sizeof(short), cudaMemcpyHostToDevice, s));
+  ix->h_fslot = L.fslot;
+  KV_CUDA(cudaMemcpyAsync(ix->d_fslot.p, ix->h_fslot.data(), (size_t)Vz * sizeof(short), cudaMemcpyHostToDevice, s));
   ix->n_ovf = (int)L.ovf.size();
   KV_CUDA(ix->d_ovf_keys.ensure(std::max(1, ix->n_ovf))); KV_CUDA(ix->d_ovf_vals.ensure(std::max(1, ix->n_ovf)));
   std::vector<unsigned long long> ok((size_t)ix->n_ovf);
@@ -597,8 +603,8 @@ static int score_impl(kv_index *ix, const uint32_t *q_ids, const uint32_t *q_tf,
   if (log_h > 13) return kv_fail(KV_ERR_INVALID, "kv_score: query has too many distinct features");
   const int H = 1 << log_h;
   // fixed point: the largest power-of-two scales that keep every row sum below 2^62
-  const int e_w = std::max(0, std::min(40, (int)std::floor(62.0 - std::log2(maxdot))));
-  const int e_c = std::max(0, std::min(40, (int)std::floor(62.0 - std::log2(maxcorr))));
+  const int e_w = std::max(0, std::min(50, (int)std::floor(62.0 - std::log2(maxdot))));
+  const int e_c = std::max(0, std::min(50, (int)std::floor(62.0 - std::log2(maxcorr))));
   const size_t tab_bytes = (size_t)H * (8 + 8 + 4);
   KV_CUDA(ix->h_qtab.ensure((int64_t)tab_bytes));
   KV_CUDA(ix->d_qtab1.ensure((int64_t)tab_bytes));
@@ -921,7 +927,7 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
     KV_CUDA(cudaEventRecord(ix->evk[4], s));
     KV_CUDA(cudaEventRecord(ix->ev[2], s));
     merge_topk_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, s>>>(ix->d_part_s.p, ix->d_part_r.p, (int)n_parts,
-                                                                         n_q, k, ix->d_qperm.p, d_out_s, d_out_r);
+                                                                         n_q, k, n_q * k, n_q * k, ix->d_qperm.p, d_out_s, d_out_r);
     KV_CUDA(cudaGetLastError());
     KV_CUDA(cudaEventRecord(ix->evk[5], s));
     launches += 2;
@@ -1183,21 +1189,24 @@ int kv_topk_device(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids,
 
 int kv_merge_topk_device(int device, const void *d_scores_in, const void *d_rows_in, int n_lists, int64_t n_q, int k,
                          void *d_scores_out, void *d_rows_out) {
-  return kv_merge_topk_device_on(device, d_scores_in, d_rows_in, n_lists, n_q, k, d_scores_out, d_rows_out, nullptr, 1);
+  return kv_merge_topk_device_on(device, d_scores_in, d_rows_in, n_lists, n_q, k, n_q * k, n_q * k, d_scores_out, d_rows_out,
+                                 nullptr, 1);
 }
 
 // stream: the CUDA stream (cudaStream_t) the input lists were produced on -- e.g. the stream an NCCL all-gather was
-// enqueued on -- or NULL for the legacy default stream; sync != 0 waits for the merge before returning
+// enqueued on -- or NULL for the legacy default stream; sync != 0 waits for the merge before returning.  stride_s /
+// stride_r: float32 / int64 elements between consecutive lists (packed all-gather buffers interleave both arrays).
 int kv_merge_topk_device_on(int device, const void *d_scores_in, const void *d_rows_in, int n_lists, int64_t n_q, int k,
-                            void *d_scores_out, void *d_rows_out, void *stream, int sync) {
-  if (n_lists < 1 || n_lists > 2048 || n_q < 0 || k < 1 || k > 255 || !d_scores_in || !d_rows_in || !d_scores_out || !d_rows_out)
+                            int64_t stride_s, int64_t stride_r, void *d_scores_out, void *d_rows_out, void *stream, int sync) {
+  if (n_lists < 1 || n_lists > 2048 || n_q < 0 || k < 1 || k > 255 || !d_scores_in || !d_rows_in || !d_scores_out || !d_rows_out ||
+      stride_s < n_q * k || stride_r < n_q * k)
     return kv_fail(KV_ERR_INVALID, "kv_merge_topk_device: bad arguments");
   if (n_q == 0) return KV_OK;
   KV_CUDA(cudaSetDevice(device));
   cudaStream_t s = (cudaStream_t)stream;
   merge_topk_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, s>>>((const float *)d_scores_in, (const long long *)d_rows_in,
-                                                                       n_lists, n_q, k, nullptr, (float *)d_scores_out,
-                                                                       (long long *)d_rows_out);
+                                                                       n_lists, n_q, k, stride_s, stride_r, nullptr,
+                                                                       (float *)d_scores_out, (long long *)d_rows_out);
   KV_CUDA(cudaGetLastError());
   if (sync) KV_CUDA(cudaStreamSynchronize(s));
   return KV_OK;

@@ -920,9 +920,10 @@ __device__ __forceinline__ bool better(float s1, long long r1, float s2, long lo
 }
 
 // out_index: optional map from the list's query slot to the output slot (un-sorts the query batch)
+// stride_s / stride_r: elements between the starts of consecutive lists (n_q * k when the lists are contiguous)
 __global__ void merge_topk_kernel(const float *__restrict__ in_s, const long long *__restrict__ in_r, int n_lists,
-                                  int64_t n_q, int k, const int *__restrict__ out_index, float *out_s,
-                                  long long *out_r) {
+                                  int64_t n_q, int k, int64_t stride_s, int64_t stride_r,
+                                  const int *__restrict__ out_index, float *out_s, long long *out_r) {
   const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (q >= n_q) return;
@@ -940,9 +941,9 @@ __global__ void merge_topk_kernel(const float *__restrict__ in_s, const long lon
       if (l >= n_lists) break;
       int h = head[i];
       if (h >= k) continue;
-      size_t o = ((size_t)l * n_q + q) * k + h;
-      float s = in_s[o];
-      long long r = in_r[o];
+      const size_t o = (size_t)q * k + h;
+      float s = in_s[(size_t)l * stride_s + o];
+      long long r = in_r[(size_t)l * stride_r + o];
       if (r >= 0 && (bl < 0 || better(s, r, bs, br))) { bs = s; br = r; bl = l; }
     }
     for (int o = 16; o; o >>= 1) {

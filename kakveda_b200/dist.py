@@ -65,14 +65,60 @@ def gather_topk(scores, rows, group=None):
 
 
 def merge_on_device(device: int, gs, gr):
-    """K5 on the gathered lists: ([W,Q,k],[W,Q,k]) -> ([Q,k],[Q,k])."""
+    """K5 on the gathered lists: ([W,Q,k],[W,Q,k]) -> ([Q,k],[Q,k]).  Runs on torch's current stream (the one the
+    all-gather was enqueued on), so no host synchronisation is needed between the collective and the merge."""
     import torch
 
     w, q, k = gs.shape
     out_s = torch.empty((q, k), dtype=torch.float32, device=gs.device)
     out_r = torch.empty((q, k), dtype=torch.int64, device=gs.device)
-    _capi.check(_capi.load().kv_merge_topk_device(device, C.c_void_p(gs.data_ptr()), C.c_void_p(gr.data_ptr()), w, q, k,
-                                                  C.c_void_p(out_s.data_ptr()), C.c_void_p(out_r.data_ptr())))
+    stream = torch.cuda.current_stream(gs.device).cuda_stream
+    _capi.check(_capi.load().kv_merge_topk_device_on(device, C.c_void_p(gs.data_ptr()), C.c_void_p(gr.data_ptr()), w, q, k,
+                                                     q * k, q * k, C.c_void_p(out_s.data_ptr()), C.c_void_p(out_r.data_ptr()),
+                                                     C.c_void_p(stream), 0))
+    return out_s, out_r
+
+
+def packed_layout(q: int, k: int) -> Tuple[int, int]:
+    """(offset of the rows array, total bytes) of one rank's packed partial top-k: [q*k float32][pad to 8][q*k int64]."""
+    off_r = (q * k * 4 + 7) // 8 * 8
+    return off_r, off_r + q * k * 8
+
+
+def packed_views(buf, q: int, k: int):
+    """float32 [q,k] / int64 [q,k] views of a packed uint8 buffer (any torch device)."""
+    import torch
+
+    off_r, total = packed_layout(q, k)
+    return (buf[: q * k * 4].view(torch.float32).view(q, k), buf[off_r:total].view(torch.int64).view(q, k))
+
+
+def gather_packed(buf, group=None):
+    """ONE all-gather of the packed per-shard partial top-k (scores and rows travel together): [total] uint8 ->
+    [W, total] uint8 on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        return buf.unsqueeze(0)
+    out = torch.empty((world, buf.numel()), dtype=torch.uint8, device=buf.device)
+    dist.all_gather_into_tensor(out.view(-1), buf.contiguous(), group=group)
+    return out
+
+
+def merge_packed_on_device(device: int, gathered, q: int, k: int):
+    """K5 directly on the packed all-gather buffer ([W, total] uint8), on torch's current stream, no host sync."""
+    import torch
+
+    w = gathered.shape[0]
+    off_r, total = packed_layout(q, k)
+    out_s = torch.empty((q, k), dtype=torch.float32, device=gathered.device)
+    out_r = torch.empty((q, k), dtype=torch.int64, device=gathered.device)
+    stream = torch.cuda.current_stream(gathered.device).cuda_stream
+    _capi.check(_capi.load().kv_merge_topk_device_on(device, C.c_void_p(gathered.data_ptr()), C.c_void_p(gathered.data_ptr() + off_r),
+                                                     w, q, k, total // 4, total // 8, C.c_void_p(out_s.data_ptr()),
+                                                     C.c_void_p(out_r.data_ptr()), C.c_void_p(stream), 0))
     return out_s, out_r
 
 
@@ -198,15 +244,25 @@ class ShardedGfkb:
             keep = torch.cat([torch.arange(w * per, w * per + (shard_bounds(q, self.world, w)[1] - shard_bounds(q, self.world, w)[0]),
                                            device=dev) for w in range(self.world)])
             return gs[keep], gr[keep]
-        s = torch.empty((q, k), dtype=torch.float32, device=dev)
-        r = torch.empty((q, k), dtype=torch.int64, device=dev)
+        # rows mode: the local result lands in ONE packed buffer (scores + rows), which is what travels
+        buf = torch.empty(packed_layout(q, k)[1], dtype=torch.uint8, device=dev)
+        s, r = packed_views(buf, q, k)
         self.index.topk_resident(k, s.data_ptr(), r.data_ptr())
         if self.row_map is not None:  # text-range shard: local row -> global row id (-1 stays -1)
-            r = torch.where(r >= 0, self.row_map[r.clamp(min=0)], r)
+            r.copy_(torch.where(r >= 0, self.row_map[r.clamp(min=0)], r))
         if self.world == 1:
             return s, r
-        gs, gr = gather_topk(s, r, self.group)
-        return merge_on_device(self.device, gs, gr)
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True); t2 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        gathered = gather_packed(buf, self.group)          # the single NCCL all-gather of the path
+        t1.record()
+        out = merge_packed_on_device(self.device, gathered, q, k)
+        t2.record()
+        # The collective doubles as the barrier between batches for the cross-GPU threshold pushes: no rank may start
+        # the next batch's scan (which resets and pushes thresholds) before every rank has finished this one's.
+        torch.cuda.current_stream().synchronize()
+        self.last_exchange_ms = (t0.elapsed_time(t1), t1.elapsed_time(t2))
+        return out
 
     def set_resident(self, qfb: FeatureBatch) -> None:
         self.upload(qfb)

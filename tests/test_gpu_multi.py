@@ -38,7 +38,7 @@ def _worker(rank, world, port, n, q, k, tmp, mode):
         np.save(Path(tmp, f"s{rank}{mode}.npy"), s)
         np.save(Path(tmp, f"r{rank}{mode}.npy"), r)
         lay = sh.index.layout()
-        Path(tmp, f"info{rank}{mode}.txt").write_text(f"{getattr(sh, 'n_threshold_peers', 0)} {lay['chunks_scanned']}")
+        Path(tmp, f"info{rank}{mode}.txt").write_text(f"{getattr(sh, 'n_threshold_peers', 0)} {lay['pairs_scored']}")
     finally:
         dist.destroy_process_group()
 

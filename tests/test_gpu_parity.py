@@ -166,7 +166,7 @@ def test_medium_vs_vectorised_oracle(lib):
     for i in (0, 3, 4, 77):
         np.testing.assert_allclose(ix.score(queries[i]), oracle[i], rtol=RTOL64, atol=1e-15)
     lay = ix.layout()
-    assert lay["rows"] == n and lay["tf_overflow_entries"] >= 4   # "tok" x35 and "tok tok" x34 in rows 17, 18 (+ their chunk summary)
+    assert lay["rows"] == n and lay["tf_overflow_entries"] >= 2   # "tok" x35 and "tok tok" x34 (rows 17, 18 share the block entries)
     clean = GfkbIndex()
     clean.add_texts(synth.corpus(5000))
     clean.finalize()
@@ -268,11 +268,14 @@ def test_pruned_scan_equals_exhaustive_scan(lib):
     queries = synth.queries(q, n) + ["", "zz qq unseen", "intent_tags prompt_hint tools env_keys"]
     s1, r1 = ix.topk(queries, k)
     lay = ix.layout()
-    assert lay["chunks_pruned"] > 0.05 * (lay["chunks_scanned"] + lay["chunks_pruned"]), lay
+    # the tensor-core bounds leave only a small share of the (query, chunk) pairs to the exact scan
+    assert 0 < lay["pairs_passed_bound"] < 0.2 * len(queries) * lay["chunks"], lay
+    assert lay["pairs_scored"] >= lay["pairs_passed_bound"] and lay["records_written"] > 0
     os.environ["KAKVEDA_B200_NO_PRUNE"] = "1"
     try:
         s2, r2 = ix.topk(queries, k)
-        assert ix.layout()["chunks_pruned"] == 0
+        lay2 = ix.layout()
+        assert lay2["pairs_passed_bound"] == 0 and lay2["pairs_scored"] >= q * lay2["chunks"]  # exhaustive: no bound kernel
     finally:
         del os.environ["KAKVEDA_B200_NO_PRUNE"]
     np.testing.assert_array_equal(r1, r2)

@@ -149,7 +149,7 @@ def test_rescore_is_float64_and_ties_exactly(lib):
     dup = [j for j in range(k) if rows[0, j] in (7, 100, 19000)]
     assert len(dup) == 3 and len({f64[0, j] for j in dup}) == 1            # identical rows: identical bits
     full = ix.score(queries[0])
-    np.testing.assert_allclose(f64[0], full[rows[0]], rtol=1e-14)
+    np.testing.assert_allclose(f64[0], full[rows[0]], rtol=1e-13)  # K1a: exact fixed-point sums (2^-50), K6: ordered float64 sums
 
 
 def test_selfjoin_corpus_fit_matches_sklearn_golden(lib, golden):
