@@ -221,6 +221,10 @@ int kv_index_last_timing(const kv_index *ix, float ms[4]);
 /* ... and of its kernels: ms[0] = bound pass 0 (seeds; tcgen05 GEMM + rare-feature join), ms[1] = seed scan,
  * ms[2] = bound pass 1 (candidate lists), ms[3] = candidate scan, ms[4] = merge.  Exhaustive mode: only [3], [4]. */
 int kv_index_last_kernel_ms(const kv_index *ix, float ms[5]);
+/* Test hook: runs the resident batch once and returns the numerators (dot-product upper bounds) the bound kernel formed
+ * for every (query slot, chunk): out[n_q][chunks] floats, slot_query[i] = original query of sorted slot i.  Needs an
+ * index large enough for the pruned path (>= 512 chunks of 32 rows); tests/test_gpu_parity.py compares with NumPy. */
+int kv_debug_bound_numerators(kv_index *ix, int k, float *out, int32_t *slot_query);
 /* CUDA-event milliseconds of the scan kernel of the last kv_score call (K1a). */
 int kv_index_last_score_ms(const kv_index *ix, float *ms);
 

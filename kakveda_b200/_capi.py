@@ -69,6 +69,7 @@ SIGNATURES = {
     "kv_index_last_timing": (C.c_int, [C.c_void_p, c_f32p]),
     "kv_index_last_kernel_ms": (C.c_int, [C.c_void_p, c_f32p]),
     "kv_index_last_score_ms": (C.c_int, [C.c_void_p, c_f32p]),
+    "kv_debug_bound_numerators": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.POINTER(C.c_int32)]),
     "kv_index_layout": (C.c_int, [C.c_void_p, c_i64p, c_i64p]),
     "kv_dense_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
     "kv_dense_destroy": (None, [C.c_void_p]),

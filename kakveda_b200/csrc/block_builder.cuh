@@ -69,6 +69,8 @@ struct BlockLayout {
   std::vector<short> fslot;                   // [V] column of a frequent feature, -1 otherwise
   std::vector<uint32_t> frequent;             // the frequent features by column
   std::vector<__half> Uf;                     // [n_chunks_pad][NF] largest tf of the frequent features per chunk
+  std::vector<unsigned short> fslot2;         // [V] bit row of a second-class feature, 0xFFFF otherwise
+  std::vector<uint32_t> Ubt;                  // [n_chunks_pad / 64][NF2][2][2]: bit c % 64 of plane 0 / 1 = present in chunk c with tf >= 1 / >= 2
   int64_t n_entries = 0, n_rare_entries = 0;
 };
 
@@ -128,7 +130,21 @@ inline void build_blocks(const int64_t *indptr, const uint32_t *ids, const uint1
       L.fslot[cand[i].second] = (short)i;
       L.frequent.push_back(cand[i].second);
     }
+    // second class: the next NF2 features by chunk frequency (any tf: the bound uses the feature's largest tf)
+    L.fslot2.assign((size_t)Vz, (unsigned short)0xFFFF);
+    std::vector<std::pair<uint32_t, uint32_t>> rest;
+    for (int64_t f = 0; f < V; f++) {
+      const uint32_t cfreq = cnt[(size_t)f].load(std::memory_order_relaxed);
+      if (cfreq > 0 && L.fslot[(size_t)f] < 0) rest.emplace_back(cfreq, (uint32_t)f);
+    }
+    const size_t keep2 = std::min<size_t>(NF2, rest.size());
+    std::partial_sort(rest.begin(), rest.begin() + (std::ptrdiff_t)keep2, rest.end(),
+                      [](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) {
+                        return a.first != b.first ? a.first > b.first : a.second < b.second;
+                      });
+    for (size_t i = 0; i < keep2; i++) L.fslot2[rest[i].second] = (unsigned short)i;
   }
+  L.Ubt.assign((size_t)(L.n_chunks_pad / 64) * NF2 * 4, 0u);
   // pass 2: the blocks
   L.parts.assign((size_t)T, {});
   L.binfo.assign((size_t)L.n_chunks_pad, BlockInfo{0, 0, 0});
@@ -160,6 +176,12 @@ inline void build_blocks(const int64_t *indptr, const uint32_t *ids, const uint1
           urow[fs] = __float2half((float)tfv);  // keys ascend in tf: the last one is the largest (exact: tf <= 2048)
         } else {
           w_r.push_back(word); m_r.push_back(mask); tf_r.push_back(tfv);
+          const unsigned short f2 = L.fslot2[f];
+          if (f2 != 0xFFFFu) {  // chunks of one 128-chunk block may belong to different threads: atomic OR
+            uint32_t *w0 = &L.Ubt[((size_t)(c >> 6) * NF2 + f2) * 4 + ((c & 63) >> 5)];
+            __atomic_fetch_or(w0, 1u << (c & 31), __ATOMIC_RELAXED);
+            if (tfv >= 2) __atomic_fetch_or(w0 + 2, 1u << (c & 31), __ATOMIC_RELAXED);
+          }
         }
       }
       const size_t E = w_r.size() + w_f.size(), E4 = (E + 3) & ~(size_t)3;

@@ -10,8 +10,13 @@
 //     rounded UP to fp16, tf exact): tcgen05.mma cta_group::1 kind::f16, M = N = 128, fp32 accumulators in TMEM
 //     (double buffered), the query operand resident in shared memory for the CTA's life, the chunk operand streamed
 //     by TMA (128B swizzle, mbarrier expect_tx) -- this only computes BOUNDS; scores stay exact integer sums (K1b-S);
-//   * the sum over RARE features is a join: the worker warps probe each chunk's rare block entries in the tile's
-//     rare-feature table (shared memory) and add the hits into R[chunk][query] (shared-memory atomics);
+//   * the next NF2 = 2048 features by chunk frequency ("second class": mid-frequency words and bigrams, each shared by
+//     many queries of a tile) are kept per 128-chunk block as TRANSPOSED presence bitmaps Ubt[feature][128 chunk bits]
+//     (32 KB, one bulk-async copy per block): a query thread reads ONE word per feature of its own list (<= 16) and has
+//     that feature's presence in its 32 chunk columns -- lane-parallel, no atomics;
+//   * the sum over the remaining RARE features is a join: the worker warps probe each chunk's non-frequent block
+//     entries first in a presence bitmap, then in the tile's rare-feature table (shared memory); the few hits
+//     (~1.4 per chunk and tile) go to per-query hit slots;
 //   * epilogue (16 warps, thread = query, tcgen05.ld of 32 chunk columns): bound vs the query's threshold.
 //     pass 0 keeps, per thread, the 4 best chunks by bound (seeds: K1b-S scores them first, which gives every query a
 //     close lower bound theta0 of its k-th best score); pass 1 appends {chunk, mask of the group's surviving queries}
@@ -24,14 +29,16 @@
 
 namespace kvk {
 
-constexpr int B_BN = 128;                    // chunks per block = N of the MMA tile
+constexpr int B_BN = 64;                     // chunks per block = N of the MMA tile
 constexpr int B_BK = 64;                     // K slice: 64 fp16 = one 128-byte swizzle row
 constexpr int B_KSLICES = NF / B_BK;         // 4
 constexpr int B_STAGES = 2;
-constexpr int B_SLICE_BYTES = 128 * B_BK * 2;  // 16 KiB: one K slice of either operand
+constexpr int B_A_SLICE_BYTES = TILE_Q * B_BK * 2;  // 16 KiB: one K slice of the query operand
+constexpr int B_B_SLICE_BYTES = B_BN * B_BK * 2;    // 8 KiB: one K slice of the chunk operand
 constexpr int B_WORKERS = 16;
 constexpr int B_THREADS = (B_WORKERS + 2) * 32;
-constexpr int B_SEEDS = 4;                   // seeds per worker thread; a query is served by 4 threads (column quarters)
+constexpr int B_COLS = B_BN / 4;             // chunk columns per epilogue thread (four threads serve a query)
+constexpr int B_SEEDS = 4;                   // seeds per worker thread
 constexpr int B_SEEDS_PER_QUERY = 4 * B_SEEDS;
 
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
@@ -53,7 +60,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem) {
   return d;
 }
 
-// instruction descriptor: D = f32, A = B = f16, both K-major, N = 128, M = 128
+// instruction descriptor: D = f32, A = B = f16, both K-major, N = 64, M = 128
 constexpr uint32_t B_IDESC = (1u << 4) | ((uint32_t)(B_BN >> 3) << 17) | ((uint32_t)(TILE_Q >> 4) << 24);
 
 __device__ __forceinline__ void umma_f16_128(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
@@ -79,6 +86,8 @@ struct BoundParams {
   int n_ovf;
   int64_t n_chunks, n_q;
   const unsigned char *rtab;                              // [n_tiles][RTAB_BYTES]
+  const uint2 *q2list;                                    // [n_tiles][Q2CAP][TILE_Q]
+  const uint32_t *ubt;                                    // [n_blocks][NF2][2][B_BN / 32]
   const float *q_nq, *q_dotS, *q_dotX, *q_corrS;          // [n_q] (sorted query order)
   const int *gthr;                                        // [n_q] float bits: lower bound of the k-th score
   int pass;                                               // 0: seeds, 1: candidate lists
@@ -93,15 +102,19 @@ struct BoundParams {
   unsigned int pool_pages;  // capacity
   int *overflow;            // set when the pool ran out (the batch is rerun with a larger pool)
   unsigned long long *stats;  // [2] surviving (query, chunk) pairs, [3] candidate records
+  float *dbg_xs;              // test hook: when set, the numerator of every bound, [n_q][n_chunks_pad]
+  int64_t dbg_stride;
 };
 
 struct __align__(1024) BoundSmem {
-  unsigned char a[B_KSLICES][B_SLICE_BYTES];   // the tile's weight rows, resident
-  unsigned char b[B_STAGES][B_SLICE_BYTES];    // chunk slices in flight
-  float R[B_BN][TILE_Q];                       // rare part of the dot bound, [chunk][query]
+  unsigned char a[B_KSLICES][B_A_SLICE_BYTES];   // the tile's weight rows, resident
+  unsigned char b[B_STAGES][B_B_SLICE_BYTES];    // chunk slices in flight
+  uint32_t ubt[NF2][2][B_BN / 32];               // second-class bitmaps (tf >= 1, tf >= 2) of the current block of chunks
+  float R[B_BN][TILE_Q];                         // rare part of the dot bound, [chunk][query]
   unsigned char rtab[RTAB_BYTES];
+  uint2 q2[Q2CAP][TILE_Q];                       // the queries' second-class lists (bit row | (tfmax - 1) << 16, weight)
   float minB[2][B_BN];
-  uint64_t full_bar[B_STAGES], empty_bar[B_STAGES], a_bar, tmem_full[2], tmem_empty[2];
+  uint64_t full_bar[B_STAGES], empty_bar[B_STAGES], a_bar, ubt_bar, tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
   unsigned int lcount[4];
   int pages[1];  // [4][max_pages], sized at launch
@@ -121,17 +134,21 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < B_STAGES; i++) { mbar_init(&S.full_bar[i], 1); mbar_init(&S.empty_bar[i], 1); }
     mbar_init(&S.a_bar, 1);
+    mbar_init(&S.ubt_bar, 1);
     for (int i = 0; i < 2; i++) { mbar_init(&S.tmem_full[i], 1); mbar_init(&S.tmem_empty[i], B_WORKERS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == B_WORKERS + 1) {  // TMEM: 256 columns = two 128x128 fp32 accumulators
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_addr(&S.tmem_base)) : "memory");
+  if (warp == B_WORKERS + 1) {  // TMEM: 128 columns = two 128x64 fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_addr(&S.tmem_base)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  {  // rare-feature table of the tile, R = 0, list state
+  {  // rare-feature table and second-class lists of the tile, hit slots, list state
     const uint4 *src = (const uint4 *)(P.rtab + (size_t)tile * RTAB_BYTES);
     uint4 *dst = (uint4 *)S.rtab;
     for (int i = threadIdx.x; i < RTAB_BYTES / 16; i += B_THREADS) dst[i] = src[i];
+    const uint4 *src2 = (const uint4 *)(P.q2list + (size_t)tile * Q2CAP * TILE_Q);
+    uint4 *dst2 = (uint4 *)&S.q2[0][0];
+    for (int i = threadIdx.x; i < Q2CAP * TILE_Q / 2; i += B_THREADS) dst2[i] = src2[i];
     float4 *r4 = (float4 *)&S.R[0][0];
     for (int i = threadIdx.x; i < B_BN * TILE_Q / 4; i += B_THREADS) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = threadIdx.x; i < 4 * P.max_pages; i += B_THREADS) S.pages[i] = -1;
@@ -145,14 +162,14 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
   if (warp == B_WORKERS) {
     // ===== TMA producer =====
     if (lane == 0) {
-      mbar_expect_tx(&S.a_bar, B_KSLICES * B_SLICE_BYTES);
+      mbar_expect_tx(&S.a_bar, B_KSLICES * B_A_SLICE_BYTES);
       for (int s = 0; s < B_KSLICES; s++) tma_load_2d(S.a[s], &map_w, &S.a_bar, s * B_BK, tile * TILE_Q);
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t bk = blk_lo; bk < blk_hi; bk++) {
         for (int s = 0; s < B_KSLICES; s++) {
           mbar_wait(&S.empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&S.full_bar[stage], B_SLICE_BYTES);
+          mbar_expect_tx(&S.full_bar[stage], B_B_SLICE_BYTES);
           tma_load_2d(S.b[stage], &map_u, &S.full_bar[stage], s * B_BK, (int)(bk * B_BN));
           if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -197,9 +214,9 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     const float base = q_ok ? P.q_dotS[slot] + P.q_dotX[slot] : 0.f;
     const float corrS = q_ok ? P.q_corrS[slot] : 0.f;
     const uint32_t *rt_keys = (const uint32_t *)S.rtab;
-    const float *rt_w = (const float *)(rt_keys + RT_SLOTS);
-    const uint32_t *rt_q = (const uint32_t *)(rt_w + RT_SLOTS);
-    const uint32_t *rt_multi = rt_q + RT_SLOTS;
+    const uint32_t *rt_wq = rt_keys + RT_SLOTS;
+    const uint32_t *rt_multi = rt_wq + RT_SLOTS;
+    const uint32_t *rt_bm = rt_multi + 4 * RT_MULTI;
     const int list = (tile * 4 + qtr) * P.n_bsplits + bsplit;
     int *my_pages = S.pages + qtr * P.max_pages;
     float sm[B_SEEDS];
@@ -207,47 +224,85 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
 #pragma unroll
     for (int i = 0; i < B_SEEDS; i++) { sm[i] = -1.f; sc[i] = -1; }
     unsigned int n_pairs = 0, n_recs = 0;
+    if (threadIdx.x == 0 && blk_lo < blk_hi) {  // second-class bitmaps of the first block
+      mbar_expect_tx(&S.ubt_bar, sizeof(S.ubt));
+      bulk_copy_g2s(&S.ubt[0][0][0], P.ubt + (size_t)blk_lo * (sizeof(S.ubt) / 4), sizeof(S.ubt), &S.ubt_bar);
+    }
     int64_t it = 0;
     for (int64_t bk = blk_lo; bk < blk_hi; bk++, it++) {
       const int as = (int)(it & 1);
       const uint32_t aphase = (uint32_t)((it >> 1) & 1);
       const int64_t c0 = bk * B_BN;
-      // ---- join: rare entries of this warp's chunks against the tile's rare-feature table ----
-      for (int j = warp; j < B_BN; j += B_WORKERS) {
-        const int64_t c = c0 + j;
-        if (c >= P.n_chunks) break;
-        const BlockInfo bi = P.binfo[c];
-        const int nr = bi.n_rare;
-        const uint32_t *words = P.blk + (size_t)bi.off4 * 4;
-        float *Rj = &S.R[j][0];
-        uint32_t nxt = lane < nr ? __ldg(words + lane) : PAD_WORD;
-        for (int e0 = 0; e0 < nr; e0 += 32) {
-          const uint32_t w = nxt;
-          const int en = e0 + 32 + lane;
-          nxt = en < nr ? __ldg(words + en) : PAD_WORD;
+      // ---- join: non-frequent entries of this warp's chunks against the tile's rare-feature table ----
+      // The warp owns chunks warp, warp + 16, ... of the block.  Lane l first fetches the directory entry of the l-th
+      // of them; the first 128 words of a chunk are loaded one chunk ahead (registers), so that the L2 latency of
+      // chunk j+1 hides behind the probing of chunk j.  An entry first tests the tile's presence bitmap (one
+      // shared-memory load rejects ~98 % of them); only then the table is probed.  A hit adds its weight to R[chunk]
+      // for every query holding the feature.  (Rows are text-sorted, so a query may hit the same rare feature in most
+      // chunks of a block: R is dense.)
+      {
+        constexpr int PER_WARP = B_BN / B_WORKERS;
+        uint32_t my_off = 0, my_nr = 0;
+        if (lane < PER_WARP && c0 + warp + B_WORKERS * lane < P.n_chunks) {
+          const BlockInfo bi = P.binfo[c0 + warp + B_WORKERS * lane];
+          my_off = bi.off4;
+          my_nr = bi.n_rare;
+        }
+        auto probe = [&](uint32_t w, int j, uint32_t e) {
           const uint32_t fid = (w >> 5) & FID_MASK;
-          if (fid == FID_NONE) continue;
+          if (fid == FID_NONE) return;
+          const uint32_t bb = rt_bit(fid);
+          if (!((rt_bm[bb >> 5] >> (bb & 31u)) & 1u)) return;
           uint32_t h = hash_fid(fid, 11);
           for (;;) {
             const uint32_t key = rt_keys[h];
-            if (key == KEY_EMPTY) break;
-            if (key == fid) {
-              uint32_t tf = w & 31u;
-              if (tf == TF_OVF) tf = ovf_lookup(P.ovf_keys, P.ovf_vals, P.n_ovf, c, (uint32_t)(e0 + lane));
-              const float x = __fmul_ru(rt_w[h], (float)tf);
-              const uint32_t qinfo = rt_q[h];
-              if (qinfo < (uint32_t)TILE_Q) {
-                atomicAdd(&Rj[qinfo], x);
-              } else if (qinfo != 0xFFFFFFFFu) {
-                const uint32_t *mm = rt_multi + 4 * (qinfo & 0x7FFFFFFFu);
-#pragma unroll
-                for (int g = 0; g < 4; g++)
-                  for (uint32_t bits = mm[g]; bits; bits &= bits - 1) atomicAdd(&Rj[g * 32 + __ffs(bits) - 1], x);
-              }
-              break;
-            }
+            if (key == KEY_EMPTY) return;
+            if (key == fid) break;
             h = (h + 1) & (RT_SLOTS - 1);
           }
+          uint32_t tf = w & 31u;
+          if (tf == TF_OVF) tf = ovf_lookup(P.ovf_keys, P.ovf_vals, P.n_ovf, c0 + j, e);
+          const uint32_t wq = rt_wq[h];
+          const float x = __fmul_ru(__half2float(__ushort_as_half((unsigned short)(wq & 0xFFFFu))), (float)tf);
+          const uint32_t qinfo = wq >> 16;
+          float *Rj = &S.R[j][0];
+          if (qinfo < (uint32_t)TILE_Q) {
+            atomicAdd(&Rj[qinfo], x);
+          } else if (qinfo != 0xFFFFu) {
+            const uint32_t *mm = rt_multi + 4 * (qinfo & 0x7FFFu);
+#pragma unroll
+            for (int g = 0; g < 4; g++)
+              for (uint32_t bits = mm[g]; bits; bits &= bits - 1) atomicAdd(&Rj[g * 32 + __ffs(bits) - 1], x);
+          }
+        };
+        uint32_t cur[4], nxt[4];
+        auto load4 = [&](int jj, uint32_t (&dst)[4]) {
+          const uint32_t off = __shfl_sync(FULL, my_off, jj), nr = __shfl_sync(FULL, my_nr, jj);
+          const uint32_t *words = P.blk + (size_t)off * 4;
+#pragma unroll
+          for (int bq = 0; bq < 4; bq++) {
+            const uint32_t e = (uint32_t)(bq * 32 + lane);
+            dst[bq] = e < nr ? __ldg(words + e) : PAD_WORD;
+          }
+        };
+        load4(0, cur);
+#pragma unroll 1
+        for (int jj = 0; jj < PER_WARP; jj++) {
+          if (jj + 1 < PER_WARP) load4(jj + 1, nxt);
+          const int j = warp + B_WORKERS * jj;
+          const uint32_t nr = __shfl_sync(FULL, my_nr, jj);
+#pragma unroll
+          for (int bq = 0; bq < 4; bq++)
+            if ((uint32_t)(bq * 32) < nr) probe(cur[bq], j, (uint32_t)(bq * 32 + lane));
+          if (nr > 128u) {  // rare: a chunk with more than 128 non-frequent entries
+            const uint32_t *words = P.blk + (size_t)__shfl_sync(FULL, my_off, jj) * 4;
+            for (uint32_t e0 = 128; e0 < nr; e0 += 32) {
+              const uint32_t e = e0 + lane;
+              probe(e < nr ? __ldg(words + e) : PAD_WORD, j, e);
+            }
+          }
+#pragma unroll
+          for (int bq = 0; bq < 4; bq++) cur[bq] = nxt[bq];
         }
       }
       if (threadIdx.x < B_BN) S.minB[as][threadIdx.x] = P.chunk_minB[c0 + threadIdx.x];
@@ -258,20 +313,48 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         if (th > 0.f) tq = P.jaccard ? th / PRUNE_SLACK : th * th * nq / (PRUNE_SLACK * PRUNE_SLACK);
       }
       asm volatile("bar.sync 1, 512;" ::: "memory");
-      // ---- epilogue: frequent part from TMEM + rare part from R -> bound -> seed / candidate ----
+      // ---- epilogue, thread = query, B_COLS chunk columns: rare part (R) + second-class part (bitmaps) + frequent
+      //      part (TMEM) -> bound -> seed / candidate ----
+      float x[B_COLS];
+      {
+        float *Rcol = &S.R[cs * B_COLS][qi];
+#pragma unroll
+        for (int j = 0; j < B_COLS; j++) { x[j] = Rcol[j * TILE_Q]; Rcol[j * TILE_Q] = 0.f; }
+      }
+      mbar_wait(&S.ubt_bar, (uint32_t)(it & 1));
+      const uint32_t bsh = (uint32_t)((cs * B_COLS) & 31), bword = (uint32_t)((cs * B_COLS) >> 5);
+      constexpr uint32_t CMASK = B_COLS == 32 ? 0xFFFFFFFFu : ((1u << B_COLS) - 1u);
+#pragma unroll 1
+      for (int i = 0; i < Q2CAP; i++) {
+        const uint2 f2 = S.q2[i][qi];
+        const float w2 = __uint_as_float(f2.y);
+        if (!__any_sync(FULL, w2 > 0.f)) break;  // the lists are filled from the front
+        const uint32_t row2 = f2.x & 0xFFFFu, tm1 = f2.x >> 16;
+        const uint32_t m = w2 > 0.f ? ((S.ubt[row2][0][bword] >> bsh) & CMASK) : 0u;
+        if (m) {
+#pragma unroll
+          for (int j = 0; j < B_COLS; j++)
+            if ((m >> j) & 1u) x[j] += w2;
+          const uint32_t mm = tm1 ? ((S.ubt[row2][1][bword] >> bsh) & CMASK) : 0u;  // tf >= 2 there: up to tfmax - 1 more
+          if (mm) {
+            const float wex = __fmul_ru(w2, (float)tm1);
+#pragma unroll
+            for (int j = 0; j < B_COLS; j++)
+              if ((mm >> j) & 1u) x[j] += wex;
+          }
+        }
+      }
       mbar_wait(&S.tmem_full[as], aphase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t v[32];
+      uint32_t v[B_COLS];
       {
-        const uint32_t taddr = tmem_base + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(as * B_BN + cs * 32);
+        static_assert(B_COLS == 16, "the TMEM load below reads 16 columns");
+        const uint32_t taddr = tmem_base + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(as * B_BN + cs * B_COLS);
         asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
             : "r"(taddr)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -279,23 +362,22 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.tmem_empty[as]);  // the values are in registers: the accumulator may be overwritten
-      const float *mb = &S.minB[as][cs * 32];
-      float *Rcol = &S.R[cs * 32][qi];
-      const int64_t cbase = c0 + cs * 32;
+      const float *mb = &S.minB[as][cs * B_COLS];
+      const int64_t cbase = c0 + cs * B_COLS;
       uint32_t mymask = 0;
 #pragma unroll
-      for (int j = 0; j < 32; j++) {
-        const float x = base + __uint_as_float(v[j]) + Rcol[j * TILE_Q];
-        Rcol[j * TILE_Q] = 0.f;
+      for (int j = 0; j < B_COLS; j++) {
+        const float xs = base + __uint_as_float(v[j]) + x[j];
         const bool c_ok = cbase + j < P.n_chunks;
-        const float den = P.jaccard ? (nq + mb[j] - x) : (mb[j] + corrS);
+        if (P.dbg_xs && q_in && c_ok) P.dbg_xs[(size_t)slot * P.dbg_stride + cbase + j] = xs;
+        const float den = P.jaccard ? (nq + mb[j] - xs) : (mb[j] + corrS);
         if (P.pass == 1) {
-          const float lhs = P.jaccard ? x : x * x;
+          const float lhs = P.jaccard ? xs : xs * xs;
           const bool sv = q_ok && c_ok && (tq <= 0.f || den <= 0.f || lhs >= tq * den);
           const uint32_t m = __ballot_sync(FULL, sv);
           if (lane == j) mymask = m;
         } else if (q_ok && c_ok) {
-          const float lhs = P.jaccard ? x : x * x;
+          const float lhs = P.jaccard ? xs : xs * xs;
           float metric = den > 0.f ? __fdividef(lhs, den) : INFINITY;
           if (metric > sm[B_SEEDS - 1]) {
             int cc = (int)(cbase + j);
@@ -340,7 +422,11 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
           }
         }
       }
-      asm volatile("bar.sync 1, 512;" ::: "memory");  // R is clean again before the next block's join
+      asm volatile("bar.sync 1, 512;" ::: "memory");  // R is clean again and every reader of this block's bitmaps is done
+      if (threadIdx.x == 0 && bk + 1 < blk_hi) {
+        mbar_expect_tx(&S.ubt_bar, sizeof(S.ubt));
+        bulk_copy_g2s(&S.ubt[0][0][0], P.ubt + (size_t)(bk + 1) * (sizeof(S.ubt) / 4), sizeof(S.ubt), &S.ubt_bar);
+      }
     }
     if (P.pass == 0) {
       if (q_in) {
@@ -366,7 +452,7 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
   __syncthreads();
   if (warp == B_WORKERS + 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -374,8 +460,8 @@ typedef CUresult (*PFN_encodeTiled_kv)(CUtensorMap *, CUtensorMapDataType, cuuin
                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// tensor map of a row-major fp16 matrix [rows][NF], box = 64 columns x 128 rows, 128-byte swizzle
-static int make_map_f16_nf(CUtensorMap *map, const void *base, int64_t rows) {
+// tensor map of a row-major fp16 matrix [rows][NF], box = 64 columns x box_rows rows, 128-byte swizzle
+static int make_map_f16_nf(CUtensorMap *map, const void *base, int64_t rows, int box_rows) {
   static PFN_encodeTiled_kv fn = nullptr;
   if (!fn) {
     void *p = nullptr;
@@ -386,7 +472,7 @@ static int make_map_f16_nf(CUtensorMap *map, const void *base, int64_t rows) {
   }
   cuuint64_t gdim[2] = {(cuuint64_t)NF, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)NF * 2};
-  cuuint32_t box[2] = {(cuuint32_t)B_BK, 128u};
+  cuuint32_t box[2] = {(cuuint32_t)B_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -73,6 +73,8 @@ struct kv_index {
   DevBuf<BlockInfo> d_binfo;
   DevBuf<__half> d_Uf;
   DevBuf<short> d_fslot;
+  DevBuf<unsigned short> d_fslot2;
+  DevBuf<uint32_t> d_ubt;
   CUtensorMap map_u;
   DevBuf<unsigned long long> d_ovf_keys;
   DevBuf<uint32_t> d_ovf_vals;
@@ -80,6 +82,7 @@ struct kv_index {
   int64_t blk_words = 0, n_chunks = 0, n_chunks_pad = 0, n_entries = 0, n_rare_entries = 0;
   std::vector<uint32_t> h_df, h_tfmax;
   std::vector<short> h_fslot;
+  std::vector<unsigned short> h_fslot2;
   std::vector<uint8_t> h_univ;
   std::vector<uint32_t> h_utf;
   int64_t n_univ = 0;
@@ -102,6 +105,7 @@ struct kv_index {
   DevBuf<uint8_t> d_flags;
   DevBuf<float> d_qconst;     // 7 * n_q: nq, dotU, corrU, dotS, corrS, dotX, -inf
   DevBuf<unsigned char> d_qtab, d_rtab;
+  DevBuf<uint2> d_q2list;
   DevBuf<__half> d_Wf;
   CUtensorMap map_w;
   DevBuf<int> d_gthr;
@@ -136,6 +140,7 @@ struct kv_index {
   std::vector<uint32_t> irr_ids, irr_tf;
   std::vector<double> irr_oov;
 
+  float *dbg_xs = nullptr;  // test hook (kv_debug_bound_numerators)
   float last_ms[4] = {0, 0, 0, 0};
   float last_kernel_ms[5] = {0, 0, 0, 0, 0};  // bound pass 0, seed scan, bound pass 1, scan, merge
   float last_score_ms = 0;
@@ -250,7 +255,8 @@ void kv_index_destroy(kv_index *ix) {
   ix->d_df.release(); ix->d_cnt.release(); ix->d_tfmin.release(); ix->d_tfmax.release(); ix->d_utf.release();
   ix->d_a64.release(); ix->d_d64.release(); ix->d_bb64.release(); ix->d_B64.release();
   ix->d_B32.release(); ix->d_cminB.release(); ix->d_univ.release(); ix->d_perm.release(); ix->d_invperm.release();
-  ix->d_blk.release(); ix->d_binfo.release(); ix->d_Uf.release(); ix->d_fslot.release();
+  ix->d_blk.release(); ix->d_binfo.release(); ix->d_Uf.release(); ix->d_fslot.release(); ix->d_fslot2.release(); ix->d_ubt.release();
+  ix->d_q2list.release();
   ix->d_ovf_keys.release(); ix->d_ovf_vals.release();
   ix->d_rq_indptr.release(); ix->d_rq_ids.release(); ix->d_rq_tf.release(); ix->d_rq_const.release(); ix->d_rq_out.release();
   ix->d_rq_rows.release();
@@ -489,8 +495,11 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
     if (same) {
       if ((int64_t)ix->h_fslot.size() < Vz) {  // new feature ids (rows of another segment): none of them is a dense column
         ix->h_fslot.resize((size_t)Vz, (short)-1);
+        ix->h_fslot2.resize((size_t)Vz, (unsigned short)0xFFFF);
         KV_CUDA(ix->d_fslot.ensure(Vz));
+        KV_CUDA(ix->d_fslot2.ensure(Vz));
         KV_CUDA(cudaMemcpyAsync(ix->d_fslot.p, ix->h_fslot.data(), (size_t)Vz * sizeof(short), cudaMemcpyHostToDevice, s));
+        KV_CUDA(cudaMemcpyAsync(ix->d_fslot2.p, ix->h_fslot2.data(), (size_t)Vz * sizeof(short), cudaMemcpyHostToDevice, s));
       }
       rownorm_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(ix->indptr.p, ix->ids.p, ix->tf.p, ix->d_perm.p, n,
                                                                       ix->d_bb64.p, ix->d_B64.p, ix->d_B32.p);
@@ -540,7 +549,12 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
   KV_CUDA(cudaMemcpyAsync(ix->d_binfo.p, L.binfo.data(), (size_t)L.n_chunks_pad * sizeof(BlockInfo), cudaMemcpyHostToDevice, s));
   KV_CUDA(cudaMemcpyAsync(ix->d_Uf.p, L.Uf.data(), (size_t)L.n_chunks_pad * NF * sizeof(__half), cudaMemcpyHostToDevice, s));
   ix->h_fslot = L.fslot;
+  ix->h_fslot2 = L.fslot2;
   KV_CUDA(cudaMemcpyAsync(ix->d_fslot.p, ix->h_fslot.data(), (size_t)Vz * sizeof(short), cudaMemcpyHostToDevice, s));
+  KV_CUDA(ix->d_fslot2.ensure(Vz));
+  KV_CUDA(cudaMemcpyAsync(ix->d_fslot2.p, ix->h_fslot2.data(), (size_t)Vz * sizeof(short), cudaMemcpyHostToDevice, s));
+  KV_CUDA(ix->d_ubt.ensure((int64_t)L.Ubt.size()));
+  KV_CUDA(cudaMemcpyAsync(ix->d_ubt.p, L.Ubt.data(), L.Ubt.size() * 4, cudaMemcpyHostToDevice, s));
   ix->n_ovf = (int)L.ovf.size();
   KV_CUDA(ix->d_ovf_keys.ensure(std::max(1, ix->n_ovf))); KV_CUDA(ix->d_ovf_vals.ensure(std::max(1, ix->n_ovf)));
   std::vector<unsigned long long> ok((size_t)ix->n_ovf);
@@ -552,7 +566,7 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
   }
   KV_CUDA(cudaStreamSynchronize(s));  // the staging vectors go out of scope
   {
-    int rc = make_map_f16_nf(&ix->map_u, ix->d_Uf.p, L.n_chunks_pad);
+    int rc = make_map_f16_nf(&ix->map_u, ix->d_Uf.p, L.n_chunks_pad, B_BN);
     if (rc != KV_OK) return rc;
   }
   ix->V = V;
@@ -754,6 +768,7 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
   KV_CUDA(ix->d_qtab.ensure(n_q * (int64_t)QTAB_BYTES));
   KV_CUDA(ix->d_rtab.ensure(n_tiles * (int64_t)RTAB_BYTES));
   KV_CUDA(ix->d_Wf.ensure(n_q_pad * NF));
+  KV_CUDA(ix->d_q2list.ensure(n_q_pad * Q2CAP));
   KV_CUDA(cudaEventRecord(ix->ev[0], s));
   KV_CUDA(cudaMemcpyAsync(ix->d_q_indptr.p, ix->h_q_indptr.p, (size_t)(n_q + 1) * 8, cudaMemcpyHostToDevice, s));
   if (nnz) {
@@ -771,14 +786,16 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
   P.qperm = ix->d_qperm.p; P.flags = ix->d_flags.p;
   P.n_q = n_q; P.V = ix->V; P.n_total = ix->n_total;
   P.a64 = ix->d_a64.p; P.d64 = ix->d_d64.p; P.univ = ix->d_univ.p; P.utf = ix->d_utf.p; P.tfmax = ix->d_tfmax.p;
-  P.fslot = ix->d_fslot.p; P.jaccard = ix->jaccard; P.corpus_fit = ix->corpus_fit;
+  P.q2cap = Q2CAP;
+  if (const char *e = getenv("KAKVEDA_B200_Q2CAP")) P.q2cap = std::max(0, std::min(Q2CAP, atoi(e)));
+  P.fslot = ix->d_fslot.p; P.fslot2 = ix->d_fslot2.p; P.q2list = ix->d_q2list.p; P.jaccard = ix->jaccard; P.corpus_fit = ix->corpus_fit;
   P.q_nq = ix->d_qconst.p; P.q_dotU = P.q_nq + n_q; P.q_corrU = P.q_nq + 2 * n_q; P.q_dotS = P.q_nq + 3 * n_q;
   P.q_corrS = P.q_nq + 4 * n_q; P.q_dotX = P.q_nq + 5 * n_q;
   P.qtab = ix->d_qtab.p; P.Wf = ix->d_Wf.p; P.rtab = ix->d_rtab.p;
   prep_queries_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, s>>>(P);
   KV_CUDA(cudaGetLastError());
   static bool attr_set[64] = {false};
-  const int prep_smem = RT_SLOTS * 4 * 6;
+  const int prep_smem = RT_SLOTS * 4 * 6 + RT_BITMAP_BITS / 8;
   if (!attr_set[ix->device & 63]) {
     KV_CUDA(cudaFuncSetAttribute(prep_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
     attr_set[ix->device & 63] = true;
@@ -786,7 +803,7 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
   prep_tiles_kernel<<<(unsigned)n_tiles, TILE_Q, prep_smem, s>>>(P);
   KV_CUDA(cudaGetLastError());
   {
-    int rc = make_map_f16_nf(&ix->map_w, ix->d_Wf.p, n_q_pad);
+    int rc = make_map_f16_nf(&ix->map_w, ix->d_Wf.p, n_q_pad, TILE_Q);
     if (rc != KV_OK) return rc;
   }
   KV_CUDA(cudaStreamSynchronize(s));  // the pinned staging buffers may be rewritten by the next call
@@ -811,10 +828,13 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
   // Pruned mode: bound pass 0 -> seed scan -> bound pass 1 -> scan of the candidates.  Exhaustive mode (small
   // indexes, KAKVEDA_B200_NO_PRUNE=1): every chunk is a candidate of every query.
   const char *env = getenv("KAKVEDA_B200_NO_PRUNE");
-  const int prune = (env && env[0] == '1') ? 0 : (ix->n_chunks >= 4 * B_BN ? 1 : 0);
+  const int prune = (env && env[0] == '1') ? 0 : (ix->n_chunks >= 512 ? 1 : 0);
   int64_t n_bsplits, n_ssplits;
   if (prune) {
     n_bsplits = std::max<int64_t>(1, std::min<int64_t>((ix->sm_count + n_tiles - 1) / n_tiles, n_blocks));
+    // a bound CTA keeps the page table of its four candidate lists in shared memory: bound the chunks per row range
+    while (n_bsplits < n_blocks && bound_smem_bytes((int)((((n_blocks + n_bsplits - 1) / n_bsplits + 1) * B_BN) / PAGE_RECS + 2)) > 232448)
+      n_bsplits++;
     n_ssplits = std::max<int64_t>(1, std::min<int64_t>((4LL * ix->sm_count + n_groups * n_bsplits - 1) / (n_groups * n_bsplits), 8));
   } else {
     n_bsplits = std::max<int64_t>(1, std::min<int64_t>((8LL * ix->sm_count + n_groups - 1) / n_groups,
@@ -839,9 +859,10 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
   if (prune) {
     KV_CUDA(ix->d_seeds.ensure(n_q * n_seed));
     KV_CUDA(ix->d_direct.ensure(n_groups * GROUP_Q * n_seed));
-    KV_CUDA(ix->d_list_count.ensure(n_groups + n_lists));
-    KV_CUDA(ix->d_list_pages.ensure(n_lists * max_pages));
-    const int64_t want_pages = std::min<int64_t>(n_lists * max_pages, 131072 + n_lists);
+    // the bound kernel writes the lists of whole tiles (4 groups each), including the groups past the last query
+    KV_CUDA(ix->d_list_count.ensure(n_groups + n_tiles * 4 * n_bsplits));
+    KV_CUDA(ix->d_list_pages.ensure(n_tiles * 4 * n_bsplits * max_pages));
+    const int64_t want_pages = std::min<int64_t>(n_lists * max_pages, 524288 + n_lists);  // up to 4 GiB of records
     if (want_pages > ix->pool_pages) {
       KV_CUDA(ix->d_pool.ensure(want_pages * PAGE_RECS));
       ix->pool_pages = want_pages;
@@ -886,13 +907,14 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
       BoundParams BP;
       BP.blk = ix->d_blk.p; BP.binfo = ix->d_binfo.p; BP.chunk_minB = ix->d_cminB.p;
       BP.ovf_keys = ix->d_ovf_keys.p; BP.ovf_vals = ix->d_ovf_vals.p; BP.n_ovf = ix->n_ovf;
-      BP.n_chunks = ix->n_chunks; BP.n_q = n_q; BP.rtab = ix->d_rtab.p;
+      BP.n_chunks = ix->n_chunks; BP.n_q = n_q; BP.rtab = ix->d_rtab.p; BP.q2list = ix->d_q2list.p; BP.ubt = ix->d_ubt.p;
       BP.q_nq = qc; BP.q_dotS = qc + 3 * n_q; BP.q_corrS = qc + 4 * n_q; BP.q_dotX = qc + 5 * n_q;
       BP.gthr = ix->d_gthr.p; BP.n_bsplits = (int)n_bsplits; BP.jaccard = ix->jaccard;
       BP.seeds = ix->d_seeds.p;
       BP.list_count = ix->d_list_count.p + n_groups; BP.list_pages = ix->d_list_pages.p; BP.max_pages = max_pages;
       BP.pool = ix->d_pool.p; BP.pool_next = ix->d_pool_ctl.p; BP.pool_pages = (unsigned int)ix->pool_pages;
       BP.overflow = (int *)(ix->d_pool_ctl.p + 1); BP.stats = ix->d_stats.p;
+      BP.dbg_xs = ix->dbg_xs; BP.dbg_stride = ix->n_chunks_pad;
       const size_t b_smem = bound_smem_bytes(max_pages);
       const dim3 bgrid((unsigned)n_tiles, (unsigned)n_bsplits);
       // pass 0: seeds
@@ -1210,6 +1232,35 @@ int kv_merge_topk_device_on(int device, const void *d_scores_in, const void *d_r
   KV_CUDA(cudaGetLastError());
   if (sync) KV_CUDA(cudaStreamSynchronize(s));
   return KV_OK;
+}
+
+// Test hook: the numerators of the chunk bounds the bound kernel forms for the resident batch (sorted query slot i =
+// query order[i]), [n_q][n_chunks] floats on the host, plus the slot -> query map.  Small indexes only.
+int kv_debug_bound_numerators(kv_index *ix, int k, float *out, int32_t *slot_query) {
+  if (!ix || !out || !slot_query) return kv_fail(KV_ERR_INVALID, "kv_debug_bound_numerators: bad arguments");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (!ix->batch_valid) return kv_fail(KV_ERR_STATE, "kv_debug_bound_numerators: no query batch uploaded");
+  KV_CUDA(cudaSetDevice(ix->device));
+  const int64_t n_q = ix->batch_q, stride = ix->n_chunks_pad;
+  DevBuf<float> xs;
+  KV_CUDA(xs.ensure(n_q * stride));
+  KV_CUDA(cudaMemset(xs.p, 0, (size_t)(n_q * stride) * 4));
+  KV_CUDA(ix->d_out_s.ensure(n_q * k)); KV_CUDA(ix->d_out_r.ensure(n_q * k));
+  ix->dbg_xs = xs.p;
+  int rc = run_batch(ix, k, ix->d_out_s.p, ix->d_out_r.p);
+  ix->dbg_xs = nullptr;
+  if (rc == KV_OK) {
+    KV_CUDA(cudaEventRecord(ix->ev[4], ix->stream));
+    KV_CUDA(cudaStreamSynchronize(ix->stream));
+    std::vector<float> h((size_t)(n_q * stride));
+    KV_CUDA(cudaMemcpy(h.data(), xs.p, h.size() * 4, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n_q; i++) {
+      memcpy(out + i * ix->n_chunks, h.data() + i * stride, (size_t)ix->n_chunks * 4);
+      slot_query[i] = ix->h_qperm.p[i];
+    }
+  }
+  xs.release();
+  return rc;
 }
 
 int kv_index_last_timing(const kv_index *ix, float ms[4]) {

@@ -39,7 +39,9 @@
 namespace kvk {
 
 constexpr int CHUNK_ROWS = 32;
-constexpr int NF = 256;  // features evaluated densely by the bound kernel
+constexpr int NF = 256;   // features evaluated densely (tensor cores) by the bound kernel
+constexpr int NF2 = 1024; // the next most frequent features: per 128-chunk block two transposed bitmaps [NF2][tf >= 1, tf >= 2][128 bits]
+constexpr int Q2CAP = 32; // features of that class a query keeps in its own list (further ones go to the tile's rare table)
 constexpr uint32_t FID_BITS = 26;
 constexpr uint32_t FID_MASK = (1u << FID_BITS) - 1;
 constexpr uint32_t FID_NONE = FID_MASK;  // sentinel feature id (never in a table)
@@ -53,10 +55,11 @@ constexpr int QFEATS = 64;   // features a query may hold in it (more: float64 f
 constexpr int QTAB_BYTES = QKEYS * 4 + QFEATS * 16;
 constexpr int GROUP_Q = 32;  // queries per scan group (one candidate list, one K1b-S CTA)
 constexpr int TILE_Q = 128;  // queries per bound tile (4 groups; the M of the bound GEMM)
-constexpr int RT_SLOTS = 2048;  // rare-feature table of a bound tile
-constexpr int RT_CAP = 1500;    // features it accepts (the rest enters the bounds as per-query constants)
-constexpr int RT_MULTI = 512;   // of those, features shared by several queries of the tile (128-bit membership masks)
-constexpr int RTAB_BYTES = RT_SLOTS * 12 + RT_MULTI * 16;
+constexpr int RT_SLOTS = 2048;  // rare-feature table of a bound tile: keys[RT_SLOTS], then (fp16 weight | query info << 16)
+constexpr int RT_CAP = 1400;    // features it accepts (the rest enters the bounds as per-query constants)
+constexpr int RT_MULTI = 256;   // of those, features shared by several queries of the tile (128-bit membership masks)
+constexpr int RT_BITMAP_BITS = 1 << 16;  // presence bitmap probed before the table (1 shared-memory load rejects ~98 % of the entries)
+constexpr int RTAB_BYTES = RT_SLOTS * 8 + RT_MULTI * 16 + RT_BITMAP_BITS / 8;
 constexpr float PRUNE_SLACK = 1.0005f;  // bounds: fp16 round-up of weights, fp32 tensor-core sums, constants rounded outwards
 constexpr float FILTER_SLACK = 0.999996f;
 constexpr int PAGE_RECS = 1024;  // candidate records per pool page
@@ -302,11 +305,14 @@ struct PrepParams {
   const uint8_t *univ;
   const uint32_t *utf, *tfmax;
   const short *fslot;       // feature -> column of the dense matrices, -1: not a frequent feature
+  const unsigned short *fslot2;  // feature -> bit row of the block bitmaps (second class), 0xFFFF: none
   int jaccard, corpus_fit;
+  int q2cap;                // second-class features a query lists itself (<= Q2CAP)
   float *q_nq, *q_dotU, *q_corrU, *q_dotS, *q_corrS, *q_dotX;  // [n_q] by sorted slot
   unsigned char *qtab;      // [n_q][QTAB_BYTES]
   __half *Wf;               // [n_q_pad][NF], zeroed by the caller
   unsigned char *rtab;      // [n_tiles][RTAB_BYTES]
+  uint2 *q2list;            // [n_tiles][Q2CAP][TILE_Q] (bit row | (tfmax(t) - 1) << 16, weight tf_q a(t) as float bits)
 };
 
 __global__ void prep_queries_kernel(PrepParams P) {
@@ -319,8 +325,10 @@ __global__ void prep_queries_kernel(PrepParams P) {
   const double idf0 = P.jaccard ? 1.0 : (P.corpus_fit ? 0.0 : log((double)(P.n_total + 2) / 2.0) + 1.0);
   double nq = (P.q_oov ? P.q_oov[q] : 0.0) * idf0 * idf0;
   double dotU = 0.0, corrU = 0.0, corrS = 0.0;
-  int cnt = 0;
+  int cnt = 0, c2 = 0;
   const bool regular = P.flags[i] == 0;
+  uint2 *q2 = P.q2list + ((size_t)(i / TILE_Q) * Q2CAP) * TILE_Q + (i % TILE_Q);
+  for (int j = 0; j < Q2CAP; j++) q2[(size_t)j * TILE_Q] = make_uint2(0u, 0u);
   for (int64_t p = P.q_indptr[q]; p < P.q_indptr[q + 1]; p++) {
     const uint32_t t = P.q_ids[p];
     const double f = (double)P.q_tf[p];
@@ -344,7 +352,13 @@ __global__ void prep_queries_kernel(PrepParams P) {
       qf.tfq = P.q_tf[p];
       feats[cnt++] = qf;
       const int fs = P.fslot[t];
-      if (fs >= 0) P.Wf[(size_t)i * NF + fs] = __float2half_ru(__double2float_ru(f * a));
+      if (fs >= 0) {
+        P.Wf[(size_t)i * NF + fs] = __float2half_ru(__double2float_ru(f * a));
+      } else if (P.fslot2[t] != 0xFFFFu && c2 < P.q2cap) {
+        const uint32_t tm1 = min(P.tfmax[t] - 1u, 65535u);  // weight of the 'tf >= 2' plane: (largest tf - 1) more times
+        q2[(size_t)c2 * TILE_Q] = make_uint2((uint32_t)P.fslot2[t] | (tm1 << 16), __float_as_uint(__double2float_ru(f * a * (1.0 + 1e-6))));
+        c2++;
+      }
     }
   }
   P.q_nq[i] = regular ? (float)nq : 0.f;  // nq == 0 switches the query off in the kernels
@@ -356,12 +370,16 @@ __global__ void prep_queries_kernel(PrepParams P) {
 }
 
 // one CTA (128 threads = the tile's queries) per tile: the tile's rare-feature table.  Slot = (feature, largest
-// tf_q a(t) over the tile's queries holding it, the query or the index of a 128-bit membership mask).
+// tf_q a(t) over the tile's queries holding it as fp16 rounded up, the query or the index of a 128-bit membership mask),
+// plus a presence bitmap over a second hash of the feature id.
+__device__ __forceinline__ uint32_t rt_bit(uint32_t fid) { return (fid * 0x85EBCA6Bu) >> 16; }  // 16 bits
+
 __global__ void __launch_bounds__(TILE_Q) prep_tiles_kernel(PrepParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t *s_keys = (uint32_t *)smem_raw;          // [RT_SLOTS]
   uint32_t *s_w = s_keys + RT_SLOTS;                 // float bits
   uint32_t *s_m = s_w + RT_SLOTS;                    // [RT_SLOTS][4]
+  uint32_t *s_bm = s_m + 4 * RT_SLOTS;               // [RT_BITMAP_BITS / 32]
   __shared__ int s_cnt, s_multi;
   __shared__ float s_dotX[TILE_Q];
   const int tile = blockIdx.x, qi = threadIdx.x;
@@ -370,19 +388,21 @@ __global__ void __launch_bounds__(TILE_Q) prep_tiles_kernel(PrepParams P) {
     s_w[j] = 0;
     s_m[4 * j] = s_m[4 * j + 1] = s_m[4 * j + 2] = s_m[4 * j + 3] = 0;
   }
+  for (int j = qi; j < RT_BITMAP_BITS / 32; j += TILE_Q) s_bm[j] = 0;
   if (qi == 0) { s_cnt = 0; s_multi = 0; }
   s_dotX[qi] = 0.f;
   __syncthreads();
   const int64_t i = (int64_t)tile * TILE_Q + qi;
   if (i < P.n_q && P.flags[i] == 0) {
     const int q = P.qperm[i];
-    int cnt = 0;
+    int cnt = 0, c2 = 0;
     for (int64_t p = P.q_indptr[q]; p < P.q_indptr[q + 1]; p++) {
       const uint32_t t = P.q_ids[p];
       if ((int64_t)t >= P.V || P.univ[t]) continue;
       if (cnt++ >= QFEATS) break;
       if (P.fslot[t] >= 0) continue;
-      const float w = __double2float_ru((double)P.q_tf[p] * P.a64[t]);
+      if (P.fslot2[t] != 0xFFFFu && c2 < P.q2cap) { c2++; continue; }  // in the query's own second-class list
+      const float w = __half2float(__float2half_ru(__double2float_ru((double)P.q_tf[p] * P.a64[t])));
       uint32_t h = hash_fid(t, 11);
       bool placed = false;
       for (int probes = 0; probes < RT_SLOTS; probes++) {
@@ -398,6 +418,8 @@ __global__ void __launch_bounds__(TILE_Q) prep_tiles_kernel(PrepParams P) {
       if (placed) {
         atomicMax(&s_w[h], __float_as_uint(w));
         atomicOr(&s_m[4 * h + (qi >> 5)], 1u << (qi & 31));
+        const uint32_t b = rt_bit(t);
+        atomicOr(&s_bm[b >> 5], 1u << (b & 31));
       } else {
         s_dotX[qi] += __fmul_ru(w, (float)P.tfmax[t]);  // assumed present everywhere with its largest tf
       }
@@ -405,12 +427,12 @@ __global__ void __launch_bounds__(TILE_Q) prep_tiles_kernel(PrepParams P) {
   }
   __syncthreads();
   uint32_t *o_keys = (uint32_t *)(P.rtab + (size_t)tile * RTAB_BYTES);
-  float *o_w = (float *)(o_keys + RT_SLOTS);
-  uint32_t *o_q = (uint32_t *)(o_w + RT_SLOTS);
-  uint32_t *o_multi = o_q + RT_SLOTS;  // [RT_MULTI][4]
+  uint32_t *o_wq = o_keys + RT_SLOTS;      // fp16 weight | query info << 16
+  uint32_t *o_multi = o_wq + RT_SLOTS;     // [RT_MULTI][4]
+  uint32_t *o_bm = o_multi + 4 * RT_MULTI;
   for (int j = qi; j < RT_SLOTS; j += TILE_Q) {
     const uint32_t k = s_keys[j];
-    uint32_t qinfo = 0xFFFFFFFFu;
+    uint32_t qinfo = 0xFFFFu;
     float w = __uint_as_float(s_w[j]);
     if (k != KEY_EMPTY) {
       const uint32_t m0 = s_m[4 * j], m1 = s_m[4 * j + 1], m2 = s_m[4 * j + 2], m3 = s_m[4 * j + 3];
@@ -421,7 +443,7 @@ __global__ void __launch_bounds__(TILE_Q) prep_tiles_kernel(PrepParams P) {
         const int mi = atomicAdd(&s_multi, 1);
         if (mi < RT_MULTI) {
           o_multi[4 * mi] = m0; o_multi[4 * mi + 1] = m1; o_multi[4 * mi + 2] = m2; o_multi[4 * mi + 3] = m3;
-          qinfo = 0x80000000u | (uint32_t)mi;
+          qinfo = 0x8000u | (uint32_t)mi;
         } else {  // no mask slot left: constant for every member query (the key stays: probe chains must not break)
           const float x = __fmul_ru(w, (float)P.tfmax[k]);
           const uint32_t mm[4] = {m0, m1, m2, m3};
@@ -432,9 +454,9 @@ __global__ void __launch_bounds__(TILE_Q) prep_tiles_kernel(PrepParams P) {
       }
     }
     o_keys[j] = k;
-    o_w[j] = w;
-    o_q[j] = qinfo;
+    o_wq[j] = (uint32_t)__half_as_ushort(__float2half_ru(w)) | (qinfo << 16);
   }
+  for (int j = qi; j < RT_BITMAP_BITS / 32; j += TILE_Q) o_bm[j] = s_bm[j];
   __syncthreads();
   if (i < P.n_q) P.q_dotX[i] = s_dotX[qi] * 1.00001f;
 }
@@ -726,7 +748,11 @@ __global__ void __launch_bounds__(S_WARPS * 32, 2) tfidf_scan_kernel(ScanParams 
           }
           __syncwarp();
         }
-        // fused epilogue: pre-test without division, exact score for survivors, insertion under the query's lock
+        // fused epilogue: pre-test without division, exact score for survivors; the warp then takes the query's lock
+        // ONCE and inserts all surviving rows of the chunk into the sorted list held one entry per lane (k <= 32)
+        float sc = -INFINITY;
+        int row = 0x7fffffff;
+        bool cand = false;
         if (lane < rows) {
           const float dot = s_dotU[qi] + __ull2float_rn(acc_w) * (1.f / 4294967296.f);
           const float corr = s_corrU[qi] - __ull2float_rn(acc_c) * (1.f / 16777216.f);
@@ -739,45 +765,53 @@ __global__ void __launch_bounds__(S_WARPS * 32, 2) tfidf_scan_kernel(ScanParams 
             const int kr = *(volatile int *)&s_lrow[qi * k + k - 1];
             if (ks > filt || (ks == filt && kr < krow)) { filt = ks; krow = kr; }
           }
-          bool pass;
+          bool pass = true;
           if (filt > 0.f) {
             const float fq = P.jaccard ? filt * FILTER_SLACK : filt * filt * nq * FILTER_SLACK;
             const float lhs = P.jaccard ? dot : dot * dot;
             const float rhs = fq * (P.jaccard ? (nq + t - dot) : t);
             pass = lhs >= rhs;
-          } else {
-            pass = true;
           }
           if (pass) {
-            const float s = pair_score(P.jaccard, dot, nq, t);
-            const int row = P.perm[pos0 + lane];
-            if (row != s_excl[qi] && (s > filt || (s == filt && row < krow))) {
-              while (atomicCAS(&s_lock[qi], 0, 1) != 0) {}
-              __threadfence_block();
-              float *ls = s_lscore + qi * k;
-              int *lr = s_lrow + qi * k;
-              int cnt = s_cnt[qi];
-              int pos = -1;
-              if (cnt < k) {
-                pos = cnt;
-                s_cnt[qi] = ++cnt;
-              } else if (s > ls[k - 1] || (s == ls[k - 1] && row < lr[k - 1])) {
-                pos = k - 1;
-              }
-              if (pos >= 0) {
-                while (pos > 0 && (ls[pos - 1] < s || (ls[pos - 1] == s && lr[pos - 1] > row))) {
-                  ls[pos] = ls[pos - 1];
-                  lr[pos] = lr[pos - 1];
-                  pos--;
-                }
-                ls[pos] = s;
-                lr[pos] = row;
-                if (cnt == k) publish_threshold(q0 + qi, ls[k - 1]);
-              }
-              __threadfence_block();
-              atomicExch(&s_lock[qi], 0);
+            sc = pair_score(P.jaccard, dot, nq, t);
+            row = P.perm[pos0 + lane];
+            cand = row != s_excl[qi] && (sc > filt || (sc == filt && row < krow));
+          }
+        }
+        const uint32_t cm = __ballot_sync(FULL, cand);
+        if (cm) {
+          if (lane == 0) while (atomicCAS(&s_lock[qi], 0, 1) != 0) {}
+          __syncwarp();
+          __threadfence_block();
+          int cnt = *(volatile int *)&s_cnt[qi];
+          float ls = lane < k ? *(volatile float *)&s_lscore[qi * k + lane] : -INFINITY;   // unused slots hold (-inf, INT_MAX)
+          int lr = lane < k ? *(volatile int *)&s_lrow[qi * k + lane] : 0x7fffffff;
+          bool changed = false;
+          for (uint32_t m = cm; m; m &= m - 1) {
+            const int j = __ffs(m) - 1;
+            const float ns = __shfl_sync(FULL, sc, j);
+            const int nr = __shfl_sync(FULL, row, j);
+            // entries that stay ahead of the new one form a prefix of the sorted list
+            const bool ahead = lane < k && (ls > ns || (ls == ns && lr < nr));
+            const int pos = __popc(__ballot_sync(FULL, ahead));
+            const float us = __shfl_up_sync(FULL, ls, 1);
+            const int ur = __shfl_up_sync(FULL, lr, 1);
+            if (pos < k) {
+              if (lane > pos) { ls = us; lr = ur; }
+              else if (lane == pos) { ls = ns; lr = nr; }
+              if (cnt < k) cnt++;
+              changed = true;
             }
           }
+          if (changed) {
+            if (lane < k) { s_lscore[qi * k + lane] = ls; s_lrow[qi * k + lane] = lr; }
+            if (lane == 0) s_cnt[qi] = cnt;
+            const float ks = __shfl_sync(FULL, ls, k - 1);
+            if (lane == 0 && cnt == k) publish_threshold(q0 + qi, ks);
+          }
+          __threadfence_block();
+          __syncwarp();
+          if (lane == 0) atomicExch(&s_lock[qi], 0);
         }
         __syncwarp();
       }

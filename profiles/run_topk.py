@@ -1,4 +1,4 @@
-"""Driver for ncu captures of K1b (tfidf_topk_kernel): `python profiles/run_topk.py ROWS QUERIES [K]`."""
+"""Driver for ncu captures of K1b (tfidf_bound_kernel / tfidf_scan_kernel): `python profiles/run_topk.py ROWS QUERIES [K]`."""
 import sys
 from pathlib import Path
 
@@ -21,6 +21,6 @@ for _ in range(3):
     s, r = sh.topk_resident(k)
     torch.cuda.synchronize()
     lay = sh.index.layout()
-    print("ms", sh.index.last_timing_ms(), {x: lay[x] for x in ("last_tiles", "last_splits", "chunks_scanned", "chunks_pruned",
-                                                               "cycles_bound_pass", "cycles_bound_requery", "cycles_scan")})
+    print("ms", sh.index.last_timing_ms(), "kernels", sh.index.last_kernel_ms(),
+          {x: lay[x] for x in ("last_tiles", "last_splits", "pairs_scored", "pairs_passed_bound", "records_written")})
 print("checksum", int(r.sum().item()))

@@ -84,6 +84,8 @@ static void check_case(int64_t n, int64_t V, int n_univ, unsigned seed, bool big
   CHECK(L1.ovf == L4.ovf && L1.fslot == L4.fslot, "threaded build: overflow table / columns differ");
   CHECK(memcmp(L1.binfo.data(), L4.binfo.data(), L1.binfo.size() * sizeof(BlockInfo)) == 0, "threaded build: directory differs");
   CHECK(memcmp(L1.Uf.data(), L4.Uf.data(), L1.Uf.size() * sizeof(__half)) == 0, "threaded build: dense matrix differs");
+  CHECK(L1.fslot2 == L4.fslot2 && L1.Ubt == L4.Ubt, "threaded build: second-class bitmaps differ");
+  CHECK((int64_t)L1.Ubt.size() == L1.n_chunks_pad / 64 * NF2 * 4, "bitmap size");
   CHECK(L1.n_chunks == (n + 31) / 32 && L1.n_chunks_pad % 128 == 0 && L1.n_chunks_pad >= L1.n_chunks, "chunk counts");
   // decode
   std::vector<std::map<uint32_t, uint32_t>> got((size_t)n);
@@ -96,6 +98,7 @@ static void check_case(int64_t n, int64_t V, int n_univ, unsigned seed, bool big
     const uint32_t valid = rows == 32 ? 0xFFFFFFFFu : ((1u << rows) - 1u);
     unsigned long long prev = 0;
     std::map<int, uint32_t> umax;
+    std::set<int> have2, have2b;
     for (int e = 0; e < E4; e++) {
       if (e >= E) { CHECK(words[e] == PAD_WORD && masks[e] == 0, "padding entry"); continue; }
       const uint32_t w = words[e], f = (w >> 5) & FID_MASK;
@@ -110,12 +113,19 @@ static void check_case(int64_t n, int64_t V, int n_univ, unsigned seed, bool big
       CHECK(masks[e] != 0 && (masks[e] & ~valid) == 0, "mask of entry");
       CHECK(((w & W_ALL) != 0) == (masks[e] == valid), "W_ALL flag");
       if (!rare) umax[L1.fslot[f]] = std::max(umax[L1.fslot[f]], t);
+      CHECK(!(L1.fslot[f] >= 0 && L1.fslot2[f] != 0xFFFF), "feature in both classes");
+      if (L1.fslot2[f] != 0xFFFF) { have2.insert((int)L1.fslot2[f]); if (t >= 2) have2b.insert((int)L1.fslot2[f]); }
       for (int r = 0; r < rows; r++)
         if ((masks[e] >> r) & 1u) {
           auto &row = got[(size_t)c.perm[(size_t)(ch * 32 + r)]];
           CHECK(row.find(f) == row.end(), "feature twice in a row");
           row[f] = t;
         }
+    }
+    for (int s2 = 0; s2 < NF2; s2++) {
+      const bool bit = (L1.Ubt[((size_t)(ch >> 6) * NF2 + s2) * 4 + ((ch & 63) >> 5)] >> (ch & 31)) & 1u;
+      const bool bit2 = (L1.Ubt[((size_t)(ch >> 6) * NF2 + s2) * 4 + 2 + ((ch & 63) >> 5)] >> (ch & 31)) & 1u;
+      CHECK(bit == (have2.count(s2) != 0) && bit2 == (have2b.count(s2) != 0), "second-class bits of chunk %lld, row %d", (long long)ch, s2);
     }
     for (int s = 0; s < NF; s++) {
       const float u = __half2float(L1.Uf[(size_t)ch * NF + s]);
