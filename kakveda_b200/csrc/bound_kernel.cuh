@@ -40,6 +40,7 @@ constexpr int B_THREADS = (B_WORKERS + 2) * 32;
 constexpr int B_COLS = B_BN / 4;             // chunk columns per epilogue thread (four threads serve a query)
 constexpr int B_SEEDS = 4;                   // seeds per worker thread
 constexpr int B_SEEDS_PER_QUERY = 4 * B_SEEDS;
+constexpr float UBQ_SCALE = 250.f;           // 8-bit bound code = ceil(bound * 250), saturating at 255 (bounds reach ~1.001)
 
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
   asm volatile(
@@ -73,6 +74,25 @@ __device__ __forceinline__ void umma_f16_128(uint32_t tmem_d, uint64_t da, uint6
       "l"(da), "l"(db), "r"(B_IDESC), "r"(accumulate)
       : "memory");
 }
+// wait of a single-lane role (TMA producer, MMA issuer): polls with a pause, so that the spinning lane does not
+// take issue slots from the worker warps sharing its scheduler
+__device__ __forceinline__ void mbar_wait_idle(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
+}
+
 __device__ __forceinline__ void umma_commit_1(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
@@ -102,6 +122,8 @@ struct BoundParams {
   unsigned int pool_pages;  // capacity
   int *overflow;            // set when the pool ran out (the batch is rerun with a larger pool)
   unsigned long long *stats;  // [2] surviving (query, chunk) pairs, [3] candidate records
+  unsigned char *ubq;         // pass 0, optional: every bound as an 8-bit code (rounded up), [n_q][ubq_stride]
+  int64_t ubq_stride;
   float *dbg_xs;              // test hook: when set, the numerator of every bound, [n_q][n_chunks_pad]
   int64_t dbg_stride;
 };
@@ -125,7 +147,9 @@ static inline size_t bound_smem_bytes(int max_pages) { return sizeof(BoundSmem) 
 __global__ void __launch_bounds__(B_THREADS, 1)
 tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_u, BoundParams P) {
   extern __shared__ unsigned char smem_raw[];
-  BoundSmem &S = *reinterpret_cast<BoundSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by an OFFSET into the shared array (not by rounding a generic pointer): the compiler keeps
+  // the shared address space, so every access below is LDS/STS/ATOMS instead of a generic load / store / atomic
+  BoundSmem &S = *reinterpret_cast<BoundSmem *>(smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, bsplit = blockIdx.y;
   const int64_t n_blocks = (P.n_chunks + B_BN - 1) / B_BN;
@@ -168,7 +192,7 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       uint32_t phase = 0;
       for (int64_t bk = blk_lo; bk < blk_hi; bk++) {
         for (int s = 0; s < B_KSLICES; s++) {
-          mbar_wait(&S.empty_bar[stage], phase ^ 1);
+          mbar_wait_idle(&S.empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&S.full_bar[stage], B_B_SLICE_BYTES);
           tma_load_2d(S.b[stage], &map_u, &S.full_bar[stage], s * B_BK, (int)(bk * B_BN));
           if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
@@ -178,18 +202,18 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
   } else if (warp == B_WORKERS + 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      mbar_wait(&S.a_bar, 0);
+      mbar_wait_idle(&S.a_bar, 0);
       int stage = 0;
       uint32_t phase = 0;
       int64_t it = 0;
       for (int64_t bk = blk_lo; bk < blk_hi; bk++, it++) {
         const int as = (int)(it & 1);
         const uint32_t aphase = (uint32_t)((it >> 1) & 1);
-        mbar_wait(&S.tmem_empty[as], aphase ^ 1);
+        mbar_wait_idle(&S.tmem_empty[as], aphase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * B_BN);
         for (int s = 0; s < B_KSLICES; s++) {
-          mbar_wait(&S.full_bar[stage], phase);
+          mbar_wait_idle(&S.full_bar[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t da = umma_desc_sw128(S.a[s]);
           const uint64_t db = umma_desc_sw128(S.b[stage]);
@@ -365,6 +389,9 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       const float *mb = &S.minB[as][cs * B_COLS];
       const int64_t cbase = c0 + cs * B_COLS;
       uint32_t mymask = 0;
+      uint32_t codes[B_COLS / 4];
+#pragma unroll
+      for (int j = 0; j < B_COLS / 4; j++) codes[j] = 0;
 #pragma unroll
       for (int j = 0; j < B_COLS; j++) {
         const float xs = base + __uint_as_float(v[j]) + x[j];
@@ -379,6 +406,11 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         } else if (q_ok && c_ok) {
           const float lhs = P.jaccard ? xs : xs * xs;
           float metric = den > 0.f ? __fdividef(lhs, den) : INFINITY;
+          if (P.ubq) {  // the bound itself, as a code that can only err upwards
+            const float ub = den > 0.f ? (P.jaccard ? metric : xs * rsqrtf(nq * den)) * (PRUNE_SLACK * 1.00001f) : INFINITY;
+            const uint32_t code = (uint32_t)fminf(255.f, ceilf(ub * UBQ_SCALE));
+            codes[j >> 2] |= code << ((j & 3) * 8);
+          }
           if (metric > sm[B_SEEDS - 1]) {
             int cc = (int)(cbase + j);
 #pragma unroll
@@ -390,6 +422,8 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
           }
         }
       }
+      if (P.pass == 0 && P.ubq && q_in)
+        *reinterpret_cast<uint4 *>(P.ubq + (size_t)slot * P.ubq_stride + cbase) = make_uint4(codes[0], codes[1], codes[2], codes[3]);
       if (P.pass == 1) {
         // lanes holding a non-empty mask append {chunk, mask} to the group's list (warp-aggregated; four warps share
         // a list; the warp whose range crosses into a new page allocates it)
@@ -453,6 +487,104 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
   if (warp == B_WORKERS + 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// K1b-B2: candidate lists from the stored 8-bit bound codes (second pass without recomputing the bounds).  One CTA =
+// one scan group (32 queries = the lanes) x one chunk range; a warp reads, per query, 32 codes (one 32-byte sector) and
+// compares them with the query's threshold code; ballots give the group's query mask per chunk; non-empty masks are
+// appended to the group's paged candidate list exactly as K1b-B's pass 1 does.  HBM-bound: n_q x chunks bytes read once.
+// ----------------------------------------------------------------------------------------
+struct SelectParams {
+  const unsigned char *ubq;
+  int64_t ubq_stride, n_chunks, n_q;
+  const float *q_nq;
+  const int *gthr;
+  int n_bsplits;
+  uint32_t *list_count;
+  uint32_t *list_pages;
+  int max_pages;
+  uint2 *pool;
+  unsigned int *pool_next;
+  unsigned int pool_pages;
+  int *overflow;
+  unsigned long long *stats;
+};
+
+constexpr int SEL_WARPS = 8;
+
+__global__ void __launch_bounds__(SEL_WARPS * 32) tfidf_select_kernel(SelectParams P) {
+  extern __shared__ int s_pages[];  // [max_pages]
+  __shared__ unsigned int s_count;
+  const int group = blockIdx.x, bsplit = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int list = group * P.n_bsplits + bsplit;
+  for (int i = threadIdx.x; i < P.max_pages; i += blockDim.x) s_pages[i] = -1;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  const int64_t slot = (int64_t)group * GROUP_Q + lane;
+  const bool q_ok = slot < P.n_q && P.q_nq[slot] > 0.f;
+  uint32_t tcode = 256;  // never reached: the query takes no candidates
+  if (q_ok) {
+    const float th = __int_as_float(P.gthr[slot]);
+    tcode = th > 0.f ? (uint32_t)fminf(255.f, floorf(th * UBQ_SCALE)) : 0u;
+  }
+  // the chunk range of this split, in units of 32 chunks, interleaved over the warps
+  const int64_t n_blocks = (P.n_chunks + B_BN - 1) / B_BN;
+  const int64_t c_lo = (n_blocks * bsplit / P.n_bsplits) * B_BN, c_hi = min(P.n_chunks, (n_blocks * (bsplit + 1) / P.n_bsplits) * B_BN);
+  const unsigned char *row = P.ubq + (size_t)min(slot, P.n_q - 1) * P.ubq_stride;
+  unsigned int n_pairs = 0, n_recs = 0;
+  for (int64_t c = c_lo + 32 * warp; c < c_hi; c += 32 * SEL_WARPS) {
+    const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(row + c)), b = __ldcs(reinterpret_cast<const uint4 *>(row + c + 16));
+    const uint32_t wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t mymask = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      const uint32_t code = (wds[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+      const uint32_t m = __ballot_sync(FULL, q_ok && code >= tcode && c + j < c_hi);
+      if (lane == j) mymask = m;
+    }
+    const uint32_t am = __ballot_sync(FULL, mymask != 0);
+    if (am) {
+      const int n = __popc(am);
+      unsigned int bpos = 0;
+      if (lane == 0) {
+        bpos = atomicAdd(&s_count, (unsigned int)n);
+        for (unsigned int pg = (bpos + PAGE_RECS - 1) / PAGE_RECS; pg * PAGE_RECS < bpos + n; pg++) {
+          unsigned int np = atomicAdd(P.pool_next, 1u);
+          if (np >= P.pool_pages) { *P.overflow = 1; np = 0; }
+          P.list_pages[(size_t)list * P.max_pages + pg] = np;
+          __threadfence_block();
+          *(volatile int *)&s_pages[pg] = (int)np;
+        }
+      }
+      bpos = __shfl_sync(FULL, bpos, 0);
+      if (mymask) {
+        const unsigned int pos = bpos + (unsigned int)__popc(am & lanemask_lt());
+        const unsigned int pg = pos / PAGE_RECS;
+        int page;
+        while ((page = *(volatile int *)&s_pages[pg]) < 0) {}
+        uint2 rec;
+        rec.x = (uint32_t)(c + lane);
+        rec.y = mymask;
+        P.pool[(size_t)page * PAGE_RECS + (pos % PAGE_RECS)] = rec;
+        n_pairs += (unsigned int)__popc(mymask);
+        n_recs++;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) P.list_count[list] = s_count;
+  if (P.stats) {
+    for (int o = 16; o; o >>= 1) {
+      n_pairs += __shfl_xor_sync(FULL, n_pairs, o);
+      n_recs += __shfl_xor_sync(FULL, n_recs, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&P.stats[2], (unsigned long long)n_pairs);
+      atomicAdd(&P.stats[3], (unsigned long long)n_recs);
+    }
   }
 }
 

@@ -114,6 +114,8 @@ struct kv_index {
   DevBuf<uint2> d_direct, d_pool;
   DevBuf<uint32_t> d_list_count, d_list_pages;
   DevBuf<unsigned int> d_pool_ctl;  // [0] pages handed out, [1] overflow flag
+  DevBuf<unsigned char> d_ubq;      // 8-bit bound codes of a batch, [n_q][n_chunks_pad] (when they fit)
+  int last_used_codes = 0;
   int64_t pool_pages = 0;
   // cross-GPU threshold exchange (row-sharded GFKB): d_gthr is exported over CUDA IPC, the peers' arrays are mapped here
   bool gthr_exported = false;
@@ -266,7 +268,7 @@ void kv_index_destroy(kv_index *ix) {
   ix->d_flags.release(); ix->d_qconst.release(); ix->d_qtab.release(); ix->d_rtab.release(); ix->d_Wf.release();
   ix->d_gthr.release();
   ix->d_seeds.release(); ix->d_direct.release(); ix->d_pool.release(); ix->d_list_count.release(); ix->d_list_pages.release();
-  ix->d_pool_ctl.release();
+  ix->d_pool_ctl.release(); ix->d_ubq.release();
   close_peers(ix);
   ix->d_excl_sorted.release(); ix->d_excl_orig.release();
   ix->d_stats.release();
@@ -869,6 +871,18 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
     }
     KV_CUDA(ix->d_pool_ctl.ensure(2));
   }
+  // Second pass without recomputation: the first bound pass stores every bound as an 8-bit code (n_q x chunks bytes)
+  // when that fits comfortably (KAKVEDA_B200_BOUND_CODES=0 forces the recomputing second pass).
+  bool use_codes = false;
+  if (prune) {
+    const char *ce = getenv("KAKVEDA_B200_BOUND_CODES");
+    const int64_t want = n_q * ix->n_chunks_pad;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    use_codes = !(ce && ce[0] == '0') && (want <= ix->d_ubq.cap || want <= (int64_t)std::min<size_t>((size_t)64 << 30, free_b / 2));
+    if (use_codes) KV_CUDA(ix->d_ubq.ensure(want));
+  }
+  ix->last_used_codes = use_codes ? 1 : 0;
   static bool attr_set[64] = {false};
   if (!attr_set[ix->device & 63]) {
     KV_CUDA(cudaFuncSetAttribute(tfidf_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(32)));
@@ -915,6 +929,7 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
       BP.pool = ix->d_pool.p; BP.pool_next = ix->d_pool_ctl.p; BP.pool_pages = (unsigned int)ix->pool_pages;
       BP.overflow = (int *)(ix->d_pool_ctl.p + 1); BP.stats = ix->d_stats.p;
       BP.dbg_xs = ix->dbg_xs; BP.dbg_stride = ix->n_chunks_pad;
+      BP.ubq = use_codes ? ix->d_ubq.p : nullptr; BP.ubq_stride = ix->n_chunks_pad;
       const size_t b_smem = bound_smem_bytes(max_pages);
       const dim3 bgrid((unsigned)n_tiles, (unsigned)n_bsplits);
       // pass 0: seeds
@@ -932,9 +947,18 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
       tfidf_scan_kernel<<<dim3((unsigned)n_groups, (unsigned)n_ssplits_a), S_WARPS * 32, s_smem, s>>>(SP);
       KV_CUDA(cudaGetLastError());
       KV_CUDA(cudaEventRecord(ix->evk[2], s));
-      // pass 1: candidate lists
-      BP.pass = 1;
-      tfidf_bound_kernel<<<bgrid, B_THREADS, b_smem, s>>>(ix->map_w, ix->map_u, BP);
+      // pass 1: candidate lists -- from the stored codes when they were kept, else by recomputing the bounds
+      if (use_codes) {
+        SelectParams LP;
+        LP.ubq = ix->d_ubq.p; LP.ubq_stride = ix->n_chunks_pad; LP.n_chunks = ix->n_chunks; LP.n_q = n_q;
+        LP.q_nq = qc; LP.gthr = ix->d_gthr.p; LP.n_bsplits = (int)n_bsplits;
+        LP.list_count = BP.list_count; LP.list_pages = BP.list_pages; LP.max_pages = max_pages;
+        LP.pool = BP.pool; LP.pool_next = BP.pool_next; LP.pool_pages = BP.pool_pages; LP.overflow = BP.overflow; LP.stats = BP.stats;
+        tfidf_select_kernel<<<dim3((unsigned)n_groups, (unsigned)n_bsplits), SEL_WARPS * 32, (size_t)max_pages * sizeof(int), s>>>(LP);
+      } else {
+        BP.pass = 1;
+        tfidf_bound_kernel<<<bgrid, B_THREADS, b_smem, s>>>(ix->map_w, ix->map_u, BP);
+      }
       KV_CUDA(cudaGetLastError());
       KV_CUDA(cudaEventRecord(ix->evk[3], s));
       SP.list_mode = 0; SP.list_count = ix->d_list_count.p + n_groups; SP.list_pages = ix->d_list_pages.p;
