@@ -71,7 +71,7 @@ struct BlockLayout {
   std::vector<__half> Uf;                     // [n_chunks_pad][NF] largest tf of the frequent features per chunk
   std::vector<unsigned short> fslot2;         // [V] bit row of a second-class feature, 0xFFFF otherwise
   std::vector<uint32_t> Ubt;                  // [n_chunks_pad / 64][NF2][2][2]: bit c % 64 of plane 0 / 1 = present in chunk c with tf >= 1 / >= 2
-  int64_t n_entries = 0, n_rare_entries = 0;
+  int64_t n_entries = 0, n_rare_entries = 0, n_f2_entries = 0;
 };
 
 // the sorted (feature, tf, row-in-chunk) keys of a chunk's non-universal entries
@@ -147,21 +147,21 @@ inline void build_blocks(const int64_t *indptr, const uint32_t *ids, const uint1
   L.Ubt.assign((size_t)(L.n_chunks_pad / 64) * NF2 * 4, 0u);
   // pass 2: the blocks
   L.parts.assign((size_t)T, {});
-  L.binfo.assign((size_t)L.n_chunks_pad, BlockInfo{0, 0, 0});
+  L.binfo.assign((size_t)L.n_chunks_pad, BlockInfo{0, 0, 0, 0, 0});
   L.Uf.assign((size_t)L.n_chunks_pad * NF, __float2half(0.f));
   std::vector<std::vector<std::pair<unsigned long long, uint32_t>>> povf((size_t)T);
   std::vector<int64_t> words_of((size_t)L.n_chunks, 0);
-  std::vector<int64_t> ent((size_t)T, 0), rare((size_t)T, 0);
+  std::vector<int64_t> ent((size_t)T, 0), rare((size_t)T, 0), sec((size_t)T, 0);
   parallel_for(L.n_chunks, T, [&](int t, int64_t c0, int64_t c1) {
     std::vector<unsigned long long> keys;
-    std::vector<uint32_t> w_r, m_r, w_f, m_f;  // rare / frequent entries of the chunk: words and masks
-    std::vector<uint32_t> tf_r, tf_f;          // full term frequencies (overflow table)
+    std::vector<uint32_t> w_r, m_r, w_2, m_2, w_f, m_f;  // rare / second-class / frequent entries of the chunk: words and masks
+    std::vector<uint32_t> tf_r, tf_2, tf_f;              // full term frequencies (overflow table)
     auto &out = L.parts[(size_t)t];
     for (int64_t c = c0; c < c1; c++) {
       chunk_keys(indptr, ids, tf, perm, n, univ, c, keys);
       const int rows = (int)std::min<int64_t>(CHUNK_ROWS, n - c * CHUNK_ROWS);
       const uint32_t valid = rows == 32 ? 0xFFFFFFFFu : ((1u << rows) - 1u);
-      w_r.clear(); m_r.clear(); w_f.clear(); m_f.clear(); tf_r.clear(); tf_f.clear();
+      w_r.clear(); m_r.clear(); w_2.clear(); m_2.clear(); w_f.clear(); m_f.clear(); tf_r.clear(); tf_2.clear(); tf_f.clear();
       __half *urow = L.Uf.data() + (size_t)c * NF;
       for (size_t i = 0; i < keys.size();) {
         const unsigned long long ft = keys[i] >> 5;  // (feature, tf)
@@ -174,36 +174,43 @@ inline void build_blocks(const int64_t *indptr, const uint32_t *ids, const uint1
         if (fs >= 0) {
           w_f.push_back(word); m_f.push_back(mask); tf_f.push_back(tfv);
           urow[fs] = __float2half((float)tfv);  // keys ascend in tf: the last one is the largest (exact: tf <= 2048)
+        } else if (L.fslot2[f] != 0xFFFFu) {
+          w_2.push_back(word); m_2.push_back(mask); tf_2.push_back(tfv);
+          const unsigned short f2 = L.fslot2[f];  // chunks of one 64-chunk block may belong to different threads: atomic OR
+          uint32_t *w0 = &L.Ubt[((size_t)(c >> 6) * NF2 + f2) * 4 + ((c & 63) >> 5)];
+          __atomic_fetch_or(w0, 1u << (c & 31), __ATOMIC_RELAXED);
+          if (tfv >= 2) __atomic_fetch_or(w0 + 2, 1u << (c & 31), __ATOMIC_RELAXED);
         } else {
           w_r.push_back(word); m_r.push_back(mask); tf_r.push_back(tfv);
-          const unsigned short f2 = L.fslot2[f];
-          if (f2 != 0xFFFFu) {  // chunks of one 128-chunk block may belong to different threads: atomic OR
-            uint32_t *w0 = &L.Ubt[((size_t)(c >> 6) * NF2 + f2) * 4 + ((c & 63) >> 5)];
-            __atomic_fetch_or(w0, 1u << (c & 31), __ATOMIC_RELAXED);
-            if (tfv >= 2) __atomic_fetch_or(w0 + 2, 1u << (c & 31), __ATOMIC_RELAXED);
-          }
         }
       }
-      const size_t E = w_r.size() + w_f.size(), E4 = (E + 3) & ~(size_t)3;
+      const size_t E = w_r.size() + w_2.size() + w_f.size(), E4 = (E + 3) & ~(size_t)3;
       const size_t before = out.size();
       out.insert(out.end(), w_r.begin(), w_r.end());
+      out.insert(out.end(), w_2.begin(), w_2.end());
       out.insert(out.end(), w_f.begin(), w_f.end());
       out.resize(before + E4, PAD_WORD);
       out.insert(out.end(), m_r.begin(), m_r.end());
+      out.insert(out.end(), m_2.begin(), m_2.end());
       out.insert(out.end(), m_f.begin(), m_f.end());
       out.resize(before + 2 * E4, 0u);
       for (size_t i = 0; i < tf_r.size(); i++)
         if (tf_r[i] >= TF_OVF) povf[(size_t)t].emplace_back(((unsigned long long)c << 32) | (unsigned long long)i, tf_r[i]);
+      for (size_t i = 0; i < tf_2.size(); i++)
+        if (tf_2[i] >= TF_OVF) povf[(size_t)t].emplace_back(((unsigned long long)c << 32) | (unsigned long long)(w_r.size() + i), tf_2[i]);
       for (size_t i = 0; i < tf_f.size(); i++)
-        if (tf_f[i] >= TF_OVF) povf[(size_t)t].emplace_back(((unsigned long long)c << 32) | (unsigned long long)(w_r.size() + i), tf_f[i]);
+        if (tf_f[i] >= TF_OVF) povf[(size_t)t].emplace_back(((unsigned long long)c << 32) | (unsigned long long)(w_r.size() + w_2.size() + i), tf_f[i]);
       BlockInfo bi;
       bi.off4 = 0;
       bi.n_entries = (uint16_t)E;
       bi.n_rare = (uint16_t)w_r.size();
+      bi.n_f2 = (uint16_t)w_2.size();
+      bi.pad = 0;
       L.binfo[(size_t)c] = bi;
       words_of[(size_t)c] = (int64_t)(2 * E4);
       ent[(size_t)t] += (int64_t)E;
       rare[(size_t)t] += (int64_t)w_r.size();
+      sec[(size_t)t] += (int64_t)w_2.size();
     }
   });
   int64_t off = 0;
@@ -219,11 +226,12 @@ inline void build_blocks(const int64_t *indptr, const uint32_t *ids, const uint1
     for (int t = 0; t < T; t++) { L.part_off[(size_t)t] = o; o += (int64_t)L.parts[(size_t)t].size(); }
   }
   L.ovf.clear();
-  L.n_entries = L.n_rare_entries = 0;
+  L.n_entries = L.n_rare_entries = L.n_f2_entries = 0;
   for (int t = 0; t < T; t++) {
     L.ovf.insert(L.ovf.end(), povf[(size_t)t].begin(), povf[(size_t)t].end());
     L.n_entries += ent[(size_t)t];
     L.n_rare_entries += rare[(size_t)t];
+    L.n_f2_entries += sec[(size_t)t];
   }
   std::sort(L.ovf.begin(), L.ovf.end());
 }

@@ -241,6 +241,7 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     const uint32_t *rt_wq = rt_keys + RT_SLOTS;
     const uint32_t *rt_multi = rt_wq + RT_SLOTS;
     const uint32_t *rt_bm = rt_multi + 4 * RT_MULTI;
+    const bool probe_f2 = rt_bm[RT_BITMAP_BITS / 32] != 0;  // some query's second-class list overflowed into the table
     const int list = (tile * 4 + qtr) * P.n_bsplits + bsplit;
     int *my_pages = S.pages + qtr * P.max_pages;
     float sm[B_SEEDS];
@@ -270,7 +271,7 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         if (lane < PER_WARP && c0 + warp + B_WORKERS * lane < P.n_chunks) {
           const BlockInfo bi = P.binfo[c0 + warp + B_WORKERS * lane];
           my_off = bi.off4;
-          my_nr = bi.n_rare;
+          my_nr = probe_f2 ? (uint32_t)bi.n_rare + bi.n_f2 : bi.n_rare;
         }
         auto probe = [&](uint32_t w, int j, uint32_t e) {
           const uint32_t fid = (w >> 5) & FID_MASK;
@@ -389,6 +390,7 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       const float *mb = &S.minB[as][cs * B_COLS];
       const int64_t cbase = c0 + cs * B_COLS;
       uint32_t mymask = 0;
+      const bool dbg = P.dbg_xs != nullptr;
       uint32_t codes[B_COLS / 4];
 #pragma unroll
       for (int j = 0; j < B_COLS / 4; j++) codes[j] = 0;
@@ -396,7 +398,7 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       for (int j = 0; j < B_COLS; j++) {
         const float xs = base + __uint_as_float(v[j]) + x[j];
         const bool c_ok = cbase + j < P.n_chunks;
-        if (P.dbg_xs && q_in && c_ok) P.dbg_xs[(size_t)slot * P.dbg_stride + cbase + j] = xs;
+        if (dbg && q_in && c_ok) P.dbg_xs[(size_t)slot * P.dbg_stride + cbase + j] = xs;
         const float den = P.jaccard ? (nq + mb[j] - xs) : (mb[j] + corrS);
         if (P.pass == 1) {
           const float lhs = P.jaccard ? xs : xs * xs;
@@ -404,13 +406,9 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
           const uint32_t m = __ballot_sync(FULL, sv);
           if (lane == j) mymask = m;
         } else if (q_ok && c_ok) {
-          const float lhs = P.jaccard ? xs : xs * xs;
-          float metric = den > 0.f ? __fdividef(lhs, den) : INFINITY;
-          if (P.ubq) {  // the bound itself, as a code that can only err upwards
-            const float ub = den > 0.f ? (P.jaccard ? metric : xs * rsqrtf(nq * den)) * (PRUNE_SLACK * 1.00001f) : INFINITY;
-            const uint32_t code = (uint32_t)fminf(255.f, ceilf(ub * UBQ_SCALE));
-            codes[j >> 2] |= code << ((j & 3) * 8);
-          }
+          // the bound itself (slack included): seeds are ranked by it, and it is stored as a code that only errs upwards
+          float metric = den > 0.f ? (P.jaccard ? __fdividef(xs, den) : xs * rsqrtf(nq * den)) * (PRUNE_SLACK * 1.00001f) : INFINITY;
+          if (P.ubq) codes[j >> 2] |= (uint32_t)fminf(255.f, ceilf(metric * UBQ_SCALE)) << ((j & 3) * 8);
           if (metric > sm[B_SEEDS - 1]) {
             int cc = (int)(cbase + j);
 #pragma unroll

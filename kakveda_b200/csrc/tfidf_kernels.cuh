@@ -59,14 +59,17 @@ constexpr int RT_SLOTS = 2048;  // rare-feature table of a bound tile: keys[RT_S
 constexpr int RT_CAP = 1400;    // features it accepts (the rest enters the bounds as per-query constants)
 constexpr int RT_MULTI = 256;   // of those, features shared by several queries of the tile (128-bit membership masks)
 constexpr int RT_BITMAP_BITS = 1 << 16;  // presence bitmap probed before the table (1 shared-memory load rejects ~98 % of the entries)
-constexpr int RTAB_BYTES = RT_SLOTS * 8 + RT_MULTI * 16 + RT_BITMAP_BITS / 8;
+constexpr int RTAB_BYTES = RT_SLOTS * 8 + RT_MULTI * 16 + RT_BITMAP_BITS / 8 + 16;  // + flags: [0] the table holds second-class features
 constexpr float PRUNE_SLACK = 1.0005f;  // bounds: fp16 round-up of weights, fp32 tensor-core sums, constants rounded outwards
 constexpr float FILTER_SLACK = 0.999996f;
 constexpr int PAGE_RECS = 1024;  // candidate records per pool page
 
 struct BlockInfo {
-  uint32_t off4;  // offset of the block in 16-byte units
-  uint16_t n_entries, n_rare;  // entries; of those, leading entries of non-frequent features
+  uint32_t off4;       // offset of the block in 16-byte units
+  uint16_t n_entries;  // entries of the block, ordered [rare][second class][frequent], each part sorted by (feature, tf)
+  uint16_t n_rare;     // leading entries of features in neither dense class (what the bound kernel's join probes)
+  uint16_t n_f2;       // following entries of second-class features (bitmaps in the bound kernel)
+  uint16_t pad;
 };
 
 // ----------------------------------------------------------------------------------------
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(TILE_Q) prep_tiles_kernel(PrepParams P) {
   uint32_t *s_w = s_keys + RT_SLOTS;                 // float bits
   uint32_t *s_m = s_w + RT_SLOTS;                    // [RT_SLOTS][4]
   uint32_t *s_bm = s_m + 4 * RT_SLOTS;               // [RT_BITMAP_BITS / 32]
-  __shared__ int s_cnt, s_multi;
+  __shared__ int s_cnt, s_multi, s_has2;
   __shared__ float s_dotX[TILE_Q];
   const int tile = blockIdx.x, qi = threadIdx.x;
   for (int j = qi; j < RT_SLOTS; j += TILE_Q) {
@@ -389,7 +392,7 @@ __global__ void __launch_bounds__(TILE_Q) prep_tiles_kernel(PrepParams P) {
     s_m[4 * j] = s_m[4 * j + 1] = s_m[4 * j + 2] = s_m[4 * j + 3] = 0;
   }
   for (int j = qi; j < RT_BITMAP_BITS / 32; j += TILE_Q) s_bm[j] = 0;
-  if (qi == 0) { s_cnt = 0; s_multi = 0; }
+  if (qi == 0) { s_cnt = 0; s_multi = 0; s_has2 = 0; }
   s_dotX[qi] = 0.f;
   __syncthreads();
   const int64_t i = (int64_t)tile * TILE_Q + qi;
@@ -401,7 +404,10 @@ __global__ void __launch_bounds__(TILE_Q) prep_tiles_kernel(PrepParams P) {
       if ((int64_t)t >= P.V || P.univ[t]) continue;
       if (cnt++ >= QFEATS) break;
       if (P.fslot[t] >= 0) continue;
-      if (P.fslot2[t] != 0xFFFFu && c2 < P.q2cap) { c2++; continue; }  // in the query's own second-class list
+      if (P.fslot2[t] != 0xFFFFu) {
+        if (c2 < P.q2cap) { c2++; continue; }  // in the query's own second-class list
+        s_has2 = 1;                             // list full: the feature goes to the table (its block entries must be probed)
+      }
       const float w = __half2float(__float2half_ru(__double2float_ru((double)P.q_tf[p] * P.a64[t])));
       uint32_t h = hash_fid(t, 11);
       bool placed = false;
@@ -457,6 +463,7 @@ __global__ void __launch_bounds__(TILE_Q) prep_tiles_kernel(PrepParams P) {
     o_wq[j] = (uint32_t)__half_as_ushort(__float2half_ru(w)) | (qinfo << 16);
   }
   for (int j = qi; j < RT_BITMAP_BITS / 32; j += TILE_Q) o_bm[j] = s_bm[j];
+  if (qi < 4) o_bm[RT_BITMAP_BITS / 32 + qi] = qi == 0 ? (uint32_t)s_has2 : 0u;
   __syncthreads();
   if (i < P.n_q) P.q_dotX[i] = s_dotX[qi] * 1.00001f;
 }

@@ -105,14 +105,15 @@ static void check_case(int64_t n, int64_t V, int n_univ, unsigned seed, bool big
       uint32_t t = w & 31u;
       if (t == TF_OVF) t = ovf_get(L1, ch, (uint32_t)e);
       CHECK(t >= 1, "tf of entry");
-      const bool rare = e < bi.n_rare;
-      CHECK((L1.fslot[f] < 0) == rare, "entry %d of chunk %lld on the wrong side of n_rare", e, (long long)ch);
+      const bool rare = e < bi.n_rare, sec = !rare && e < bi.n_rare + bi.n_f2;
+      CHECK((L1.fslot[f] < 0 && L1.fslot2[f] == 0xFFFF) == rare && (L1.fslot2[f] != 0xFFFF) == sec,
+            "entry %d of chunk %lld in the wrong part of the block", e, (long long)ch);
       const unsigned long long key = ((unsigned long long)f << 16) | t;
-      if (e != 0 && e != bi.n_rare) CHECK(key > prev, "entries not sorted");
+      if (e != 0 && e != bi.n_rare && e != bi.n_rare + bi.n_f2) CHECK(key > prev, "entries not sorted");
       prev = key;
       CHECK(masks[e] != 0 && (masks[e] & ~valid) == 0, "mask of entry");
       CHECK(((w & W_ALL) != 0) == (masks[e] == valid), "W_ALL flag");
-      if (!rare) umax[L1.fslot[f]] = std::max(umax[L1.fslot[f]], t);
+      if (!rare && !sec) umax[L1.fslot[f]] = std::max(umax[L1.fslot[f]], t);
       CHECK(!(L1.fslot[f] >= 0 && L1.fslot2[f] != 0xFFFF), "feature in both classes");
       if (L1.fslot2[f] != 0xFFFF) { have2.insert((int)L1.fslot2[f]); if (t >= 2) have2b.insert((int)L1.fslot2[f]); }
       for (int r = 0; r < rows; r++)
