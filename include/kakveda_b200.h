@@ -171,6 +171,13 @@ int kv_query_upload(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids
 int kv_topk_resident(kv_index *ix, int k, void *d_scores, void *d_rows);
 /* Same with host outputs (out_scores float32[n_q*k], out_rows int64[n_q*k]). */
 int kv_topk_resident_host(kv_index *ix, int k, float *out_scores, int64_t *out_rows);
+/* kv_topk_resident in two phases, for a row-sharded GFKB (kakveda_b200/dist.py): _seed = bound pass + seed scan, the
+ * outputs receive this shard's seed top-k (device, [n_q*k], by original query); kv_index_raise_thresholds takes, per
+ * query, a lower bound of the GLOBAL k-th score (device float32[n_q]; the k-th of the merged seed lists of all shards)
+ * and raises the pruning thresholds of the resident batch; _finish = candidate selection + scan + merge. */
+int kv_topk_resident_seed(kv_index *ix, int k, void *d_scores, void *d_rows);
+int kv_index_raise_thresholds(kv_index *ix, const void *d_kth_scores, int64_t n_q);
+int kv_topk_resident_finish(kv_index *ix, int k, void *d_scores, void *d_rows);
 /* Self-join support: after kv_query_upload, query q never matches GLOBAL row exclude_rows[q] (-1: none; rows of
  * other shards are ignored).  Used when the queries ARE stored rows (all-pairs clustering: every row's k nearest
  * OTHER rows).  NULL clears; the next kv_query_upload clears too. */

@@ -39,6 +39,8 @@ struct kv_index {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t evk[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // bound/scan kernel boundaries of a batch
+  cudaEvent_t evp2 = nullptr;  // start of phase 2 of a two-phase batch
+  bool two_phase = false;
   std::mutex mu;
   int sm_count = 148;
 
@@ -245,6 +247,7 @@ int kv_index_create(int device, int64_t row_base, kv_index **out) {
   KV_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
   for (auto &e : ix->ev) KV_CUDA(cudaEventCreate(&e));
   for (auto &e : ix->evk) KV_CUDA(cudaEventCreate(&e));
+  KV_CUDA(cudaEventCreate(&ix->evp2));
   *out = ix;
   return KV_OK;
 }
@@ -277,6 +280,7 @@ void kv_index_destroy(kv_index *ix) {
   ix->h_qtab.release(); ix->d_qtab1.release(); ix->d_scores.release();
   for (auto &e : ix->ev) if (e) cudaEventDestroy(e);
   for (auto &e : ix->evk) if (e) cudaEventDestroy(e);
+  if (ix->evp2) cudaEventDestroy(ix->evp2);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   delete ix;
 }
@@ -819,7 +823,9 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
 }
 
 // Device-only half: bounds + scans + merge (+ fallback scans for irregular queries) of the uploaded batch.
-static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
+// phase 0: the whole batch.  phase 1: up to the seed scan; the outputs receive the seed top-k (their k-th score is a
+// lower bound of the final k-th score; a row-sharded GFKB exchanges it between the GPUs).  phase 2: the rest.
+static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r, int phase = 0) {
   if (!ix->batch_valid) return kv_fail(KV_ERR_STATE, "kv_topk_resident: no query batch uploaded");
   if (k < 1 || k > 32) return kv_fail(KV_ERR_INVALID, "kv_topk: k must be 1..32");
   KV_CUDA(cudaSetDevice(ix->device));
@@ -877,12 +883,20 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
   if (prune) {
     const char *ce = getenv("KAKVEDA_B200_BOUND_CODES");
     const int64_t want = n_q * ix->n_chunks_pad;
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    use_codes = !(ce && ce[0] == '0') && (want <= ix->d_ubq.cap || want <= (int64_t)std::min<size_t>((size_t)64 << 30, free_b / 2));
-    if (use_codes) KV_CUDA(ix->d_ubq.ensure(want));
+    if (phase == 2) {
+      use_codes = ix->last_used_codes != 0;
+    } else if (!(ce && ce[0] == '0')) {
+      use_codes = want <= ix->d_ubq.cap;
+      if (!use_codes) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        use_codes = want <= (int64_t)std::min<size_t>((size_t)64 << 30, free_b / 2);
+        if (use_codes) KV_CUDA(ix->d_ubq.ensure(want));
+      }
+    }
   }
-  ix->last_used_codes = use_codes ? 1 : 0;
+  if (phase != 2) ix->last_used_codes = use_codes ? 1 : 0;
+  const bool do_p1 = phase != 2, do_p2 = phase != 1;
   static bool attr_set[64] = {false};
   if (!attr_set[ix->device & 63]) {
     KV_CUDA(cudaFuncSetAttribute(tfidf_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(32)));
@@ -893,15 +907,18 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
     return kv_fail(KV_ERR_INVALID, "kv_topk: index too large for one bound-kernel row range (max_pages %d)", max_pages);
 
   int64_t launches = 0;
-  KV_CUDA(cudaEventRecord(ix->ev[1], s));
-  for (auto &e : ix->evk) KV_CUDA(cudaEventRecord(e, s));
+  if (do_p1) {
+    KV_CUDA(cudaEventRecord(ix->ev[1], s));
+    for (auto &e : ix->evk) KV_CUDA(cudaEventRecord(e, s));
+  }
   if (ix->n_rows > 0) {
-    // global lower bounds of the k-th score start at -inf
     const float *qc = ix->d_qconst.p;
-    KV_CUDA(cudaMemsetAsync(ix->d_stats.p, 0, 8 * sizeof(unsigned long long), s));
-    fill_int_kernel<<<(unsigned)((n_q + 255) / 256), 256, 0, s>>>(ix->d_gthr.p, n_q, (int)0xFF800000);
-    KV_CUDA(cudaGetLastError());
-    launches++;
+    if (do_p1) {  // global lower bounds of the k-th score start at -inf
+      KV_CUDA(cudaMemsetAsync(ix->d_stats.p, 0, 8 * sizeof(unsigned long long), s));
+      fill_int_kernel<<<(unsigned)((n_q + 255) / 256), 256, 0, s>>>(ix->d_gthr.p, n_q, (int)0xFF800000);
+      KV_CUDA(cudaGetLastError());
+      launches++;
+    }
     ScanParams SP;
     SP.blk = ix->d_blk.p; SP.binfo = ix->d_binfo.p; SP.B32 = ix->d_B32.p; SP.perm = ix->d_perm.p;
     SP.n_chunks = ix->n_chunks; SP.n_rows = ix->n_rows; SP.row_base = ix->row_base;
@@ -917,7 +934,7 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
     SP.direct_stride = 0;
     const size_t s_smem = scan_smem_bytes(k);
     if (prune) {
-      KV_CUDA(cudaMemsetAsync(ix->d_pool_ctl.p, 0, 2 * sizeof(unsigned int), s));
+      if (do_p1) KV_CUDA(cudaMemsetAsync(ix->d_pool_ctl.p, 0, 2 * sizeof(unsigned int), s));
       BoundParams BP;
       BP.blk = ix->d_blk.p; BP.binfo = ix->d_binfo.p; BP.chunk_minB = ix->d_cminB.p;
       BP.ovf_keys = ix->d_ovf_keys.p; BP.ovf_vals = ix->d_ovf_vals.p; BP.n_ovf = ix->n_ovf;
@@ -932,21 +949,36 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
       BP.ubq = use_codes ? ix->d_ubq.p : nullptr; BP.ubq_stride = ix->n_chunks_pad;
       const size_t b_smem = bound_smem_bytes(max_pages);
       const dim3 bgrid((unsigned)n_tiles, (unsigned)n_bsplits);
-      // pass 0: seeds
-      KV_CUDA(cudaEventRecord(ix->evk[0], s));
-      BP.pass = 0;
-      tfidf_bound_kernel<<<bgrid, B_THREADS, b_smem, s>>>(ix->map_w, ix->map_u, BP);
-      KV_CUDA(cudaGetLastError());
-      seeds_to_lists_kernel<<<(unsigned)((n_groups * GROUP_Q * n_seed + 255) / 256), 256, 0, s>>>(ix->d_seeds.p, n_q, n_seed,
-                                                                                                 ix->d_direct.p, ix->d_list_count.p);
-      KV_CUDA(cudaGetLastError());
-      KV_CUDA(cudaEventRecord(ix->evk[1], s));
-      // seed scan: gives every query a lower bound of its k-th score
-      SP.list_mode = 1; SP.list_count = ix->d_list_count.p; SP.direct = ix->d_direct.p; SP.direct_stride = GROUP_Q * n_seed;
-      SP.n_bsplits = 1; SP.n_ssplits = (int)n_ssplits_a;
-      tfidf_scan_kernel<<<dim3((unsigned)n_groups, (unsigned)n_ssplits_a), S_WARPS * 32, s_smem, s>>>(SP);
-      KV_CUDA(cudaGetLastError());
-      KV_CUDA(cudaEventRecord(ix->evk[2], s));
+      if (do_p1) {
+        // pass 0: seeds
+        KV_CUDA(cudaEventRecord(ix->evk[0], s));
+        BP.pass = 0;
+        tfidf_bound_kernel<<<bgrid, B_THREADS, b_smem, s>>>(ix->map_w, ix->map_u, BP);
+        KV_CUDA(cudaGetLastError());
+        seeds_to_lists_kernel<<<(unsigned)((n_groups * GROUP_Q * n_seed + 255) / 256), 256, 0, s>>>(ix->d_seeds.p, n_q, n_seed,
+                                                                                                   ix->d_direct.p, ix->d_list_count.p);
+        KV_CUDA(cudaGetLastError());
+        KV_CUDA(cudaEventRecord(ix->evk[1], s));
+        // seed scan: gives every query a lower bound of its k-th score
+        SP.list_mode = 1; SP.list_count = ix->d_list_count.p; SP.direct = ix->d_direct.p; SP.direct_stride = GROUP_Q * n_seed;
+        SP.n_bsplits = 1; SP.n_ssplits = (int)n_ssplits_a;
+        tfidf_scan_kernel<<<dim3((unsigned)n_groups, (unsigned)n_ssplits_a), S_WARPS * 32, s_smem, s>>>(SP);
+        KV_CUDA(cudaGetLastError());
+        KV_CUDA(cudaEventRecord(ix->evk[2], s));
+        launches += 3;
+        if (phase == 1) {  // the seed top-k of this shard, by original query
+          merge_topk_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, s>>>(ix->d_part_s.p, ix->d_part_r.p, (int)n_ssplits_a,
+                                                                               n_q, k, n_q * k, n_q * k, ix->d_qperm.p, d_out_s, d_out_r);
+          KV_CUDA(cudaGetLastError());
+          launches++;
+        }
+      }
+      if (!do_p2) {
+        ix->last_launches = launches;
+        return KV_OK;
+      }
+      ix->two_phase = phase == 2;
+      if (phase == 2) KV_CUDA(cudaEventRecord(ix->evp2, s));  // the caller's threshold exchange sits between evk[2] and this point
       // pass 1: candidate lists -- from the stored codes when they were kept, else by recomputing the bounds
       if (use_codes) {
         SelectParams LP;
@@ -963,9 +995,16 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
       KV_CUDA(cudaEventRecord(ix->evk[3], s));
       SP.list_mode = 0; SP.list_count = ix->d_list_count.p + n_groups; SP.list_pages = ix->d_list_pages.p;
       SP.pool = ix->d_pool.p; SP.direct = nullptr;
-      launches += 4;
+      launches += 1;
     } else {
       SP.list_mode = 2;
+      if (!do_p2) {  // exhaustive mode has no seed phase: empty seed lists
+        fill_int_kernel<<<(unsigned)((n_q * k + 255) / 256), 256, 0, s>>>((int *)d_out_s, n_q * k, (int)0xFF800000);
+        fill_ll_kernel<<<(unsigned)((n_q * k + 255) / 256), 256, 0, s>>>(d_out_r, n_q * k, -1LL);
+        KV_CUDA(cudaGetLastError());
+        ix->last_launches = launches + 2;
+        return KV_OK;
+      }
     }
     SP.n_bsplits = (int)n_bsplits; SP.n_ssplits = (int)n_ssplits;
     tfidf_scan_kernel<<<dim3((unsigned)n_lists, (unsigned)n_ssplits), S_WARPS * 32, s_smem, s>>>(SP);
@@ -1003,7 +1042,7 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
     KV_CUDA(cudaMemcpyAsync(d_out_r, er.data(), er.size() * 8, cudaMemcpyHostToDevice, s));
     KV_CUDA(cudaStreamSynchronize(s));
   }
-  ix->last_launches = launches;
+  ix->last_launches = (phase == 2 ? ix->last_launches : 0) + launches;
   KV_CUDA(cudaEventRecord(ix->ev[3], s));
   return KV_OK;
 }
@@ -1012,6 +1051,7 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r) {
 static int finish_batch(kv_index *ix) {
   for (int i = 1; i < 4; i++) cudaEventElapsedTime(&ix->last_ms[i], ix->ev[i], ix->ev[i + 1]);
   for (int i = 0; i < 5; i++) cudaEventElapsedTime(&ix->last_kernel_ms[i], ix->evk[i], ix->evk[i + 1]);
+  if (ix->two_phase) cudaEventElapsedTime(&ix->last_kernel_ms[2], ix->evp2, ix->evk[3]);
   const unsigned int *ctl = (const unsigned int *)&ix->last_stats[6];
   if (ix->n_rows > 0 && ctl[1] != 0) {
     ix->last_stats[6] = 0;
@@ -1215,6 +1255,42 @@ int kv_topk_resident(kv_index *ix, int k, void *d_scores, void *d_rows) {
   if (!ix || !d_scores || !d_rows) return kv_fail(KV_ERR_INVALID, "kv_topk_resident: bad arguments");
   std::lock_guard<std::mutex> g(ix->mu);
   int rc = run_batch(ix, k, (float *)d_scores, (long long *)d_rows);
+  if (rc != KV_OK) return rc;
+  KV_CUDA(cudaEventRecord(ix->ev[4], ix->stream));
+  KV_CUDA(cudaStreamSynchronize(ix->stream));
+  return finish_batch(ix);
+}
+
+// Two-phase form for a row-sharded GFKB: _seed runs the bound pass and the seed scan of the resident batch and returns
+// this shard's seed top-k (device, by original query); the caller merges the shards' seed lists (one small all-gather)
+// and feeds the GLOBAL k-th seed score of every query back with kv_index_raise_thresholds; _finish then selects and
+// scans only the chunks that can still beat it.  Every shard prunes with the threshold a single index would have.
+int kv_topk_resident_seed(kv_index *ix, int k, void *d_scores, void *d_rows) {
+  if (!ix || !d_scores || !d_rows) return kv_fail(KV_ERR_INVALID, "kv_topk_resident_seed: bad arguments");
+  std::lock_guard<std::mutex> g(ix->mu);
+  int rc = run_batch(ix, k, (float *)d_scores, (long long *)d_rows, 1);
+  if (rc != KV_OK) return rc;
+  KV_CUDA(cudaStreamSynchronize(ix->stream));
+  return KV_OK;
+}
+
+int kv_index_raise_thresholds(kv_index *ix, const void *d_kth_scores, int64_t n_q) {
+  if (!ix || !d_kth_scores) return kv_fail(KV_ERR_INVALID, "kv_index_raise_thresholds: bad arguments");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (!ix->batch_valid || n_q != ix->batch_q) return kv_fail(KV_ERR_STATE, "kv_index_raise_thresholds: no matching resident batch");
+  if (n_q > ix->d_gthr.cap) return kv_fail(KV_ERR_STATE, "kv_index_raise_thresholds: run kv_topk_resident_seed first");
+  KV_CUDA(cudaSetDevice(ix->device));
+  raise_thresholds_kernel<<<(unsigned)((n_q + 255) / 256), 256, 0, ix->stream>>>((const float *)d_kth_scores, ix->d_qperm.p, n_q,
+                                                                                  ix->d_gthr.p);
+  KV_CUDA(cudaGetLastError());
+  KV_CUDA(cudaStreamSynchronize(ix->stream));
+  return KV_OK;
+}
+
+int kv_topk_resident_finish(kv_index *ix, int k, void *d_scores, void *d_rows) {
+  if (!ix || !d_scores || !d_rows) return kv_fail(KV_ERR_INVALID, "kv_topk_resident_finish: bad arguments");
+  std::lock_guard<std::mutex> g(ix->mu);
+  int rc = run_batch(ix, k, (float *)d_scores, (long long *)d_rows, 2);
   if (rc != KV_OK) return rc;
   KV_CUDA(cudaEventRecord(ix->ev[4], ix->stream));
   KV_CUDA(cudaStreamSynchronize(ix->stream));

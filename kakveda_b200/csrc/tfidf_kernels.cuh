@@ -152,6 +152,19 @@ __global__ void fill_int_kernel(int *p, int64_t n, int v) {
   if (i < n) p[i] = v;
 }
 
+__global__ void fill_ll_kernel(long long *p, int64_t n, long long v) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// gthr[slot] = max(gthr[slot], kth[query of the slot]) for positive scores (float bits order like ints)
+__global__ void raise_thresholds_kernel(const float *__restrict__ kth, const int *__restrict__ qperm, int64_t n_q, int *gthr) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_q) return;
+  const float v = kth[qperm[i]];
+  if (v > 0.f) atomicMax(&gthr[i], __float_as_int(v));
+}
+
 __global__ void invperm_kernel(const int *__restrict__ perm, int64_t n, int *invperm) {
   const int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (pos < n) invperm[perm[pos]] = (int)pos;

@@ -247,21 +247,36 @@ class ShardedGfkb:
         # rows mode: the local result lands in ONE packed buffer (scores + rows), which is what travels
         buf = torch.empty(packed_layout(q, k)[1], dtype=torch.uint8, device=dev)
         s, r = packed_views(buf, q, k)
-        self.index.topk_resident(k, s.data_ptr(), r.data_ptr())
+        if self.world == 1:
+            self.index.topk_resident(k, s.data_ptr(), r.data_ptr())
+            if self.row_map is not None:
+                r.copy_(torch.where(r >= 0, self.row_map[r.clamp(min=0)], r))
+            return s, r
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        # phase 1: bounds + seed scan on every shard; the shards' seed lists are merged (small all-gather) and the GLOBAL
+        # k-th seed score of every query becomes every shard's pruning threshold -- each shard then scans only what a
+        # single index would scan of its rows
+        self.index.topk_resident_seed(k, s.data_ptr(), r.data_ptr())
+        ev[0].record()
+        seeds = gather_packed(buf, self.group)
+        ms, _ = merge_packed_on_device(self.device, seeds, q, k)
+        kth = ms[:, k - 1].contiguous()
+        ev[1].record()
+        torch.cuda.current_stream().synchronize()
+        self.index.raise_thresholds(kth.data_ptr(), q)
+        # phase 2: candidate selection + scan, then the exchange of the partial top-k
+        self.index.topk_resident_finish(k, s.data_ptr(), r.data_ptr())
         if self.row_map is not None:  # text-range shard: local row -> global row id (-1 stays -1)
             r.copy_(torch.where(r >= 0, self.row_map[r.clamp(min=0)], r))
-        if self.world == 1:
-            return s, r
-        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True); t2 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        gathered = gather_packed(buf, self.group)          # the single NCCL all-gather of the path
-        t1.record()
+        ev[2].record()
+        gathered = gather_packed(buf, self.group)          # the all-gather of the partial top-k
+        ev[3].record()
         out = merge_packed_on_device(self.device, gathered, q, k)
-        t2.record()
+        ev[4].record()
         # The collective doubles as the barrier between batches for the cross-GPU threshold pushes: no rank may start
         # the next batch's scan (which resets and pushes thresholds) before every rank has finished this one's.
         torch.cuda.current_stream().synchronize()
-        self.last_exchange_ms = (t0.elapsed_time(t1), t1.elapsed_time(t2))
+        self.last_exchange_ms = (ev[2].elapsed_time(ev[3]), ev[3].elapsed_time(ev[4]), ev[0].elapsed_time(ev[1]))
         return out
 
     def set_resident(self, qfb: FeatureBatch) -> None:

@@ -322,6 +322,18 @@ class GfkbIndex:
         """Device-only scan + merge of the uploaded batch into caller-owned device buffers."""
         _capi.check(_capi.load().kv_topk_resident(self._h, k, C.c_void_p(d_scores_ptr), C.c_void_p(d_rows_ptr)))
 
+    def topk_resident_seed(self, k: int, d_scores_ptr: int, d_rows_ptr: int) -> None:
+        """Phase 1 of a sharded step: bound pass + seed scan; the buffers receive this shard's seed top-k."""
+        _capi.check(_capi.load().kv_topk_resident_seed(self._h, k, C.c_void_p(d_scores_ptr), C.c_void_p(d_rows_ptr)))
+
+    def raise_thresholds(self, d_kth_ptr: int, n_q: int) -> None:
+        """Per query a lower bound of the GLOBAL k-th score (device float32[n_q]): raises the pruning thresholds."""
+        _capi.check(_capi.load().kv_index_raise_thresholds(self._h, C.c_void_p(d_kth_ptr), n_q))
+
+    def topk_resident_finish(self, k: int, d_scores_ptr: int, d_rows_ptr: int) -> None:
+        """Phase 2 of a sharded step: candidate selection + scan + merge of the resident batch."""
+        _capi.check(_capi.load().kv_topk_resident_finish(self._h, k, C.c_void_p(d_scores_ptr), C.c_void_p(d_rows_ptr)))
+
     def topk(self, queries: Sequence[str], k: int) -> Tuple[np.ndarray, np.ndarray]:
         """(scores float32 [Q,k], rows int64 [Q,k]) ordered by (score desc, row asc) (K1b+K5)."""
         fb = self.vocab.featurize(queries, grow=False)
