@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -341,6 +342,8 @@ int kv_featurize(kv_vocab *v, const char *bytes, const int64_t *offsets, int64_t
     if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > 0x7fffffffLL)
       return kv_fail(KV_ERR_INVALID, "kv_featurize: offsets must be non-decreasing, docs < 2 GiB");
   int T = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+  if (n_threads <= 0)  // several ranks share one host: their launcher sets the per-process thread budget
+    if (const char *e = getenv("KAKVEDA_B200_THREADS")) T = atoi(e);
   if (T < 1) T = 1;
   if (T > 256) T = 256;
   try {

@@ -284,12 +284,26 @@ class ShardedGfkb:
         self._resident_q = qfb.n
 
     def topk_packed(self, data, offsets: np.ndarray, k: int, mode: int = 0):
-        """End-to-end step from host text: featurise, upload, scan, exchange, merge, read back."""
+        """End-to-end step from host text: featurise, upload, scan, exchange, merge, read back.  ``last_e2e_ms`` keeps
+        the wall-clock split of the last call (featurise / upload incl. table kernels / device step / read-back)."""
+        import time
+
+        t0 = time.perf_counter()
         qfb = self.vocab.featurize_packed(data, offsets, mode, grow=False)
         try:
+            t1 = time.perf_counter()
             self.set_resident(qfb)
+            t2 = time.perf_counter()
             s, r = self.topk_resident(k)
-            return s.cpu().numpy(), r.cpu().numpy()
+            import torch
+
+            torch.cuda.current_stream().synchronize()
+            t3 = time.perf_counter()
+            out = s.cpu().numpy(), r.cpu().numpy()
+            t4 = time.perf_counter()
+            self.last_e2e_ms = {"featurize": 1e3 * (t1 - t0), "upload": 1e3 * (t2 - t1), "device_step": 1e3 * (t3 - t2),
+                                "read_back": 1e3 * (t4 - t3)}
+            return out
         finally:
             qfb.close()
 

@@ -36,7 +36,29 @@ from . import sidecar as _sidecar
 from .similarity import FeatureBatch, GfkbIndex, Vocabulary
 
 CANDIDATES = 16  # float32 candidates per query and segment that get re-scored in float64 (>= MATCH_LIMIT)
+MAX_LIMIT = 32   # the fused top-k of the scan holds at most 32 rows per query and segment
+MAX_TF = 65535   # largest term frequency a row may hold (kv_index_append rejects more)
+MAX_FEATURES = (1 << 26) - 2  # vocabulary capacity of the scan layout (kv_index_finalize rejects more)
 PATTERN_NAME = "Citation hallucination without sources"  # services/pattern_detector/app.py:48
+
+
+def check_indexable(text: str, vocab_size: int = 0) -> Optional[str]:
+    """None when ``text`` can be indexed, else the reason.  Called BEFORE a record is persisted: a row the index
+    would reject (a 1- or 2-gram repeated more than 65535 times; a vocabulary past 2^26 features) must never reach
+    failures.jsonl, or every later match/warn -- and every restart -- would fail on it (the reference has no such
+    limits: these are capacity limits of the scan layout, reported to the caller instead of corrupting the store)."""
+    n_tok_max = len(text) // 3 + 1                 # a token is >= 2 word characters + a separator
+    if n_tok_max > MAX_TF:                          # only then can any feature repeat that often: count exactly
+        import re
+        from collections import Counter
+
+        toks = re.findall(r"(?u)\b\w\w+\b", text.lower())
+        grams = Counter(toks) + Counter(zip(toks, toks[1:]))
+        if grams and max(grams.values()) > MAX_TF:
+            return f"a feature of signature_text repeats more than {MAX_TF} times"
+    if vocab_size + 2 * n_tok_max >= MAX_FEATURES:
+        return f"the vocabulary would exceed its capacity of {MAX_FEATURES} features"
+    return None
 
 
 def _iso(dt: datetime) -> str:
@@ -55,6 +77,7 @@ class GfkbStore:
         self.tail_limit = int(tail_limit)
         self._now = now or (lambda: datetime.now(timezone.utc))  # app.py:34-35
         self._lock = threading.RLock()
+        self._quarantine_set: set = set()
         self.records: List[Dict[str, Any]] = []
         self._latest: Dict[Tuple[str, str], int] = {}  # (failure_type, signature_text) -> index of the newest record
         self.vocab = Vocabulary()
@@ -64,7 +87,8 @@ class GfkbStore:
         self._n_indexed = 0       # records[:_n_indexed] are on the device (main + tail)
         self._main_df: Optional[np.ndarray] = None
         self._dirty = False
-        self.stats = {"full_rebuilds": 0, "stat_refreshes": 0, "compactions": 0}
+        self.stats = {"full_rebuilds": 0, "stat_refreshes": 0, "compactions": 0, "quarantined": 0}
+        self.quarantined: List[int] = []  # indices of loaded records that cannot be indexed (they keep their row, with no features)
         if self.path is not None and self.path.exists():
             self.load()
 
@@ -79,8 +103,16 @@ class GfkbStore:
                         rows.append(json.loads(line))
             self._reset(rows)
 
+    def _index_text(self, i: int) -> str:
+        """The text record i is indexed under: its signature_text, or '' (a row that matches nothing) when a record
+        written by another program cannot be indexed -- the store stays usable and the record keeps its row id."""
+        return "" if i in self._quarantine_set else self.records[i]["signature_text"]
+
     def _reset(self, rows: List[Dict[str, Any]]) -> None:
         self.records = list(rows)
+        self.quarantined = [i for i, r in enumerate(self.records) if check_indexable(r["signature_text"]) is not None]
+        self._quarantine_set = set(self.quarantined)
+        self.stats["quarantined"] = len(self.quarantined)
         self._latest = {}
         for i, r in enumerate(self.records):
             self._latest[(r["failure_type"], r["signature_text"])] = i
@@ -94,7 +126,7 @@ class GfkbStore:
         self._main_df = None
         n = len(self.records)
         if n:
-            texts = [r["signature_text"] for r in self.records]
+            texts = [self._index_text(i) for i in range(n)]
             cached = _sidecar.load(self.sidecar_path, texts) if self.sidecar_path is not None else None
             if cached is not None and len(self.vocab) == 0:
                 # cold start from the sidecar: the vocabulary and the first n0 rows come back as arrays
@@ -131,7 +163,7 @@ class GfkbStore:
         """Bring the device index up to date with ``records`` (called lazily before a query)."""
         if not self._dirty and self._n_indexed == len(self.records):
             return
-        pending = [r["signature_text"] for r in self.records[self._n_indexed:]]
+        pending = [self._index_text(i) for i in range(self._n_indexed, len(self.records))]
         n_tail = len(self.records) - self._n_main
         if self._main is None or n_tail > max(self.tail_limit, 0):
             self.stats["compactions"] += self._main is not None
@@ -162,6 +194,9 @@ class GfkbStore:
     # -- upsert (services/gfkb/app.py:104-147) -----------------------------------------------------------------
     def upsert(self, req: Mapping[str, Any]) -> Dict[str, Any]:
         with self._lock:
+            why = check_indexable(req["signature_text"], len(self.vocab))
+            if why is not None:  # refuse BEFORE anything is persisted
+                raise ValueError(f"upsert rejected: {why}")
             key = (req["failure_type"], req["signature_text"])
             idx = self._latest.get(key)  # == the reference's reversed() scan for the newest equal record (app.py:108-112)
             now = _iso(self._now())
@@ -218,6 +253,8 @@ class GfkbStore:
 
     def match_batch(self, signature_texts: Sequence[str], failure_types: Optional[Sequence[Optional[str]]] = None,
                     limit: int = MATCH_LIMIT) -> List[List[dict]]:
+        if limit > MAX_LIMIT:
+            raise ValueError(f"limit {limit} exceeds the {MAX_LIMIT} rows the fused top-k holds per query")
         with self._lock:
             if not self.records:
                 return [[] for _ in signature_texts]  # app.py:82-83

@@ -190,3 +190,14 @@ def test_store_match_and_warn_host_logic_with_canned_candidates(golden, built_li
     w = st.warn_batch([{"app_id": "a", "prompt": q}], threshold=2.0, default_action="silent")[0]
     assert w == {"action": "silent", "confidence": best["score"], "pattern_id": None, "references": [],
                  "message": "No high-similarity match found in GFKB."}
+
+
+def test_store_rejects_unindexable_rows_before_persisting(tmp_path):
+    """A record the scan layout cannot hold must never reach failures.jsonl (it would break every later request and
+    every restart); loading a file that contains one quarantines it instead of failing."""
+    from kakveda_b200 import store as S
+
+    assert S.check_indexable("intent_tags: | prompt_hint:summarize this paper | tools: | env_keys:os") is None
+    assert S.check_indexable("tok " * 70000) is not None               # 'tok' x 70000 > 65535
+    assert S.check_indexable("ab cd", vocab_size=S.MAX_FEATURES) is not None
+    assert S.check_indexable(" ".join(f"w{i}" for i in range(70000))) is None  # long, but no feature repeats
