@@ -137,7 +137,9 @@ struct __align__(1024) DenseSmem {
 __global__ void __launch_bounds__(N_THREADS, 1)
 dense_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c, DenseParams P) {
   extern __shared__ unsigned char smem_raw[];
-  DenseSmem &S = *reinterpret_cast<DenseSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned by an OFFSET into the shared array (not by rounding a generic pointer): the compiler keeps the shared
+  // address space, so list and norm accesses are LDS/STS instead of generic loads / stores
+  DenseSmem &S = *reinterpret_cast<DenseSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // work item = (query tile, row split); consecutive CTAs take consecutive query tiles of the same split, so the
   // CTAs resident at one time stream the same corpus rows (B tiles are shared through L2)

@@ -777,14 +777,11 @@ __global__ void __launch_bounds__(S_WARPS * 32, 2) tfidf_scan_kernel(ScanParams 
           const float dot = s_dotU[qi] + __ull2float_rn(acc_w) * (1.f / 4294967296.f);
           const float corr = s_corrU[qi] - __ull2float_rn(acc_c) * (1.f / 16777216.f);
           const float t = Bc + corr;
-          // current filter: the list's k-th score once it is full, and the global lower bound of the k-th score
+          // optimistic filter (read without the lock): the list's k-th SCORE once it is full, and the global lower bound
+          // of the k-th score.  Scores only ever rise, so a stale value merely lets a few more rows through; rows tying
+          // with it are let through as well -- the exact (score desc, row asc) comparison happens under the lock.
           float filt = __int_as_float(*(volatile int *)&P.gthr[q0 + qi]);
-          int krow = 0x7fffffff;
-          if (*(volatile int *)&s_cnt[qi] == k) {
-            const float ks = *(volatile float *)&s_lscore[qi * k + k - 1];
-            const int kr = *(volatile int *)&s_lrow[qi * k + k - 1];
-            if (ks > filt || (ks == filt && kr < krow)) { filt = ks; krow = kr; }
-          }
+          if (*(volatile int *)&s_cnt[qi] == k) filt = fmaxf(filt, *(volatile float *)&s_lscore[qi * k + k - 1]);
           bool pass = true;
           if (filt > 0.f) {
             const float fq = P.jaccard ? filt * FILTER_SLACK : filt * filt * nq * FILTER_SLACK;
@@ -795,7 +792,7 @@ __global__ void __launch_bounds__(S_WARPS * 32, 2) tfidf_scan_kernel(ScanParams 
           if (pass) {
             sc = pair_score(P.jaccard, dot, nq, t);
             row = P.perm[pos0 + lane];
-            cand = row != s_excl[qi] && (sc > filt || (sc == filt && row < krow));
+            cand = row != s_excl[qi] && sc >= filt;
           }
         }
         const uint32_t cm = __ballot_sync(FULL, cand);
