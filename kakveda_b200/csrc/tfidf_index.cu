@@ -836,7 +836,10 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r, in
   // Pruned mode: bound pass 0 -> seed scan -> bound pass 1 -> scan of the candidates.  Exhaustive mode (small
   // indexes, KAKVEDA_B200_NO_PRUNE=1): every chunk is a candidate of every query.
   const char *env = getenv("KAKVEDA_B200_NO_PRUNE");
-  const int prune = (env && env[0] == '1') ? 0 : (ix->n_chunks >= 512 ? 1 : 0);
+  // Jaccard mode: token sets have no text structure to prune on -- the dense-regime kernel K3 scores every chunk for a
+  // whole scan group at once (KAKVEDA_B200_JACCARD_GENERIC=1 forces the generic bound + scan path)
+  const bool jdense = ix->jaccard && !getenv("KAKVEDA_B200_JACCARD_GENERIC");
+  const int prune = (env && env[0] == '1') || jdense ? 0 : (ix->n_chunks >= 512 ? 1 : 0);
   int64_t n_bsplits, n_ssplits;
   if (prune) {
     n_bsplits = std::max<int64_t>(1, std::min<int64_t>((ix->sm_count + n_tiles - 1) / n_tiles, n_blocks));
@@ -998,6 +1001,33 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r, in
       launches += 1;
     } else {
       SP.list_mode = 2;
+      if (jdense && do_p2) {
+        const int64_t jsplits = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((4LL * ix->sm_count + n_groups - 1) / n_groups, 256),
+                                                                       std::max<int64_t>(1, ix->n_chunks / 64)));
+        KV_CUDA(ix->d_part_s.ensure(jsplits * J_WARPS * n_q * k));
+        KV_CUDA(ix->d_part_r.ensure(jsplits * J_WARPS * n_q * k));
+        JaccardParams JP;
+        JP.blk = ix->d_blk.p; JP.binfo = ix->d_binfo.p; JP.B32 = ix->d_B32.p; JP.perm = ix->d_perm.p;
+        JP.n_chunks = ix->n_chunks; JP.n_rows = ix->n_rows; JP.row_base = ix->row_base;
+        JP.qtab = ix->d_qtab.p; JP.q_nq = qc; JP.q_dotU = qc + n_q; JP.q_excl = SP.q_excl; JP.gthr = ix->d_gthr.p;
+        JP.n_q = n_q; JP.k = k; JP.n_splits = (int)jsplits; JP.part_scores = ix->d_part_s.p; JP.part_rows = ix->d_part_r.p;
+        JP.stats = ix->d_stats.p;
+        static bool jattr[64] = {false};
+        if (!jattr[ix->device & 63]) {
+          KV_CUDA(cudaFuncSetAttribute(jaccard_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jaccard_smem_bytes(32)));
+          jattr[ix->device & 63] = true;
+        }
+        jaccard_scan_kernel<<<dim3((unsigned)n_groups, (unsigned)jsplits), J_WARPS * 32, jaccard_smem_bytes(k), s>>>(JP);
+        KV_CUDA(cudaGetLastError());
+        KV_CUDA(cudaEventRecord(ix->evk[4], s));
+        KV_CUDA(cudaEventRecord(ix->ev[2], s));
+        merge_topk_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, s>>>(ix->d_part_s.p, ix->d_part_r.p, (int)(jsplits * J_WARPS),
+                                                                             n_q, k, n_q * k, n_q * k, ix->d_qperm.p, d_out_s, d_out_r);
+        KV_CUDA(cudaGetLastError());
+        KV_CUDA(cudaEventRecord(ix->evk[5], s));
+        launches += 2;
+        goto after_scan;
+      }
       if (!do_p2) {  // exhaustive mode has no seed phase: empty seed lists
         fill_int_kernel<<<(unsigned)((n_q * k + 255) / 256), 256, 0, s>>>((int *)d_out_s, n_q * k, (int)0xFF800000);
         fill_ll_kernel<<<(unsigned)((n_q * k + 255) / 256), 256, 0, s>>>(d_out_r, n_q * k, -1LL);
@@ -1016,6 +1046,7 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r, in
     KV_CUDA(cudaGetLastError());
     KV_CUDA(cudaEventRecord(ix->evk[5], s));
     launches += 2;
+  after_scan:
     if (ix->batch_null) {
       fill_null_kernel<<<(unsigned)((ix->batch_null * k + 255) / 256), 256, 0, s>>>(ix->d_qperm.p + n_q, (int)ix->batch_null, k,
                                                                                     ix->n_rows, ix->row_base,

@@ -865,6 +865,170 @@ static inline size_t scan_smem_bytes(int k) {
          (size_t)S_WARPS * 2 * 8 + (size_t)GROUP_Q * k * 8 + (size_t)GROUP_Q * 4 * 6 + 16;
 }
 
+// ----------------------------------------------------------------------------------------
+// K3: token-set Jaccard, dense regime.  Random token sets have no text structure, so chunk bounds prune nothing and
+// the per-(query, chunk) scan would redo the probing for every query; here one warp scores a chunk for the 32 queries
+// of its scan group AT ONCE (lane = query).  The group's union table (token -> mask of the queries holding it) sits in
+// shared memory; the lanes probe 32 block entries at a time; every hit's row mask is spread into eight words of four
+// 8-bit counters (lane-parallel) and added by the lanes whose query holds the token -- after the chunk a lane holds
+// |q ∩ row| for all 32 rows as bytes.  Exact integers; score = |∩| / (|q| + |row| - |∩|); per-warp private top-k lists
+// (no locks), merged by K5.  Queries are limited to 64 tokens like everywhere (more: float64 full-scan path).
+// ----------------------------------------------------------------------------------------
+struct JaccardParams {
+  const uint32_t *blk;
+  const BlockInfo *binfo;
+  const float *B32;
+  const int *perm;
+  int64_t n_chunks, n_rows, row_base;
+  const unsigned char *qtab;
+  const float *q_nq, *q_dotU;
+  const int *q_excl;
+  int *gthr;
+  int64_t n_q;
+  int k, n_splits;
+  float *part_scores;  // [n_splits * J_WARPS][n_q][k]
+  long long *part_rows;
+  unsigned long long *stats;
+};
+
+constexpr int J_WARPS = 8;
+constexpr int J_SLOTS = 4096;  // union table of a group: <= 32 x 64 tokens
+
+static inline size_t jaccard_smem_bytes(int k) { return (size_t)J_SLOTS * 8 + (size_t)J_WARPS * 32 * 36 + (size_t)J_WARPS * k * 32 * 8; }
+
+__global__ void __launch_bounds__(J_WARPS * 32, 2) jaccard_scan_kernel(JaccardParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t *s_keys = (uint32_t *)smem_raw;                 // [J_SLOTS]
+  uint32_t *s_qm = s_keys + J_SLOTS;                       // [J_SLOTS] queries of the group holding the token
+  uint32_t *s_hit = s_qm + J_SLOTS;                        // [J_WARPS][32][9]: query mask + 8 spread words
+  float *s_ls = (float *)(s_hit + J_WARPS * 32 * 9);       // [J_WARPS][k][32]
+  int *s_lr = (int *)(s_ls + J_WARPS * P.k * 32);          // [J_WARPS][k][32]
+  const int group = blockIdx.x, split = blockIdx.y, k = P.k;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t q0 = (int64_t)group * GROUP_Q;
+  const int q_count = (int)min((int64_t)GROUP_Q, P.n_q - q0);
+  for (int i = threadIdx.x; i < J_SLOTS; i += blockDim.x) { s_keys[i] = KEY_EMPTY; s_qm[i] = 0; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < q_count * QKEYS; i += blockDim.x) {
+    const int qi = i / QKEYS, sl = i - qi * QKEYS;
+    if (!(P.q_nq[q0 + qi] > 0.f)) continue;
+    const uint32_t key = ((const uint32_t *)(P.qtab + (size_t)(q0 + qi) * QTAB_BYTES))[sl];
+    if (key == KEY_EMPTY) continue;
+    const uint32_t fid = key >> 6;
+    uint32_t h = hash_fid(fid, 12);
+    for (;;) {
+      uint32_t cur = s_keys[h];
+      if (cur == KEY_EMPTY) cur = atomicCAS(&s_keys[h], KEY_EMPTY, fid);
+      if (cur == KEY_EMPTY || cur == fid) break;
+      h = (h + 1) & (J_SLOTS - 1);
+    }
+    atomicOr(&s_qm[h], 1u << qi);
+  }
+  __syncthreads();
+  const bool valid = lane < q_count && P.q_nq[q0 + (lane < q_count ? lane : 0)] > 0.f;
+  const float nq = valid ? P.q_nq[q0 + lane] : 0.f;
+  const float dotU = valid ? P.q_dotU[q0 + lane] : 0.f;
+  const int excl = (valid && P.q_excl) ? P.q_excl[q0 + lane] : -1;
+  float *ls = s_ls + (size_t)warp * k * 32 + lane;  // element j at ls[j * 32]
+  int *lr = s_lr + (size_t)warp * k * 32 + lane;
+  for (int j = 0; j < k; j++) { ls[j * 32] = -INFINITY; lr[j * 32] = 0x7fffffff; }
+  int cnt = 0;
+  float kth = -INFINITY;
+  int kth_row = 0x7fffffff;
+  uint32_t *hit = s_hit + warp * 32 * 9;
+  const uint32_t lt = lanemask_lt();
+  const int64_t c_lo = P.n_chunks * split / P.n_splits, c_hi = P.n_chunks * (split + 1) / P.n_splits;
+  unsigned int done = 0;
+  for (int64_t c = c_lo + warp; c < c_hi; c += J_WARPS) {
+    const BlockInfo bi = P.binfo[c];
+    const int E = bi.n_entries, E4 = (E + 3) & ~3;
+    const uint32_t *words = P.blk + (size_t)bi.off4 * 4, *masks = words + E4;
+    const int64_t pos0 = c * CHUNK_ROWS;
+    const int rows = (int)min((int64_t)CHUNK_ROWS, P.n_rows - pos0);
+    const uint32_t vmask = rows == 32 ? FULL : ((1u << rows) - 1u);
+    const float myB = lane < rows ? P.B32[pos0 + lane] : 0.f;
+    const int myrow = lane < rows ? P.perm[pos0 + lane] : 0x7fffffff;
+    uint32_t cw[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) cw[i] = 0;
+    for (int e0 = 0; e0 < E; e0 += 32) {
+      const int e = e0 + lane;
+      const uint32_t w = e < E ? __ldg(words + e) : PAD_WORD;
+      const uint32_t fid = (w >> 5) & FID_MASK;
+      uint32_t qm = 0;
+      if (fid != FID_NONE) {
+        uint32_t h = hash_fid(fid, 12);
+        for (;;) {
+          const uint32_t key = s_keys[h];
+          if (key == KEY_EMPTY) break;
+          if (key == fid) { qm = s_qm[h]; break; }
+          h = (h + 1) & (J_SLOTS - 1);
+        }
+      }
+      const uint32_t hm = __ballot_sync(FULL, qm != 0);
+      if (hm == 0) continue;
+      if (qm) {
+        const uint32_t m = (w & W_ALL) ? vmask : __ldg(masks + e);
+        uint32_t *o = hit + __popc(hm & lt) * 9;
+        o[0] = qm;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[1 + i] = (((m >> (4 * i)) & 0xFu) * 0x00204081u) & 0x01010101u;  // 4 bits -> 4 bytes
+      }
+      __syncwarp();
+      const int nh = __popc(hm);
+      for (int hh = 0; hh < nh; hh++) {
+        const uint32_t *o = hit + hh * 9;
+        if ((o[0] >> lane) & 1u) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) cw[i] += o[1 + i];
+        }
+      }
+      __syncwarp();
+    }
+    done++;
+    // 32 rows of the chunk for this lane's query
+    float filt = kth;
+    if (valid) filt = fmaxf(filt, __int_as_float(__ldcg(&P.gthr[q0 + lane])));
+#pragma unroll
+    for (int r = 0; r < 32; r++) {
+      const float t = __shfl_sync(FULL, myB, r);
+      const int row = __shfl_sync(FULL, myrow, r);
+      if (r >= rows || !valid || row == excl) continue;
+      const float inter = dotU + (float)((cw[r >> 2] >> ((r & 3) * 8)) & 0xFFu);
+      const float uni = nq + t - inter;
+      if (!(inter >= filt * uni * FILTER_SLACK)) continue;  // pre-test without division (filt = -inf passes everything)
+      const float sc = uni > 0.f ? __fdiv_rn(inter, uni) : 0.f;
+      bool take = cnt < k || sc > kth || (sc == kth && row < kth_row);
+      if (!take || sc < filt) continue;
+      int pos = cnt < k ? cnt++ : k - 1;
+      while (pos > 0 && (ls[(pos - 1) * 32] < sc || (ls[(pos - 1) * 32] == sc && lr[(pos - 1) * 32] > row))) {
+        ls[pos * 32] = ls[(pos - 1) * 32];
+        lr[pos * 32] = lr[(pos - 1) * 32];
+        pos--;
+      }
+      ls[pos * 32] = sc;
+      lr[pos * 32] = row;
+      if (cnt == k) {
+        kth = ls[(k - 1) * 32];
+        kth_row = lr[(k - 1) * 32];
+        filt = fmaxf(filt, kth);
+        if (kth > 0.f) atomicMax(&P.gthr[q0 + lane], __float_as_int(kth));
+      }
+    }
+  }
+  // publish this warp's partial lists
+  const int part = split * J_WARPS + warp;
+  if (lane < q_count) {
+    for (int j = 0; j < k; j++) {
+      const size_t o = ((size_t)part * P.n_q + (q0 + lane)) * k + j;
+      const bool used = j < cnt;
+      P.part_scores[o] = used ? ls[j * 32] : -INFINITY;
+      P.part_rows[o] = used ? (long long)(P.row_base + lr[j * 32]) : -1LL;
+    }
+  }
+  if (lane == 0 && P.stats) atomicAdd(&P.stats[0], (unsigned long long)done * (unsigned long long)q_count);
+}
+
 // seeds of the first bound pass -> fixed-stride candidate lists: query slot i holds n_seed chunk ids (-1: none)
 __global__ void seeds_to_lists_kernel(const int *__restrict__ seeds, int64_t n_q, int n_seed, uint2 *direct,
                                       uint32_t *list_count) {
