@@ -562,11 +562,11 @@ def run_ours(a):
                                               "frac_of_bf16_sustained_peak": 2.0 * dn * dn * dd / (min(ams) / 1e3) / 1e12 / tsust,
                                               "rows_per_s": dn / (min(ams) / 1e3),
                                               "note": "BASELINE configs[3]: every row's 32 nearest other rows; full N x N (symmetry not exploited); parity unpinned"},
-            "k3_jaccard_1M_sets_2048_queries": {"kernel": "tfidf_bound_kernel + tfidf_scan_kernel (Jaccard mode)", "rows": jn, "queries": jq, "ms": min(jms),
+            "k3_jaccard_1M_sets_2048_queries": {"kernel": "jaccard_scan_kernel", "rows": jn, "queries": jq, "ms": min(jms),
                                                 "queries_per_s": jq / (min(jms) / 1e3), "avg_tokens_per_row": jentries / jn,
                                                 "bytes_per_row": 4.0 * jentries / jn + 4.0,
-                                                "note": "random Zipf token sets have no text structure to prune on: close to an exhaustive scan; "
-                                                        "bit-exact vs Python sets in tests; parity unpinned"},
+                                                "note": "K3 jaccard_scan_kernel (dense regime: one warp scores a chunk for the 32 queries of a scan group, byte-packed row counters); "
+                                                        "random Zipf token sets have no text structure to prune on; bit-exact vs Python sets in tests; parity unpinned"},
             "cfg0_1k_x_128_reference_in_full": {"gpu_ms_host_text_to_result": c1_gpu_s * 1e3, "reference_ms_128_sequential_score_calls": c1_ref_s * 1e3,
                                                 "speedup": c1_ref_s / c1_gpu_s, "top16_scores_match_reference_rtol_1e-5": c1_ok,
                                                 "note": "BASELINE configs[0]; GPU time = GfkbIndex.topk() from host strings (featurise, upload, exhaustive scan, read back); "
@@ -583,6 +583,105 @@ def run_ours(a):
                                            "frac_of_hbm_peak": n_hash * 8 / (min(hms) / 1e3) / 1e9 / peak,
                                            "note": "8 B/row; random 64-bit fingerprints (parity unpinned)"},
         }
+
+    # ---- secondary configs that need several GPUs (every rank takes part; short: a few seconds each) ----
+    secondary_multi = None
+    if world > 1 and not a.no_secondary:
+        from kakveda_b200.dist import ShardedDense, ShardedJaccard, shard_bounds
+        secondary_multi = {}
+        tsust = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+        dd, d10, dq = 768, 10_000_000, 100_000
+
+        def dense_rows(count, seed):
+            g = torch.Generator(device=dev).manual_seed(seed)
+            raw = torch.randint(0, 2**16, (count, dd), generator=g, device=dev, dtype=torch.int32)
+            bits = (raw & 0x807F) | ((120 + ((raw >> 7) & 7)) << 7)
+            return torch.where(bits >= 32768, bits - 65536, bits).to(torch.int16).view(torch.bfloat16).contiguous()
+
+        # BASELINE configs[2] read as dense embeddings, AS SPECIFIED: 10M x 768 bf16 row-sharded, 100k queries, fused top-16
+        lo, hi = shard_bounds(d10, world, rank)
+        sd = ShardedDense(dd, device=local, rank=rank, world=world)
+        sd.build(dense_rows(hi - lo, 100 + rank), d10)
+        dqs = dense_rows(dq, 999)
+        sd.topk(dqs, 16)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        ds_, dr_ = sd.topk(dqs, 16)
+        ev1.record()
+        barrier()
+        dms = max_over_ranks(ev0.elapsed_time(ev1))
+        kms = max_over_ranks(sd.index.last_timing()[0])
+        secondary_multi["k2_dense_cosine_10Mx768_100k_queries_sharded"] = {
+            "n_gpus": world, "ms_step_max_over_ranks": dms, "ms_kernel_max_over_ranks": kms, "flops": 2.0 * d10 * dq * dd,
+            "achieved_tflops_whole_job": 2.0 * d10 * dq * dd / (dms / 1e3) / 1e12,
+            "frac_of_bf16_sustained_peak_x_gpus": 2.0 * d10 * dq * dd / (dms / 1e3) / 1e12 / (tsust * world),
+            "queries_per_s": dq / (dms / 1e3), "result_checksum": int(dr_.sum().item()),
+            "note": "SURVEY 8(d) cfg3 as specified: rows sharded over the GPUs, queries replicated, K2 per shard, one all-gather of partial top-k + K5; "
+                    "step = kernel + exchange + merge (CUDA events, max over ranks); parity unpinned"}
+        sd.index.close()
+        del sd, dqs, ds_, dr_
+        torch.cuda.empty_cache()
+        # BASELINE configs[4] AS SPECIFIED (4 GPUs): 5M token sets (Zipf ids over 2^20, ~64 tokens), Q = 10k, top-16
+        if world == 4 or os.environ.get("KAKVEDA_BENCH_CFG5") == "1":
+            jn, jq, jv, draws = 5_000_000, 10_000, 1 << 20, 112
+
+            def token_sets(count, seed):   # Zipf-like ids by inverse-CDF sampling on the device, sorted + deduplicated per set
+                g = torch.Generator(device=dev).manual_seed(seed)
+                out_ip, out_ids = [np.zeros(1, dtype=np.int64)], []
+                for b0 in range(0, count, 500_000):
+                    nb = min(500_000, count - b0)
+                    u = torch.rand((nb, draws), generator=g, device=dev, dtype=torch.float64)
+                    ids_ = (u.pow(-10.0).floor() - 1).clamp_(0, jv - 1).to(torch.int64)   # P(id >= x) ~ x^-0.1: Zipf(1.1)
+                    ids_, _ = ids_.sort(dim=1)
+                    keep = torch.ones_like(ids_, dtype=torch.bool)
+                    keep[:, 1:] = ids_[:, 1:] != ids_[:, :-1]
+                    keep &= keep.cumsum(dim=1) <= 64          # sets are capped at 64 tokens (the scan's per-query table)
+                    cnt = keep.sum(dim=1).cpu().numpy()
+                    out_ids.append(ids_[keep].to(torch.int32).cpu().numpy().astype(np.uint32))
+                    out_ip.append(out_ip[-1][-1] + np.cumsum(cnt))
+                return np.concatenate(out_ip).astype(np.int64), np.concatenate(out_ids)
+
+            lo, hi = shard_bounds(jn, world, rank)
+            t0 = time.perf_counter()
+            lip, lids = token_sets(hi - lo, 7000 + rank)
+            qip_, qid_ = token_sets(jq, 424242)
+            sj = ShardedJaccard(jv, device=local, rank=rank, world=world)
+            sj.build_local_csr(lip, lids, jn)
+            t_build = time.perf_counter() - t0
+            sj.topk_csr(qip_, qid_, 16)
+            barrier()
+            t0 = time.perf_counter()
+            js, jr, ji, ju = sj.topk_csr(qip_, qid_, 16)
+            torch.cuda.synchronize()
+            j_e2e = max_over_ranks(time.perf_counter() - t0)
+            j_kernel = max_over_ranks(sj.index.last_timing_ms()[1])
+            # bit-exact check: this rank's first 100k sets as their own index vs Python sets, 8 queries
+            from kakveda_b200 import JaccardIndex
+            sub_n = min(100_000, hi - lo)
+            sub = JaccardIndex(jv, device=local)
+            sub.add_csr(lip[: sub_n + 1], lids[: lip[sub_n]])
+            sub.finalize()
+            ss, sr, si, su = sub.topk_csr(qip_[:9], qid_[: qip_[8]], 16)
+            sub.close()
+            rsets = [set(lids[lip[i]:lip[i + 1]].tolist()) for i in range(sub_n)]
+            exact = True
+            for qi in range(8):
+                qs_ = set(qid_[qip_[qi]:qip_[qi + 1]].tolist())
+                ref = sorted(((len(qs_ & r_) / max(1, len(qs_ | r_)), -i) for i, r_ in enumerate(rsets)), reverse=True)[:16]
+                exact &= [-i for _, i in ref] == sr[qi].tolist()
+                exact &= all(len(qs_ & rsets[int(r_)]) == int(si[qi, j]) and len(qs_ | rsets[int(r_)]) == int(su[qi, j]) for j, r_ in enumerate(sr[qi]))
+            exact_all = max_over_ranks(0.0 if exact else 1.0) == 0.0
+            avg_tokens = float(lip[-1]) / (hi - lo)
+            secondary_multi["k3_jaccard_5M_sets_10k_queries"] = {
+                "n_gpus": world, "sets": jn, "queries": jq, "avg_tokens_per_set": avg_tokens, "ms_kernels_max_over_ranks": j_kernel,
+                "ms_end_to_end_max_over_ranks": j_e2e * 1e3, "queries_per_s_kernels": jq / (j_kernel / 1e3), "queries_per_s_end_to_end": jq / j_e2e,
+                "bit_exact_vs_python_sets_top16_of_100k_subsample": bool(exact_all), "shard_build_s": t_build,
+                "result_checksum": int(jr.sum()),
+                "note": "BASELINE configs[4] / SURVEY 8(d) cfg5: sets row-sharded, K3 dense-regime Jaccard kernel per shard (exact integer counts), "
+                        "all-gather of partial top-k + K5, max-reduce of the (inter, union) integers; end to end = host CSR in, merged result on the host; "
+                        "sets capped at 64 tokens; parity unpinned (oracle: Python sets)"}
+            sj.index.close()
 
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
@@ -608,7 +707,7 @@ def run_ours(a):
             "e2e": {"value": a.queries / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s * 1e3, "rank0_split_ms": getattr(shard, "last_e2e_ms", None)},
             "gpu_launches": int(lay["kernel_launches"] + (1 if world > 1 else 0)) * a.steps,
-            "roofline": roofline, "rank_stats": rank_stats, "parity_in_run": parity, "cpu_baseline": cpu, "secondary": secondary,
+            "roofline": roofline, "rank_stats": rank_stats, "parity_in_run": parity, "cpu_baseline": cpu, "secondary": secondary, "secondary_multi_gpu": secondary_multi,
         }
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:

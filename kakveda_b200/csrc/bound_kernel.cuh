@@ -490,7 +490,7 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
 
 // ----------------------------------------------------------------------------------------
 // K1b-B2: candidate lists from the stored 8-bit bound codes (second pass without recomputing the bounds).  One CTA =
-// one scan group (32 queries = the lanes) x one chunk range; a warp reads, per query, 64 codes (one 64-byte access) and
+// one scan group (32 queries = the lanes) x one chunk range; a warp reads, per query, 32 codes (one 32-byte sector) and
 // compares them with the query's threshold code; ballots give the group's query mask per chunk; non-empty masks are
 // appended to the group's paged candidate list exactly as K1b-B's pass 1 does.  HBM-bound: n_q x chunks bytes read once.
 // ----------------------------------------------------------------------------------------
@@ -533,50 +533,42 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) tfidf_select_kernel(SelectPara
   const int64_t c_lo = (n_blocks * bsplit / P.n_bsplits) * B_BN, c_hi = min(P.n_chunks, (n_blocks * (bsplit + 1) / P.n_bsplits) * B_BN);
   const unsigned char *row = P.ubq + (size_t)min(slot, P.n_q - 1) * P.ubq_stride;
   unsigned int n_pairs = 0, n_recs = 0;
-  for (int64_t c64 = c_lo + 64 * warp; c64 < c_hi; c64 += 64 * SEL_WARPS) {
-    // 64 codes = one 64-byte DRAM access per query row; the two halves are handled one after the other
-    const uint4 *src = reinterpret_cast<const uint4 *>(row + c64);
-    const uint4 l0 = __ldcs(src), l1 = __ldcs(src + 1), l2 = __ldcs(src + 2), l3 = __ldcs(src + 3);
+  for (int64_t c = c_lo + 32 * warp; c < c_hi; c += 32 * SEL_WARPS) {
+    const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(row + c)), b = __ldcs(reinterpret_cast<const uint4 *>(row + c + 16));
+    const uint32_t wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t mymask = 0;
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
-      const int64_t c = c64 + 32 * half;
-      if (c >= c_hi) break;
-      const uint4 a = half ? l2 : l0, b = half ? l3 : l1;
-      const uint32_t wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-      uint32_t mymask = 0;
-#pragma unroll
-      for (int j = 0; j < 32; j++) {
-        const uint32_t code = (wds[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
-        const uint32_t m = __ballot_sync(FULL, q_ok && code >= tcode && c + j < c_hi);
-        if (lane == j) mymask = m;
+    for (int j = 0; j < 32; j++) {
+      const uint32_t code = (wds[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+      const uint32_t m = __ballot_sync(FULL, q_ok && code >= tcode && c + j < c_hi);
+      if (lane == j) mymask = m;
+    }
+    const uint32_t am = __ballot_sync(FULL, mymask != 0);
+    if (am) {
+      const int n = __popc(am);
+      unsigned int bpos = 0;
+      if (lane == 0) {
+        bpos = atomicAdd(&s_count, (unsigned int)n);
+        for (unsigned int pg = (bpos + PAGE_RECS - 1) / PAGE_RECS; pg * PAGE_RECS < bpos + n; pg++) {
+          unsigned int np = atomicAdd(P.pool_next, 1u);
+          if (np >= P.pool_pages) { *P.overflow = 1; np = 0; }
+          P.list_pages[(size_t)list * P.max_pages + pg] = np;
+          __threadfence_block();
+          *(volatile int *)&s_pages[pg] = (int)np;
+        }
       }
-      const uint32_t am = __ballot_sync(FULL, mymask != 0);
-      if (am) {
-        const int n = __popc(am);
-        unsigned int bpos = 0;
-        if (lane == 0) {
-          bpos = atomicAdd(&s_count, (unsigned int)n);
-          for (unsigned int pg = (bpos + PAGE_RECS - 1) / PAGE_RECS; pg * PAGE_RECS < bpos + n; pg++) {
-            unsigned int np = atomicAdd(P.pool_next, 1u);
-            if (np >= P.pool_pages) { *P.overflow = 1; np = 0; }
-            P.list_pages[(size_t)list * P.max_pages + pg] = np;
-            __threadfence_block();
-            *(volatile int *)&s_pages[pg] = (int)np;
-          }
-        }
-        bpos = __shfl_sync(FULL, bpos, 0);
-        if (mymask) {
-          const unsigned int pos = bpos + (unsigned int)__popc(am & lanemask_lt());
-          const unsigned int pg = pos / PAGE_RECS;
-          int page;
-          while ((page = *(volatile int *)&s_pages[pg]) < 0) {}
-          uint2 rec;
-          rec.x = (uint32_t)(c + lane);
-          rec.y = mymask;
-          P.pool[(size_t)page * PAGE_RECS + (pos % PAGE_RECS)] = rec;
-          n_pairs += (unsigned int)__popc(mymask);
-          n_recs++;
-        }
+      bpos = __shfl_sync(FULL, bpos, 0);
+      if (mymask) {
+        const unsigned int pos = bpos + (unsigned int)__popc(am & lanemask_lt());
+        const unsigned int pg = pos / PAGE_RECS;
+        int page;
+        while ((page = *(volatile int *)&s_pages[pg]) < 0) {}
+        uint2 rec;
+        rec.x = (uint32_t)(c + lane);
+        rec.y = mymask;
+        P.pool[(size_t)page * PAGE_RECS + (pos % PAGE_RECS)] = rec;
+        n_pairs += (unsigned int)__popc(mymask);
+        n_recs++;
       }
     }
   }

@@ -747,8 +747,8 @@ __global__ void __launch_bounds__(S_WARPS * 32, 2) tfidf_scan_kernel(ScanParams 
             uint32_t tf = w & 31u;
             if (tf == TF_OVF) tf = ovf_lookup(P.ovf_keys, P.ovf_vals, P.n_ovf, chunk_cur, (uint32_t)e);
             const QFeat f = feats[idx];
-            const unsigned long long ww = (((unsigned long long)f.w_hi << 32) | f.w_lo) * (unsigned long long)tf;
-            const unsigned long long cc = (unsigned long long)f.cq * (unsigned long long)tf * (unsigned long long)tf;
+            unsigned long long ww = ((unsigned long long)f.w_hi << 32) | f.w_lo, cc = (unsigned long long)f.cq;
+            if (tf != 1u) { ww *= (unsigned long long)tf; cc *= (unsigned long long)tf * (unsigned long long)tf; }
             ScanHit hrec;
             hrec.m = (w & W_ALL) ? valid : masks[e];
             hrec.w_lo = (uint32_t)ww; hrec.w_hi = (uint32_t)(ww >> 32);
@@ -1041,7 +1041,10 @@ __global__ void seeds_to_lists_kernel(const int *__restrict__ seeds, int64_t n_q
   uint2 rec;
   rec.x = c >= 0 ? (uint32_t)c : 0u;
   rec.y = c >= 0 ? (1u << (q % GROUP_Q)) : 0u;
-  direct[i] = rec;
+  // seed-major inside a group: consecutive records belong to different queries, so the warps of a scan CTA do not
+  // queue on one query's list lock
+  const int64_t g = q / GROUP_Q, j = i - q * n_seed;
+  direct[(g * n_seed + j) * GROUP_Q + (q % GROUP_Q)] = rec;
 }
 
 // ----------------------------------------------------------------------------------------

@@ -400,6 +400,15 @@ class ShardedJaccard:
         self.index.add_csr(ip - ip[0], np.ascontiguousarray(ids[ip[0]:ip[-1]], dtype=np.uint32))
         self.index.finalize()
 
+    def build_local_csr(self, indptr: np.ndarray, ids: np.ndarray, n_global: int) -> None:
+        """``indptr``/``ids``: ONLY this rank's rows (global rows [n*r/W, n*(r+1)/W) of an n_global-row corpus)."""
+        lo, hi = shard_bounds(n_global, self.world, self.rank)
+        assert len(indptr) - 1 == hi - lo
+        self.n_global = n_global
+        self.index = self._cls(self.vocab_size, device=self.device, row_base=lo)
+        self.index.add_csr(np.ascontiguousarray(indptr, dtype=np.int64), np.ascontiguousarray(ids, dtype=np.uint32))
+        self.index.finalize()
+
     def topk_csr(self, indptr: np.ndarray, ids: np.ndarray, k: int = 16):
         """(scores float32, rows int64, inter int32, union int32), each [Q,k], identical on every rank."""
         import torch
