@@ -71,6 +71,11 @@ struct BlockLayout {
   std::vector<__half> Uf;                     // [n_chunks_pad][NF] largest tf of the frequent features per chunk
   std::vector<unsigned short> fslot2;         // [V] bit row of a second-class feature, 0xFFFF otherwise
   std::vector<uint32_t> Ubt;                  // [n_chunks_pad / 64][NF2][2][2]: bit c % 64 of plane 0 / 1 = present in chunk c with tf >= 1 / >= 2
+  // rare features per 64-chunk block (the bound kernel's inverted join): presence bitmap + open-addressing table
+  std::vector<uint32_t> rbloom;               // [n_blocks][RB_BITS / 32]
+  std::vector<uint32_t> rt_keys;              // all tables: feature id << 5 | largest tf in the block (31: see tfmax), KEY_EMPTY
+  std::vector<unsigned long long> rt_masks;   // ... chunks of the block holding the feature
+  std::vector<uint32_t> rt_off, rt_size;      // [n_blocks] first slot / slots of a block's table
   int64_t n_entries = 0, n_rare_entries = 0, n_f2_entries = 0;
 };
 
@@ -224,6 +229,60 @@ inline void build_blocks(const int64_t *indptr, const uint32_t *ids, const uint1
   {
     int64_t o = 0;
     for (int t = 0; t < T; t++) { L.part_off[(size_t)t] = o; o += (int64_t)L.parts[(size_t)t].size(); }
+  }
+  // pass 3: per 64-chunk block the inverted index of its rare entries
+  {
+    const int64_t n_blocks = L.n_chunks_pad / 64;
+    L.rbloom.assign((size_t)n_blocks * (RB_BITS / 32), 0u);
+    L.rt_off.assign((size_t)n_blocks, 0);
+    L.rt_size.assign((size_t)n_blocks, 1);
+    auto word_ptr = [&](int64_t off_words) -> const uint32_t * {  // position in the per-thread parts
+      size_t tt = (size_t)(std::upper_bound(L.part_off.begin(), L.part_off.end(), off_words) - L.part_off.begin()) - 1;
+      return L.parts[tt].data() + (off_words - L.part_off[tt]);
+    };
+    std::vector<std::vector<std::pair<uint32_t, unsigned long long>>> tabs((size_t)n_blocks);  // (key, mask) per block, grouped
+    parallel_for(n_blocks, T, [&](int, int64_t b0, int64_t b1) {
+      std::vector<unsigned long long> es;  // fid << 16 | tf5 << 8 | chunk in block
+      for (int64_t b = b0; b < b1; b++) {
+        es.clear();
+        for (int64_t c = b * 64; c < std::min<int64_t>(L.n_chunks, b * 64 + 64); c++) {
+          const BlockInfo bi = L.binfo[(size_t)c];
+          const uint32_t *w = word_ptr((int64_t)bi.off4 * 4);
+          for (int e = 0; e < bi.n_rare; e++)
+            es.push_back(((unsigned long long)((w[e] >> 5) & FID_MASK) << 16) | ((unsigned long long)(w[e] & 31u) << 8) | (unsigned long long)(c - b * 64));
+        }
+        std::sort(es.begin(), es.end());
+        auto &tab = tabs[(size_t)b];
+        for (size_t i = 0; i < es.size();) {
+          const uint32_t f = (uint32_t)(es[i] >> 16);
+          uint32_t tfm = 0;
+          unsigned long long mask = 0;
+          while (i < es.size() && (uint32_t)(es[i] >> 16) == f) { tfm = std::max<uint32_t>(tfm, (uint32_t)((es[i] >> 8) & 31u)); mask |= 1ULL << (es[i] & 63u); i++; }
+          tab.emplace_back((f << 5) | tfm, mask);
+          const uint32_t bb = rb_bit(f);
+          L.rbloom[(size_t)b * (RB_BITS / 32) + (bb >> 5)] |= 1u << (bb & 31u);
+        }
+        L.rt_size[(size_t)b] = (uint32_t)std::max<size_t>(4, tab.size() + tab.size() / 2 + 1);
+      }
+    });
+    int64_t total = 0;
+    for (int64_t b = 0; b < n_blocks; b++) { L.rt_off[(size_t)b] = (uint32_t)total; total += L.rt_size[(size_t)b]; }
+    L.rt_keys.assign((size_t)total, KEY_EMPTY);
+    L.rt_masks.assign((size_t)total, 0ULL);
+    parallel_for(n_blocks, T, [&](int, int64_t b0, int64_t b1) {
+      for (int64_t b = b0; b < b1; b++) {
+        const uint32_t size = L.rt_size[(size_t)b];
+        uint32_t *keys = L.rt_keys.data() + L.rt_off[(size_t)b];
+        unsigned long long *masks = L.rt_masks.data() + L.rt_off[(size_t)b];
+        for (auto &e : tabs[(size_t)b]) {
+          uint32_t h = rt_slot(e.first >> 5, size);
+          while (keys[h] != KEY_EMPTY) h = h + 1 == size ? 0 : h + 1;
+          keys[h] = e.first;
+          masks[h] = e.second;
+        }
+        std::vector<std::pair<uint32_t, unsigned long long>>().swap(tabs[(size_t)b]);
+      }
+    });
   }
   L.ovf.clear();
   L.n_entries = L.n_rare_entries = L.n_f2_entries = 0;

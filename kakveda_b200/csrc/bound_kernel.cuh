@@ -14,9 +14,11 @@
 //     many queries of a tile) are kept per 128-chunk block as TRANSPOSED presence bitmaps Ubt[feature][128 chunk bits]
 //     (32 KB, one bulk-async copy per block): a query thread reads ONE word per feature of its own list (<= 16) and has
 //     that feature's presence in its 32 chunk columns -- lane-parallel, no atomics;
-//   * the sum over the remaining RARE features is a join: the worker warps probe each chunk's non-frequent block
-//     entries first in a presence bitmap, then in the tile's rare-feature table (shared memory); the few hits
-//     (~1.4 per chunk and tile) go to per-query hit slots;
+//   * the remaining RARE features are joined the other way round: every 64-chunk block carries (built at finalize) a
+//     presence bitmap and an open-addressing table of its rare features (feature -> mask of the block's chunks holding
+//     it, largest tf); each query looks ITS OWN <= 32 rare features up -- one shared-memory bit test per (query,
+//     feature, block), and only on a hit a probe of the block's table in L2 -- and adds weight x tf into
+//     R[chunk][query] (shared memory).  1.8k bit tests per tile and block instead of 5.4k entry probes;
 //   * epilogue (16 warps, thread = query, tcgen05.ld of 32 chunk columns): bound vs the query's threshold.
 //     pass 0 keeps, per thread, the 4 best chunks by bound (seeds: K1b-S scores them first, which gives every query a
 //     close lower bound theta0 of its k-th best score); pass 1 appends {chunk, mask of the group's surviving queries}
@@ -105,7 +107,12 @@ struct BoundParams {
   const uint32_t *ovf_vals;
   int n_ovf;
   int64_t n_chunks, n_q;
-  const unsigned char *rtab;                              // [n_tiles][RTAB_BYTES]
+  const uint2 *q3list;                                    // [n_tiles][Q3CAP][TILE_Q] rare (feature, weight) lists of the queries
+  const uint32_t *rbloom;                                 // [n_blocks][RB_BITS / 32]
+  const uint32_t *rt_keys;                                // per-block rare tables: feature << 5 | largest tf (31: tfmax[])
+  const unsigned long long *rt_masks;                     // ... chunks of the block holding the feature
+  const uint32_t *rt_off, *rt_size;                       // [n_blocks]
+  const uint32_t *tfmax;                                  // [V] largest tf of a feature (for entries whose 5-bit tf overflowed)
   const uint2 *q2list;                                    // [n_tiles][Q2CAP][TILE_Q]
   const uint32_t *ubt;                                    // [n_blocks][NF2][2][B_BN / 32]
   const float *q_nq, *q_dotS, *q_dotX, *q_corrS;          // [n_q] (sorted query order)
@@ -131,12 +138,13 @@ struct BoundParams {
 struct __align__(1024) BoundSmem {
   unsigned char a[B_KSLICES][B_A_SLICE_BYTES];   // the tile's weight rows, resident
   unsigned char b[B_STAGES][B_B_SLICE_BYTES];    // chunk slices in flight
-  uint32_t ubt[NF2][2][B_BN / 32];               // second-class bitmaps (tf >= 1, tf >= 2) of the current block of chunks
+  uint32_t ubt[2][NF2][2][B_BN / 32];            // second-class bitmaps (tf >= 1, tf >= 2) of the current / next block of chunks
+  uint32_t rbm[2][RB_BITS / 32];                 // rare-feature presence bitmap of the current / next block
   float R[B_BN][TILE_Q];                         // rare part of the dot bound, [chunk][query]
-  unsigned char rtab[RTAB_BYTES];
   uint2 q2[Q2CAP][TILE_Q];                       // the queries' second-class lists (bit row | (tfmax - 1) << 16, weight)
+  uint2 q3[Q3CAP][TILE_Q];                       // the queries' rare lists (feature id, weight)
   float minB[2][B_BN];
-  uint64_t full_bar[B_STAGES], empty_bar[B_STAGES], a_bar, ubt_bar, tmem_full[2], tmem_empty[2];
+  uint64_t full_bar[B_STAGES], empty_bar[B_STAGES], a_bar, blk_bar[2], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
   unsigned int lcount[4];
   int pages[1];  // [4][max_pages], sized at launch
@@ -158,7 +166,8 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < B_STAGES; i++) { mbar_init(&S.full_bar[i], 1); mbar_init(&S.empty_bar[i], 1); }
     mbar_init(&S.a_bar, 1);
-    mbar_init(&S.ubt_bar, 1);
+    mbar_init(&S.blk_bar[0], 1);
+    mbar_init(&S.blk_bar[1], 1);
     for (int i = 0; i < 2; i++) { mbar_init(&S.tmem_full[i], 1); mbar_init(&S.tmem_empty[i], B_WORKERS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -166,13 +175,13 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_addr(&S.tmem_base)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  {  // rare-feature table and second-class lists of the tile, hit slots, list state
-    const uint4 *src = (const uint4 *)(P.rtab + (size_t)tile * RTAB_BYTES);
-    uint4 *dst = (uint4 *)S.rtab;
-    for (int i = threadIdx.x; i < RTAB_BYTES / 16; i += B_THREADS) dst[i] = src[i];
+  {  // second-class and rare lists of the tile's queries, R = 0, list state
     const uint4 *src2 = (const uint4 *)(P.q2list + (size_t)tile * Q2CAP * TILE_Q);
     uint4 *dst2 = (uint4 *)&S.q2[0][0];
     for (int i = threadIdx.x; i < Q2CAP * TILE_Q / 2; i += B_THREADS) dst2[i] = src2[i];
+    const uint4 *src3 = (const uint4 *)(P.q3list + (size_t)tile * Q3CAP * TILE_Q);
+    uint4 *dst3 = (uint4 *)&S.q3[0][0];
+    for (int i = threadIdx.x; i < Q3CAP * TILE_Q / 2; i += B_THREADS) dst3[i] = src3[i];
     float4 *r4 = (float4 *)&S.R[0][0];
     for (int i = threadIdx.x; i < B_BN * TILE_Q / 4; i += B_THREADS) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = threadIdx.x; i < 4 * P.max_pages; i += B_THREADS) S.pages[i] = -1;
@@ -237,11 +246,6 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     const bool q_ok = nq > 0.f;
     const float base = q_ok ? P.q_dotS[slot] + P.q_dotX[slot] : 0.f;
     const float corrS = q_ok ? P.q_corrS[slot] : 0.f;
-    const uint32_t *rt_keys = (const uint32_t *)S.rtab;
-    const uint32_t *rt_wq = rt_keys + RT_SLOTS;
-    const uint32_t *rt_multi = rt_wq + RT_SLOTS;
-    const uint32_t *rt_bm = rt_multi + 4 * RT_MULTI;
-    const bool probe_f2 = rt_bm[RT_BITMAP_BITS / 32] != 0;  // some query's second-class list overflowed into the table
     const int list = (tile * 4 + qtr) * P.n_bsplits + bsplit;
     int *my_pages = S.pages + qtr * P.max_pages;
     float sm[B_SEEDS];
@@ -249,85 +253,52 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
 #pragma unroll
     for (int i = 0; i < B_SEEDS; i++) { sm[i] = -1.f; sc[i] = -1; }
     unsigned int n_pairs = 0, n_recs = 0;
-    if (threadIdx.x == 0 && blk_lo < blk_hi) {  // second-class bitmaps of the first block
-      mbar_expect_tx(&S.ubt_bar, sizeof(S.ubt));
-      bulk_copy_g2s(&S.ubt[0][0][0], P.ubt + (size_t)blk_lo * (sizeof(S.ubt) / 4), sizeof(S.ubt), &S.ubt_bar);
-    }
+    // per-block side data (second-class bitmaps + rare presence bitmap): bulk-async copies, double buffered -- block
+    // b + 1 is fetched while block b is processed
+    auto fetch_block = [&](int64_t bk2, int buf) {
+      mbar_expect_tx(&S.blk_bar[buf], (uint32_t)(sizeof(S.ubt[0]) + sizeof(S.rbm[0])));
+      bulk_copy_g2s(&S.ubt[buf][0][0][0], P.ubt + (size_t)bk2 * (sizeof(S.ubt[0]) / 4), sizeof(S.ubt[0]), &S.blk_bar[buf]);
+      bulk_copy_g2s(&S.rbm[buf][0], P.rbloom + (size_t)bk2 * (RB_BITS / 32), sizeof(S.rbm[0]), &S.blk_bar[buf]);
+    };
+    if (threadIdx.x == 0 && blk_lo < blk_hi) fetch_block(blk_lo, 0);
     int64_t it = 0;
     for (int64_t bk = blk_lo; bk < blk_hi; bk++, it++) {
       const int as = (int)(it & 1);
       const uint32_t aphase = (uint32_t)((it >> 1) & 1);
       const int64_t c0 = bk * B_BN;
-      // ---- join: non-frequent entries of this warp's chunks against the tile's rare-feature table ----
-      // The warp owns chunks warp, warp + 16, ... of the block.  Lane l first fetches the directory entry of the l-th
-      // of them; the first 128 words of a chunk are loaded one chunk ahead (registers), so that the L2 latency of
-      // chunk j+1 hides behind the probing of chunk j.  An entry first tests the tile's presence bitmap (one
-      // shared-memory load rejects ~98 % of them); only then the table is probed.  A hit adds its weight to R[chunk]
-      // for every query holding the feature.  (Rows are text-sorted, so a query may hit the same rare feature in most
-      // chunks of a block: R is dense.)
+      if (threadIdx.x == 0 && bk + 1 < blk_hi) fetch_block(bk + 1, as ^ 1);  // its buffers were last read two barriers ago
+      mbar_wait(&S.blk_bar[as], aphase);
+      // ---- rare join, inverted: thread (query, quarter of its rare list) tests each feature in the block's presence
+      //      bitmap; on a hit it probes the block's table (L2) and adds weight x tf to R[chunk][query] for every chunk
+      //      of the mask.  Rows are text-sorted, so one feature can sit in most chunks of a block: R is dense. ----
       {
-        constexpr int PER_WARP = B_BN / B_WORKERS;
-        uint32_t my_off = 0, my_nr = 0;
-        if (lane < PER_WARP && c0 + warp + B_WORKERS * lane < P.n_chunks) {
-          const BlockInfo bi = P.binfo[c0 + warp + B_WORKERS * lane];
-          my_off = bi.off4;
-          my_nr = probe_f2 ? (uint32_t)bi.n_rare + bi.n_f2 : bi.n_rare;
-        }
-        auto probe = [&](uint32_t w, int j, uint32_t e) {
-          const uint32_t fid = (w >> 5) & FID_MASK;
-          if (fid == FID_NONE) return;
-          const uint32_t bb = rt_bit(fid);
-          if (!((rt_bm[bb >> 5] >> (bb & 31u)) & 1u)) return;
-          uint32_t h = hash_fid(fid, 11);
-          for (;;) {
-            const uint32_t key = rt_keys[h];
-            if (key == KEY_EMPTY) return;
-            if (key == fid) break;
-            h = (h + 1) & (RT_SLOTS - 1);
-          }
-          uint32_t tf = w & 31u;
-          if (tf == TF_OVF) tf = ovf_lookup(P.ovf_keys, P.ovf_vals, P.n_ovf, c0 + j, e);
-          const uint32_t wq = rt_wq[h];
-          const float x = __fmul_ru(__half2float(__ushort_as_half((unsigned short)(wq & 0xFFFFu))), (float)tf);
-          const uint32_t qinfo = wq >> 16;
-          float *Rj = &S.R[j][0];
-          if (qinfo < (uint32_t)TILE_Q) {
-            atomicAdd(&Rj[qinfo], x);
-          } else if (qinfo != 0xFFFFu) {
-            const uint32_t *mm = rt_multi + 4 * (qinfo & 0x7FFFu);
-#pragma unroll
-            for (int g = 0; g < 4; g++)
-              for (uint32_t bits = mm[g]; bits; bits &= bits - 1) atomicAdd(&Rj[g * 32 + __ffs(bits) - 1], x);
-          }
-        };
-        uint32_t cur[4], nxt[4];
-        auto load4 = [&](int jj, uint32_t (&dst)[4]) {
-          const uint32_t off = __shfl_sync(FULL, my_off, jj), nr = __shfl_sync(FULL, my_nr, jj);
-          const uint32_t *words = P.blk + (size_t)off * 4;
-#pragma unroll
-          for (int bq = 0; bq < 4; bq++) {
-            const uint32_t e = (uint32_t)(bq * 32 + lane);
-            dst[bq] = e < nr ? __ldg(words + e) : PAD_WORD;
-          }
-        };
-        load4(0, cur);
+        const int jq = threadIdx.x & (TILE_Q - 1), part = threadIdx.x >> 7;  // 512 worker threads = 128 queries x 4
+        const uint32_t *bm = S.rbm[as];
+        const uint32_t tsize = P.rt_size[bk], toff = P.rt_off[bk];
 #pragma unroll 1
-        for (int jj = 0; jj < PER_WARP; jj++) {
-          if (jj + 1 < PER_WARP) load4(jj + 1, nxt);
-          const int j = warp + B_WORKERS * jj;
-          const uint32_t nr = __shfl_sync(FULL, my_nr, jj);
-#pragma unroll
-          for (int bq = 0; bq < 4; bq++)
-            if ((uint32_t)(bq * 32) < nr) probe(cur[bq], j, (uint32_t)(bq * 32 + lane));
-          if (nr > 128u) {  // rare: a chunk with more than 128 non-frequent entries
-            const uint32_t *words = P.blk + (size_t)__shfl_sync(FULL, my_off, jj) * 4;
-            for (uint32_t e0 = 128; e0 < nr; e0 += 32) {
-              const uint32_t e = e0 + lane;
-              probe(e < nr ? __ldg(words + e) : PAD_WORD, j, e);
+        for (int i = part; i < Q3CAP; i += 4) {
+          const uint2 f3 = S.q3[i][jq];
+          if (f3.x >= FID_NONE) break;  // the lists are filled from the front (padding queries: all ones)
+          const uint32_t bb = rb_bit(f3.x);
+          if (!((bm[bb >> 5] >> (bb & 31u)) & 1u)) continue;
+          uint32_t h = rt_slot(f3.x, tsize);
+          for (;;) {
+            const uint32_t key = __ldg(P.rt_keys + toff + h);
+            if (key == KEY_EMPTY) break;
+            if ((key >> 5) == f3.x) {
+              uint32_t tf = key & 31u;
+              if (tf == TF_OVF) tf = __ldg(P.tfmax + f3.x);
+              const float x = __fmul_ru(__uint_as_float(f3.y), (float)tf);
+              unsigned long long cm = __ldg(P.rt_masks + toff + h);
+              while (cm) {
+                const int j = __ffsll((long long)cm) - 1;
+                cm &= cm - 1;
+                atomicAdd(&S.R[j][jq], x);
+              }
+              break;
             }
+            h = h + 1 == tsize ? 0 : h + 1;
           }
-#pragma unroll
-          for (int bq = 0; bq < 4; bq++) cur[bq] = nxt[bq];
         }
       }
       if (threadIdx.x < B_BN) S.minB[as][threadIdx.x] = P.chunk_minB[c0 + threadIdx.x];
@@ -346,21 +317,20 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
 #pragma unroll
         for (int j = 0; j < B_COLS; j++) { x[j] = Rcol[j * TILE_Q]; Rcol[j * TILE_Q] = 0.f; }
       }
-      mbar_wait(&S.ubt_bar, (uint32_t)(it & 1));
       const uint32_t bsh = (uint32_t)((cs * B_COLS) & 31), bword = (uint32_t)((cs * B_COLS) >> 5);
       constexpr uint32_t CMASK = B_COLS == 32 ? 0xFFFFFFFFu : ((1u << B_COLS) - 1u);
 #pragma unroll 1
       for (int i = 0; i < Q2CAP; i++) {
         const uint2 f2 = S.q2[i][qi];
-        const float w2 = __uint_as_float(f2.y);
+        const float w2 = q_ok ? __uint_as_float(f2.y) : 0.f;
         if (!__any_sync(FULL, w2 > 0.f)) break;  // the lists are filled from the front
         const uint32_t row2 = f2.x & 0xFFFFu, tm1 = f2.x >> 16;
-        const uint32_t m = w2 > 0.f ? ((S.ubt[row2][0][bword] >> bsh) & CMASK) : 0u;
+        const uint32_t m = w2 > 0.f ? ((S.ubt[as][row2][0][bword] >> bsh) & CMASK) : 0u;
         if (m) {
 #pragma unroll
           for (int j = 0; j < B_COLS; j++)
             if ((m >> j) & 1u) x[j] += w2;
-          const uint32_t mm = tm1 ? ((S.ubt[row2][1][bword] >> bsh) & CMASK) : 0u;  // tf >= 2 there: up to tfmax - 1 more
+          const uint32_t mm = tm1 ? ((S.ubt[as][row2][1][bword] >> bsh) & CMASK) : 0u;  // tf >= 2 there: up to tfmax - 1 more
           if (mm) {
             const float wex = __fmul_ru(w2, (float)tm1);
 #pragma unroll
@@ -454,11 +424,7 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
           }
         }
       }
-      asm volatile("bar.sync 1, 512;" ::: "memory");  // R is clean again and every reader of this block's bitmaps is done
-      if (threadIdx.x == 0 && bk + 1 < blk_hi) {
-        mbar_expect_tx(&S.ubt_bar, sizeof(S.ubt));
-        bulk_copy_g2s(&S.ubt[0][0][0], P.ubt + (size_t)(bk + 1) * (sizeof(S.ubt) / 4), sizeof(S.ubt), &S.ubt_bar);
-      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");  // R is clean again and every reader of this block's side data is done
     }
     if (P.pass == 0) {
       if (q_in) {

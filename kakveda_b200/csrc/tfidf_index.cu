@@ -76,11 +76,13 @@ struct kv_index {
   DevBuf<__half> d_Uf;
   DevBuf<short> d_fslot;
   DevBuf<unsigned short> d_fslot2;
-  DevBuf<uint32_t> d_ubt;
+  DevBuf<uint32_t> d_ubt, d_rbloom, d_rt_keys, d_rt_off, d_rt_size;
+  DevBuf<unsigned long long> d_rt_masks;
   CUtensorMap map_u;
   DevBuf<unsigned long long> d_ovf_keys;
   DevBuf<uint32_t> d_ovf_vals;
   int n_ovf = 0;
+  int64_t rare_table_bytes = 0;
   int64_t blk_words = 0, n_chunks = 0, n_chunks_pad = 0, n_entries = 0, n_rare_entries = 0;
   std::vector<uint32_t> h_df, h_tfmax;
   std::vector<short> h_fslot;
@@ -106,8 +108,8 @@ struct kv_index {
   DevBuf<int> d_qperm;
   DevBuf<uint8_t> d_flags;
   DevBuf<float> d_qconst;     // 7 * n_q: nq, dotU, corrU, dotS, corrS, dotX, -inf
-  DevBuf<unsigned char> d_qtab, d_rtab;
-  DevBuf<uint2> d_q2list;
+  DevBuf<unsigned char> d_qtab;
+  DevBuf<uint2> d_q2list, d_q3list;
   DevBuf<__half> d_Wf;
   CUtensorMap map_w;
   DevBuf<int> d_gthr;
@@ -261,14 +263,15 @@ void kv_index_destroy(kv_index *ix) {
   ix->d_a64.release(); ix->d_d64.release(); ix->d_bb64.release(); ix->d_B64.release();
   ix->d_B32.release(); ix->d_cminB.release(); ix->d_univ.release(); ix->d_perm.release(); ix->d_invperm.release();
   ix->d_blk.release(); ix->d_binfo.release(); ix->d_Uf.release(); ix->d_fslot.release(); ix->d_fslot2.release(); ix->d_ubt.release();
-  ix->d_q2list.release();
+  ix->d_rbloom.release(); ix->d_rt_keys.release(); ix->d_rt_off.release(); ix->d_rt_size.release(); ix->d_rt_masks.release();
+  ix->d_q2list.release(); ix->d_q3list.release();
   ix->d_ovf_keys.release(); ix->d_ovf_vals.release();
   ix->d_rq_indptr.release(); ix->d_rq_ids.release(); ix->d_rq_tf.release(); ix->d_rq_const.release(); ix->d_rq_out.release();
   ix->d_rq_rows.release();
   ix->h_q_indptr.release(); ix->h_q_ids.release(); ix->h_q_tf.release(); ix->h_q_oov.release(); ix->h_qperm.release();
   ix->h_flags.release();
   ix->d_q_indptr.release(); ix->d_q_ids.release(); ix->d_q_tf.release(); ix->d_q_oov.release(); ix->d_qperm.release();
-  ix->d_flags.release(); ix->d_qconst.release(); ix->d_qtab.release(); ix->d_rtab.release(); ix->d_Wf.release();
+  ix->d_flags.release(); ix->d_qconst.release(); ix->d_qtab.release(); ix->d_Wf.release();
   ix->d_gthr.release();
   ix->d_seeds.release(); ix->d_direct.release(); ix->d_pool.release(); ix->d_list_count.release(); ix->d_list_pages.release();
   ix->d_pool_ctl.release(); ix->d_ubq.release();
@@ -561,6 +564,15 @@ int kv_index_finalize(kv_index *ix, int64_t vocab_size) {
   KV_CUDA(cudaMemcpyAsync(ix->d_fslot2.p, ix->h_fslot2.data(), (size_t)Vz * sizeof(short), cudaMemcpyHostToDevice, s));
   KV_CUDA(ix->d_ubt.ensure((int64_t)L.Ubt.size()));
   KV_CUDA(cudaMemcpyAsync(ix->d_ubt.p, L.Ubt.data(), L.Ubt.size() * 4, cudaMemcpyHostToDevice, s));
+  KV_CUDA(ix->d_rbloom.ensure((int64_t)L.rbloom.size())); KV_CUDA(ix->d_rt_keys.ensure((int64_t)L.rt_keys.size()));
+  KV_CUDA(ix->d_rt_masks.ensure((int64_t)L.rt_masks.size())); KV_CUDA(ix->d_rt_off.ensure((int64_t)L.rt_off.size()));
+  KV_CUDA(ix->d_rt_size.ensure((int64_t)L.rt_size.size()));
+  KV_CUDA(cudaMemcpyAsync(ix->d_rbloom.p, L.rbloom.data(), L.rbloom.size() * 4, cudaMemcpyHostToDevice, s));
+  KV_CUDA(cudaMemcpyAsync(ix->d_rt_keys.p, L.rt_keys.data(), L.rt_keys.size() * 4, cudaMemcpyHostToDevice, s));
+  KV_CUDA(cudaMemcpyAsync(ix->d_rt_masks.p, L.rt_masks.data(), L.rt_masks.size() * 8, cudaMemcpyHostToDevice, s));
+  KV_CUDA(cudaMemcpyAsync(ix->d_rt_off.p, L.rt_off.data(), L.rt_off.size() * 4, cudaMemcpyHostToDevice, s));
+  KV_CUDA(cudaMemcpyAsync(ix->d_rt_size.p, L.rt_size.data(), L.rt_size.size() * 4, cudaMemcpyHostToDevice, s));
+  ix->rare_table_bytes = (int64_t)(L.rt_keys.size() * 12 + L.rbloom.size() * 4);
   ix->n_ovf = (int)L.ovf.size();
   KV_CUDA(ix->d_ovf_keys.ensure(std::max(1, ix->n_ovf))); KV_CUDA(ix->d_ovf_vals.ensure(std::max(1, ix->n_ovf)));
   std::vector<unsigned long long> ok((size_t)ix->n_ovf);
@@ -772,9 +784,9 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
   KV_CUDA(ix->d_flags.ensure(n_q));
   KV_CUDA(ix->d_qconst.ensure(7 * n_q));
   KV_CUDA(ix->d_qtab.ensure(n_q * (int64_t)QTAB_BYTES));
-  KV_CUDA(ix->d_rtab.ensure(n_tiles * (int64_t)RTAB_BYTES));
   KV_CUDA(ix->d_Wf.ensure(n_q_pad * NF));
   KV_CUDA(ix->d_q2list.ensure(n_q_pad * Q2CAP));
+  KV_CUDA(ix->d_q3list.ensure(n_q_pad * Q3CAP));
   KV_CUDA(cudaEventRecord(ix->ev[0], s));
   KV_CUDA(cudaMemcpyAsync(ix->d_q_indptr.p, ix->h_q_indptr.p, (size_t)(n_q + 1) * 8, cudaMemcpyHostToDevice, s));
   if (nnz) {
@@ -787,6 +799,9 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
   KV_CUDA(cudaEventRecord(ix->ev[1], s));
   // ---- device: per-query constants and tables, per-tile rare-feature tables ----
   KV_CUDA(cudaMemsetAsync(ix->d_Wf.p, 0, (size_t)n_q_pad * NF * sizeof(__half), s));
+  // the lists of the padding queries of the last tile must be empty (weight 0 / no feature)
+  KV_CUDA(cudaMemsetAsync(ix->d_q2list.p, 0, (size_t)n_q_pad * Q2CAP * sizeof(uint2), s));
+  KV_CUDA(cudaMemsetAsync(ix->d_q3list.p, 0xFF, (size_t)n_q_pad * Q3CAP * sizeof(uint2), s));
   PrepParams P;
   P.q_indptr = ix->d_q_indptr.p; P.q_ids = ix->d_q_ids.p; P.q_tf = ix->d_q_tf.p; P.q_oov = ix->d_q_oov.p;
   P.qperm = ix->d_qperm.p; P.flags = ix->d_flags.p;
@@ -797,16 +812,8 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
   P.fslot = ix->d_fslot.p; P.fslot2 = ix->d_fslot2.p; P.q2list = ix->d_q2list.p; P.jaccard = ix->jaccard; P.corpus_fit = ix->corpus_fit;
   P.q_nq = ix->d_qconst.p; P.q_dotU = P.q_nq + n_q; P.q_corrU = P.q_nq + 2 * n_q; P.q_dotS = P.q_nq + 3 * n_q;
   P.q_corrS = P.q_nq + 4 * n_q; P.q_dotX = P.q_nq + 5 * n_q;
-  P.qtab = ix->d_qtab.p; P.Wf = ix->d_Wf.p; P.rtab = ix->d_rtab.p;
+  P.qtab = ix->d_qtab.p; P.Wf = ix->d_Wf.p; P.q3list = ix->d_q3list.p;
   prep_queries_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, s>>>(P);
-  KV_CUDA(cudaGetLastError());
-  static bool attr_set[64] = {false};
-  const int prep_smem = RT_SLOTS * 4 * 6 + RT_BITMAP_BITS / 8;
-  if (!attr_set[ix->device & 63]) {
-    KV_CUDA(cudaFuncSetAttribute(prep_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
-    attr_set[ix->device & 63] = true;
-  }
-  prep_tiles_kernel<<<(unsigned)n_tiles, TILE_Q, prep_smem, s>>>(P);
   KV_CUDA(cudaGetLastError());
   {
     int rc = make_map_f16_nf(&ix->map_w, ix->d_Wf.p, n_q_pad, TILE_Q);
@@ -941,7 +948,9 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r, in
       BoundParams BP;
       BP.blk = ix->d_blk.p; BP.binfo = ix->d_binfo.p; BP.chunk_minB = ix->d_cminB.p;
       BP.ovf_keys = ix->d_ovf_keys.p; BP.ovf_vals = ix->d_ovf_vals.p; BP.n_ovf = ix->n_ovf;
-      BP.n_chunks = ix->n_chunks; BP.n_q = n_q; BP.rtab = ix->d_rtab.p; BP.q2list = ix->d_q2list.p; BP.ubt = ix->d_ubt.p;
+      BP.n_chunks = ix->n_chunks; BP.n_q = n_q; BP.q2list = ix->d_q2list.p; BP.q3list = ix->d_q3list.p; BP.ubt = ix->d_ubt.p;
+      BP.rbloom = ix->d_rbloom.p; BP.rt_keys = ix->d_rt_keys.p; BP.rt_masks = ix->d_rt_masks.p; BP.rt_off = ix->d_rt_off.p;
+      BP.rt_size = ix->d_rt_size.p; BP.tfmax = ix->d_tfmax.p;
       BP.q_nq = qc; BP.q_dotS = qc + 3 * n_q; BP.q_corrS = qc + 4 * n_q; BP.q_dotX = qc + 5 * n_q;
       BP.gthr = ix->d_gthr.p; BP.n_bsplits = (int)n_bsplits; BP.jaccard = ix->jaccard;
       BP.seeds = ix->d_seeds.p;
@@ -1417,7 +1426,7 @@ int kv_index_layout(const kv_index *ix, int64_t bytes[4], int64_t counts[17]) {
   bytes[0] = ix->blk_words * 4;
   bytes[1] = ix->n_rows * 4;
   bytes[2] = ix->n_chunks_pad * (int64_t)sizeof(BlockInfo);
-  bytes[3] = ix->n_chunks_pad * (int64_t)(NF * sizeof(__half) + sizeof(float));
+  bytes[3] = ix->n_chunks_pad * (int64_t)(NF * sizeof(__half) + sizeof(float)) + ix->rare_table_bytes + (ix->n_chunks_pad / 64) * (int64_t)(NF2 * 16);
   counts[0] = ix->n_entries; counts[1] = ix->n_univ; counts[2] = ix->n_rows;
   counts[3] = ix->last_ctas; counts[4] = ix->last_tiles; counts[5] = ix->last_splits;
   counts[6] = ix->batch_h2d_bytes; counts[7] = ix->n_ovf;

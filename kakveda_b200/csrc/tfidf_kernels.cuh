@@ -41,7 +41,7 @@ namespace kvk {
 constexpr int CHUNK_ROWS = 32;
 constexpr int NF = 256;   // features evaluated densely (tensor cores) by the bound kernel
 constexpr int NF2 = 1024; // the next most frequent features: per 128-chunk block two transposed bitmaps [NF2][tf >= 1, tf >= 2][128 bits]
-constexpr int Q2CAP = 32; // features of that class a query keeps in its own list (further ones go to the tile's rare table)
+constexpr int Q2CAP = 24; // features of that class a query keeps in its own list (further ones are treated as rare)
 constexpr uint32_t FID_BITS = 26;
 constexpr uint32_t FID_MASK = (1u << FID_BITS) - 1;
 constexpr uint32_t FID_NONE = FID_MASK;  // sentinel feature id (never in a table)
@@ -55,11 +55,8 @@ constexpr int QFEATS = 64;   // features a query may hold in it (more: float64 f
 constexpr int QTAB_BYTES = QKEYS * 4 + QFEATS * 16;
 constexpr int GROUP_Q = 32;  // queries per scan group (one candidate list, one K1b-S CTA)
 constexpr int TILE_Q = 128;  // queries per bound tile (4 groups; the M of the bound GEMM)
-constexpr int RT_SLOTS = 2048;  // rare-feature table of a bound tile: keys[RT_SLOTS], then (fp16 weight | query info << 16)
-constexpr int RT_CAP = 1400;    // features it accepts (the rest enters the bounds as per-query constants)
-constexpr int RT_MULTI = 256;   // of those, features shared by several queries of the tile (128-bit membership masks)
-constexpr int RT_BITMAP_BITS = 1 << 16;  // presence bitmap probed before the table (1 shared-memory load rejects ~98 % of the entries)
-constexpr int RTAB_BYTES = RT_SLOTS * 8 + RT_MULTI * 16 + RT_BITMAP_BITS / 8 + 16;  // + flags: [0] the table holds second-class features
+constexpr int Q3CAP = 32;       // rare features a query keeps in its own list for the bound kernel (further ones: a constant)
+constexpr int RB_BITS = 1 << 16;  // per 64-chunk block: presence bitmap of its rare features (one hash), probed before the block's table
 constexpr float PRUNE_SLACK = 1.0005f;  // bounds: fp16 round-up of weights, fp32 tensor-core sums, constants rounded outwards
 constexpr float FILTER_SLACK = 0.999996f;
 constexpr int PAGE_RECS = 1024;  // candidate records per pool page
@@ -302,7 +299,7 @@ __global__ void __launch_bounds__(256) tfidf_score_kernel(ScoreParams P) {
 
 // ----------------------------------------------------------------------------------------
 // query batch preparation (device): per-query constants, the query's own hash table (K1b-S), its row of the dense
-// weight matrix Wf (K1b-B), and per 128-query tile the table of its non-frequent features (K1b-B's join)
+// weight matrix Wf (K1b-B), and its lists of second-class and rare features (K1b-B)
 // ----------------------------------------------------------------------------------------
 struct QFeat {
   uint32_t w_lo, w_hi;  // round(tf_q a(t) 2^32)
@@ -327,7 +324,7 @@ struct PrepParams {
   float *q_nq, *q_dotU, *q_corrU, *q_dotS, *q_corrS, *q_dotX;  // [n_q] by sorted slot
   unsigned char *qtab;      // [n_q][QTAB_BYTES]
   __half *Wf;               // [n_q_pad][NF], zeroed by the caller
-  unsigned char *rtab;      // [n_tiles][RTAB_BYTES]
+  uint2 *q3list;            // [n_tiles][Q3CAP][TILE_Q] (rare feature id, weight tf_q a(t) rounded up as float bits)
   uint2 *q2list;            // [n_tiles][Q2CAP][TILE_Q] (bit row | (tfmax(t) - 1) << 16, weight tf_q a(t) as float bits)
 };
 
@@ -345,6 +342,10 @@ __global__ void prep_queries_kernel(PrepParams P) {
   const bool regular = P.flags[i] == 0;
   uint2 *q2 = P.q2list + ((size_t)(i / TILE_Q) * Q2CAP) * TILE_Q + (i % TILE_Q);
   for (int j = 0; j < Q2CAP; j++) q2[(size_t)j * TILE_Q] = make_uint2(0u, 0u);
+  uint2 *q3 = P.q3list + ((size_t)(i / TILE_Q) * Q3CAP) * TILE_Q + (i % TILE_Q);
+  for (int j = 0; j < Q3CAP; j++) q3[(size_t)j * TILE_Q] = make_uint2(FID_NONE, 0u);
+  int c3 = 0;
+  float dotX = 0.f;
   for (int64_t p = P.q_indptr[q]; p < P.q_indptr[q + 1]; p++) {
     const uint32_t t = P.q_ids[p];
     const double f = (double)P.q_tf[p];
@@ -374,6 +375,11 @@ __global__ void prep_queries_kernel(PrepParams P) {
         const uint32_t tm1 = min(P.tfmax[t] - 1u, 65535u);  // weight of the 'tf >= 2' plane: (largest tf - 1) more times
         q2[(size_t)c2 * TILE_Q] = make_uint2((uint32_t)P.fslot2[t] | (tm1 << 16), __float_as_uint(__double2float_ru(f * a * (1.0 + 1e-6))));
         c2++;
+      } else if (P.fslot2[t] == 0xFFFFu && c3 < Q3CAP) {  // rare: looked up per block of chunks by the bound kernel
+        q3[(size_t)c3 * TILE_Q] = make_uint2(t, __float_as_uint(__double2float_ru(f * a * (1.0 + 1e-6))));
+        c3++;
+      } else {  // no list slot left: assumed present in every chunk with its largest tf (a valid, loose bound)
+        dotX = __fadd_ru(dotX, __double2float_ru(f * a * tm * (1.0 + 1e-6)));
       }
     }
   }
@@ -382,103 +388,13 @@ __global__ void prep_queries_kernel(PrepParams P) {
   P.q_corrU[i] = (float)corrU;
   P.q_dotS[i] = __double2float_ru(dotU * (1.0 + 1e-6));  // bounds may only err upwards
   P.q_corrS[i] = __double2float_rd(corrU + corrS);       // ... and their denominators downwards
-  P.q_dotX[i] = 0.f;
+  P.q_dotX[i] = dotX;
 }
 
-// one CTA (128 threads = the tile's queries) per tile: the tile's rare-feature table.  Slot = (feature, largest
-// tf_q a(t) over the tile's queries holding it as fp16 rounded up, the query or the index of a 128-bit membership mask),
-// plus a presence bitmap over a second hash of the feature id.
-__device__ __forceinline__ uint32_t rt_bit(uint32_t fid) { return (fid * 0x85EBCA6Bu) >> 16; }  // 16 bits
-
-__global__ void __launch_bounds__(TILE_Q) prep_tiles_kernel(PrepParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t *s_keys = (uint32_t *)smem_raw;          // [RT_SLOTS]
-  uint32_t *s_w = s_keys + RT_SLOTS;                 // float bits
-  uint32_t *s_m = s_w + RT_SLOTS;                    // [RT_SLOTS][4]
-  uint32_t *s_bm = s_m + 4 * RT_SLOTS;               // [RT_BITMAP_BITS / 32]
-  __shared__ int s_cnt, s_multi, s_has2;
-  __shared__ float s_dotX[TILE_Q];
-  const int tile = blockIdx.x, qi = threadIdx.x;
-  for (int j = qi; j < RT_SLOTS; j += TILE_Q) {
-    s_keys[j] = KEY_EMPTY;
-    s_w[j] = 0;
-    s_m[4 * j] = s_m[4 * j + 1] = s_m[4 * j + 2] = s_m[4 * j + 3] = 0;
-  }
-  for (int j = qi; j < RT_BITMAP_BITS / 32; j += TILE_Q) s_bm[j] = 0;
-  if (qi == 0) { s_cnt = 0; s_multi = 0; s_has2 = 0; }
-  s_dotX[qi] = 0.f;
-  __syncthreads();
-  const int64_t i = (int64_t)tile * TILE_Q + qi;
-  if (i < P.n_q && P.flags[i] == 0) {
-    const int q = P.qperm[i];
-    int cnt = 0, c2 = 0;
-    for (int64_t p = P.q_indptr[q]; p < P.q_indptr[q + 1]; p++) {
-      const uint32_t t = P.q_ids[p];
-      if ((int64_t)t >= P.V || P.univ[t]) continue;
-      if (cnt++ >= QFEATS) break;
-      if (P.fslot[t] >= 0) continue;
-      if (P.fslot2[t] != 0xFFFFu) {
-        if (c2 < P.q2cap) { c2++; continue; }  // in the query's own second-class list
-        s_has2 = 1;                             // list full: the feature goes to the table (its block entries must be probed)
-      }
-      const float w = __half2float(__float2half_ru(__double2float_ru((double)P.q_tf[p] * P.a64[t])));
-      uint32_t h = hash_fid(t, 11);
-      bool placed = false;
-      for (int probes = 0; probes < RT_SLOTS; probes++) {
-        uint32_t k = s_keys[h];
-        if (k == KEY_EMPTY) {
-          if (s_cnt >= RT_CAP) break;  // table full: this feature enters the bounds as a constant
-          k = atomicCAS(&s_keys[h], KEY_EMPTY, t);
-          if (k == KEY_EMPTY) { atomicAdd(&s_cnt, 1); k = t; }
-        }
-        if (k == t) { placed = true; break; }
-        h = (h + 1) & (RT_SLOTS - 1);
-      }
-      if (placed) {
-        atomicMax(&s_w[h], __float_as_uint(w));
-        atomicOr(&s_m[4 * h + (qi >> 5)], 1u << (qi & 31));
-        const uint32_t b = rt_bit(t);
-        atomicOr(&s_bm[b >> 5], 1u << (b & 31));
-      } else {
-        s_dotX[qi] += __fmul_ru(w, (float)P.tfmax[t]);  // assumed present everywhere with its largest tf
-      }
-    }
-  }
-  __syncthreads();
-  uint32_t *o_keys = (uint32_t *)(P.rtab + (size_t)tile * RTAB_BYTES);
-  uint32_t *o_wq = o_keys + RT_SLOTS;      // fp16 weight | query info << 16
-  uint32_t *o_multi = o_wq + RT_SLOTS;     // [RT_MULTI][4]
-  uint32_t *o_bm = o_multi + 4 * RT_MULTI;
-  for (int j = qi; j < RT_SLOTS; j += TILE_Q) {
-    const uint32_t k = s_keys[j];
-    uint32_t qinfo = 0xFFFFu;
-    float w = __uint_as_float(s_w[j]);
-    if (k != KEY_EMPTY) {
-      const uint32_t m0 = s_m[4 * j], m1 = s_m[4 * j + 1], m2 = s_m[4 * j + 2], m3 = s_m[4 * j + 3];
-      const int pc = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-      if (pc == 1) {
-        qinfo = m0 ? (uint32_t)(__ffs(m0) - 1) : m1 ? (uint32_t)(31 + __ffs(m1)) : m2 ? (uint32_t)(63 + __ffs(m2)) : (uint32_t)(95 + __ffs(m3));
-      } else {
-        const int mi = atomicAdd(&s_multi, 1);
-        if (mi < RT_MULTI) {
-          o_multi[4 * mi] = m0; o_multi[4 * mi + 1] = m1; o_multi[4 * mi + 2] = m2; o_multi[4 * mi + 3] = m3;
-          qinfo = 0x8000u | (uint32_t)mi;
-        } else {  // no mask slot left: constant for every member query (the key stays: probe chains must not break)
-          const float x = __fmul_ru(w, (float)P.tfmax[k]);
-          const uint32_t mm[4] = {m0, m1, m2, m3};
-          for (int g = 0; g < 4; g++)
-            for (uint32_t b = mm[g]; b; b &= b - 1) atomicAdd(&s_dotX[g * 32 + __ffs(b) - 1], x * 1.000001f);
-          w = 0.f;
-        }
-      }
-    }
-    o_keys[j] = k;
-    o_wq[j] = (uint32_t)__half_as_ushort(__float2half_ru(w)) | (qinfo << 16);
-  }
-  for (int j = qi; j < RT_BITMAP_BITS / 32; j += TILE_Q) o_bm[j] = s_bm[j];
-  if (qi < 4) o_bm[RT_BITMAP_BITS / 32 + qi] = qi == 0 ? (uint32_t)s_has2 : 0u;
-  __syncthreads();
-  if (i < P.n_q) P.q_dotX[i] = s_dotX[qi] * 1.00001f;
+__host__ __device__ __forceinline__ uint32_t rb_bit(uint32_t fid) { return (fid * 0x85EBCA6Bu) >> 16; }  // 16 bits: RB_BITS
+// slot of a feature in a block's rare table of `size` slots (fast range reduction of a multiplicative hash)
+__host__ __device__ __forceinline__ uint32_t rt_slot(uint32_t fid, uint32_t size) {
+  return (uint32_t)(((unsigned long long)(fid * 0x9E3779B1u) * (unsigned long long)size) >> 32);
 }
 
 // ----------------------------------------------------------------------------------------

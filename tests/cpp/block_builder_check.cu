@@ -85,6 +85,8 @@ static void check_case(int64_t n, int64_t V, int n_univ, unsigned seed, bool big
   CHECK(memcmp(L1.binfo.data(), L4.binfo.data(), L1.binfo.size() * sizeof(BlockInfo)) == 0, "threaded build: directory differs");
   CHECK(memcmp(L1.Uf.data(), L4.Uf.data(), L1.Uf.size() * sizeof(__half)) == 0, "threaded build: dense matrix differs");
   CHECK(L1.fslot2 == L4.fslot2 && L1.Ubt == L4.Ubt, "threaded build: second-class bitmaps differ");
+  CHECK(L1.rbloom == L4.rbloom && L1.rt_keys == L4.rt_keys && L1.rt_masks == L4.rt_masks && L1.rt_off == L4.rt_off && L1.rt_size == L4.rt_size,
+        "threaded build: rare tables differ");
   CHECK((int64_t)L1.Ubt.size() == L1.n_chunks_pad / 64 * NF2 * 4, "bitmap size");
   CHECK(L1.n_chunks == (n + 31) / 32 && L1.n_chunks_pad % 128 == 0 && L1.n_chunks_pad >= L1.n_chunks, "chunk counts");
   // decode
@@ -116,6 +118,24 @@ static void check_case(int64_t n, int64_t V, int n_univ, unsigned seed, bool big
       if (!rare && !sec) umax[L1.fslot[f]] = std::max(umax[L1.fslot[f]], t);
       CHECK(!(L1.fslot[f] >= 0 && L1.fslot2[f] != 0xFFFF), "feature in both classes");
       if (L1.fslot2[f] != 0xFFFF) { have2.insert((int)L1.fslot2[f]); if (t >= 2) have2b.insert((int)L1.fslot2[f]); }
+      if (rare) {  // the block-level inverted index must find the feature, with this chunk in its mask and tf <= its tf
+        const int64_t b = ch >> 6;
+        const uint32_t bb = rb_bit(f);
+        CHECK((L1.rbloom[(size_t)b * (RB_BITS / 32) + (bb >> 5)] >> (bb & 31u)) & 1u, "rare feature missing in the block bitmap");
+        const uint32_t size = L1.rt_size[(size_t)b], off = L1.rt_off[(size_t)b];
+        uint32_t h = rt_slot(f, size);
+        bool found = false;
+        for (uint32_t n_probe = 0; n_probe < size; n_probe++) {
+          const uint32_t key = L1.rt_keys[off + h];
+          if (key == KEY_EMPTY) break;
+          if ((key >> 5) == f) {
+            found = ((L1.rt_masks[off + h] >> (ch & 63)) & 1ULL) && ((key & 31u) >= std::min<uint32_t>(t, 31u));
+            break;
+          }
+          h = h + 1 == size ? 0 : h + 1;
+        }
+        CHECK(found, "rare feature %u of chunk %lld not found in its block's table", f, (long long)ch);
+      }
       for (int r = 0; r < rows; r++)
         if ((masks[e] >> r) & 1u) {
           auto &row = got[(size_t)c.perm[(size_t)(ch * 32 + r)]];
