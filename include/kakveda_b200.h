@@ -235,6 +235,14 @@ int kv_debug_bound_numerators(kv_index *ix, int k, float *out, int32_t *slot_que
 /* CUDA-event milliseconds of the scan kernel of the last kv_score call (K1a). */
 int kv_index_last_score_ms(const kv_index *ix, float *ms);
 
+/* Persisted scan layout (the write side of services/gfkb/app.py:38-56 makes cold starts matter): _save
+ * writes what kv_index_finalize built on the host cores (row order, column blocks, dense matrix, bitmaps, rare tables)
+ * to one file; _load, called after the SAME rows were appended and before kv_index_finalize, restores it (the file is
+ * tied to the rows by count + checksum; KV_ERR_STATE if it does not match), so that finalize only refreshes the
+ * statistics (kv_index_last_finalize_kind == 2) instead of sorting and building (~15 s at 10M rows). */
+int kv_index_layout_save(kv_index *ix, const char *path);
+int kv_index_layout_load(kv_index *ix, const char *path);
+
 /* Scan-layout facts for roofline accounting.
  * bytes[0] = column blocks, bytes[1] = row norms (float32), bytes[2] = block directory,
  * bytes[3] = dense frequent-feature matrix (fp16) + chunk min norms.

@@ -74,6 +74,8 @@ SIGNATURES = {
     "kv_index_last_score_ms": (C.c_int, [C.c_void_p, c_f32p]),
     "kv_debug_bound_numerators": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.POINTER(C.c_int32)]),
     "kv_index_layout": (C.c_int, [C.c_void_p, c_i64p, c_i64p]),
+    "kv_index_layout_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "kv_index_layout_load": (C.c_int, [C.c_void_p, C.c_char_p]),
     "kv_dense_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
     "kv_dense_destroy": (None, [C.c_void_p]),
     "kv_dense_append": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint16), C.c_int64]),

@@ -1443,3 +1443,152 @@ int kv_index_layout(const kv_index *ix, int64_t bytes[4], int64_t counts[17]) {
 }
 
 }  // extern "C"
+
+// ----------------------------------------------------------------------------------------
+// Persisted scan layout: the arrays kv_index_finalize builds on the host cores (row order, column
+// blocks, dense / bitmap / rare-table side structures) written to one file, so that a cold start of a large GFKB is
+// "read + H2D + statistics kernels" instead of a 15 s sort and block build.  The file is tied to the rows by their
+// count, entry count and a checksum of the CSR; a file that does not match is refused (the caller then finalizes the
+// usual way).  kv_index_layout_load is called after the rows were appended and BEFORE kv_index_finalize, which then takes
+// the statistics-only path (kv_index_last_finalize_kind == 2).
+// ----------------------------------------------------------------------------------------
+namespace {
+constexpr uint64_t LAYOUT_MAGIC = 0x32594C42564B4B41ULL;  // "AKKVBLY2"
+
+uint64_t csr_checksum(const kv_index *ix) {
+  const int T = host_threads();
+  std::vector<uint64_t> part((size_t)T, 0);
+  parallel_for(ix->n_rows, T, [&](int t, int64_t a, int64_t b) {
+    uint64_t h = 1469598103934665603ULL ^ (uint64_t)a;
+    for (int64_t r = a; r < b; r++) {
+      for (int64_t p = ix->h_indptr[(size_t)r]; p < ix->h_indptr[(size_t)r + 1]; p++) {
+        h = (h ^ ix->h_ids[(size_t)p]) * 1099511628211ULL;
+        h = (h ^ ix->h_tf[(size_t)p]) * 1099511628211ULL;
+      }
+      h = (h ^ 0xFFFFFFFFULL) * 1099511628211ULL;  // row boundary
+    }
+    part[(size_t)t] = h;
+  });
+  uint64_t h = 1469598103934665603ULL;
+  for (uint64_t x : part) h = (h ^ x) * 1099511628211ULL;
+  return h;
+}
+
+struct LayoutHeader {
+  uint64_t magic, checksum;
+  int64_t n_rows, nnz, V, n_chunks, n_chunks_pad, blk_words, n_entries, n_rare_entries, n_ovf, n_rt_slots, n_blocks, univ_len;
+  int32_t jaccard, corpus_fit, threads, reserved;
+};
+
+template <class T>
+bool put(FILE *f, const std::vector<T> &v) { return v.empty() || fwrite(v.data(), sizeof(T), v.size(), f) == v.size(); }
+template <class T>
+bool get(FILE *f, std::vector<T> &v, size_t n) { v.resize(n); return n == 0 || fread(v.data(), sizeof(T), n, f) == n; }
+template <class T>
+int pull(std::vector<T> &h, const T *d, size_t n) {
+  h.resize(n);
+  if (n) KV_CUDA(cudaMemcpy(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost));
+  return KV_OK;
+}
+}  // namespace
+
+extern "C" int kv_index_layout_save(kv_index *ix, const char *path) {
+  if (!ix || !path) return kv_fail(KV_ERR_INVALID, "kv_index_layout_save: bad arguments");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (!ix->finalized || !ix->layout_valid) return kv_fail(KV_ERR_STATE, "kv_index_layout_save: index has no built layout (finalize first)");
+  KV_CUDA(cudaSetDevice(ix->device));
+  KV_CUDA(cudaStreamSynchronize(ix->stream));
+  LayoutHeader H{};
+  H.magic = LAYOUT_MAGIC; H.checksum = csr_checksum(ix);
+  H.n_rows = ix->n_rows; H.nnz = ix->nnz; H.V = (int64_t)ix->h_fslot.size(); H.n_chunks = ix->n_chunks; H.n_chunks_pad = ix->n_chunks_pad;
+  H.blk_words = ix->blk_words; H.n_entries = ix->n_entries; H.n_rare_entries = ix->n_rare_entries; H.n_ovf = ix->n_ovf;
+  H.n_blocks = ix->n_chunks_pad / 64; H.univ_len = (int64_t)ix->layout_univ.size();
+  H.jaccard = ix->jaccard; H.corpus_fit = ix->corpus_fit;
+  std::vector<uint32_t> rt_off, rt_size;
+  int rc;
+  if ((rc = pull(rt_off, ix->d_rt_off.p, (size_t)H.n_blocks)) != KV_OK || (rc = pull(rt_size, ix->d_rt_size.p, (size_t)H.n_blocks)) != KV_OK) return rc;
+  H.n_rt_slots = H.n_blocks ? (int64_t)rt_off.back() + rt_size.back() : 0;
+  std::vector<int> perm;
+  std::vector<uint32_t> blk, ubt, rbloom, rt_keys, ovf_vals;
+  std::vector<BlockInfo> binfo;
+  std::vector<__half> uf;
+  std::vector<unsigned long long> rt_masks, ovf_keys;
+  if ((rc = pull(perm, ix->d_perm.p, (size_t)H.n_rows)) != KV_OK || (rc = pull(blk, ix->d_blk.p, (size_t)H.blk_words)) != KV_OK ||
+      (rc = pull(binfo, ix->d_binfo.p, (size_t)H.n_chunks_pad)) != KV_OK || (rc = pull(uf, ix->d_Uf.p, (size_t)H.n_chunks_pad * NF)) != KV_OK ||
+      (rc = pull(ubt, ix->d_ubt.p, (size_t)H.n_blocks * NF2 * 4)) != KV_OK || (rc = pull(rbloom, ix->d_rbloom.p, (size_t)H.n_blocks * (RB_BITS / 32))) != KV_OK ||
+      (rc = pull(rt_keys, ix->d_rt_keys.p, (size_t)H.n_rt_slots)) != KV_OK || (rc = pull(rt_masks, ix->d_rt_masks.p, (size_t)H.n_rt_slots)) != KV_OK ||
+      (rc = pull(ovf_keys, ix->d_ovf_keys.p, (size_t)H.n_ovf)) != KV_OK || (rc = pull(ovf_vals, ix->d_ovf_vals.p, (size_t)H.n_ovf)) != KV_OK)
+    return rc;
+  FILE *f = fopen(path, "wb");
+  if (!f) return kv_fail(KV_ERR_INVALID, "kv_index_layout_save: cannot open %s", path);
+  bool ok = fwrite(&H, sizeof(H), 1, f) == 1 && put(f, ix->layout_univ) && put(f, ix->h_fslot) && put(f, ix->h_fslot2) && put(f, perm) &&
+            put(f, binfo) && put(f, blk) && put(f, uf) && put(f, ubt) && put(f, rbloom) && put(f, rt_off) && put(f, rt_size) && put(f, rt_keys) &&
+            put(f, rt_masks) && put(f, ovf_keys) && put(f, ovf_vals);
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) return kv_fail(KV_ERR_INVALID, "kv_index_layout_save: short write to %s", path);
+  return KV_OK;
+}
+
+extern "C" int kv_index_layout_load(kv_index *ix, const char *path) {
+  if (!ix || !path) return kv_fail(KV_ERR_INVALID, "kv_index_layout_load: bad arguments");
+  std::lock_guard<std::mutex> g(ix->mu);
+  KV_CUDA(cudaSetDevice(ix->device));
+  FILE *f = fopen(path, "rb");
+  if (!f) return kv_fail(KV_ERR_INVALID, "kv_index_layout_load: cannot open %s", path);
+  LayoutHeader H{};
+  std::vector<uint8_t> univ;
+  std::vector<short> fslot;
+  std::vector<unsigned short> fslot2;
+  std::vector<int> perm;
+  std::vector<uint32_t> blk, ubt, rbloom, rt_off, rt_size, rt_keys, ovf_vals;
+  std::vector<BlockInfo> binfo;
+  std::vector<__half> uf;
+  std::vector<unsigned long long> rt_masks, ovf_keys;
+  bool ok = fread(&H, sizeof(H), 1, f) == 1 && H.magic == LAYOUT_MAGIC;
+  if (ok && (H.n_rows != ix->n_rows || H.nnz != ix->nnz || H.jaccard != ix->jaccard || H.corpus_fit != ix->corpus_fit || H.checksum != csr_checksum(ix))) {
+    fclose(f);
+    return kv_fail(KV_ERR_STATE, "kv_index_layout_load: %s was built for other rows (or another mode)", path);
+  }
+  ok = ok && get(f, univ, (size_t)H.univ_len) && get(f, fslot, (size_t)H.V) && get(f, fslot2, (size_t)H.V) && get(f, perm, (size_t)H.n_rows) &&
+       get(f, binfo, (size_t)H.n_chunks_pad) && get(f, blk, (size_t)H.blk_words) && get(f, uf, (size_t)H.n_chunks_pad * NF) &&
+       get(f, ubt, (size_t)H.n_blocks * NF2 * 4) && get(f, rbloom, (size_t)H.n_blocks * (RB_BITS / 32)) && get(f, rt_off, (size_t)H.n_blocks) &&
+       get(f, rt_size, (size_t)H.n_blocks) && get(f, rt_keys, (size_t)H.n_rt_slots) && get(f, rt_masks, (size_t)H.n_rt_slots) &&
+       get(f, ovf_keys, (size_t)H.n_ovf) && get(f, ovf_vals, (size_t)H.n_ovf);
+  fclose(f);
+  if (!ok) return kv_fail(KV_ERR_INVALID, "kv_index_layout_load: %s is not a layout file of this version (or is truncated)", path);
+  cudaStream_t s = ix->stream;
+  const int64_t nz = std::max<int64_t>(H.n_rows, 1);
+  KV_CUDA(ix->d_perm.ensure(nz)); KV_CUDA(ix->d_invperm.ensure(nz)); KV_CUDA(ix->d_B64.ensure(nz)); KV_CUDA(ix->d_B32.ensure(nz));
+  KV_CUDA(ix->d_blk.ensure(H.blk_words + 64)); KV_CUDA(ix->d_binfo.ensure(H.n_chunks_pad)); KV_CUDA(ix->d_Uf.ensure(H.n_chunks_pad * NF));
+  KV_CUDA(ix->d_cminB.ensure(H.n_chunks_pad)); KV_CUDA(ix->d_fslot.ensure(std::max<int64_t>(H.V, 1))); KV_CUDA(ix->d_fslot2.ensure(std::max<int64_t>(H.V, 1)));
+  KV_CUDA(ix->d_ubt.ensure((int64_t)ubt.size())); KV_CUDA(ix->d_rbloom.ensure((int64_t)rbloom.size()));
+  KV_CUDA(ix->d_rt_off.ensure(std::max<int64_t>(H.n_blocks, 1))); KV_CUDA(ix->d_rt_size.ensure(std::max<int64_t>(H.n_blocks, 1)));
+  KV_CUDA(ix->d_rt_keys.ensure(std::max<int64_t>(H.n_rt_slots, 1))); KV_CUDA(ix->d_rt_masks.ensure(std::max<int64_t>(H.n_rt_slots, 1)));
+  KV_CUDA(ix->d_ovf_keys.ensure(std::max<int64_t>(H.n_ovf, 1))); KV_CUDA(ix->d_ovf_vals.ensure(std::max<int64_t>(H.n_ovf, 1)));
+  auto up = [&](void *d, const void *h, size_t bytes) { return bytes ? cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess; };
+  KV_CUDA(up(ix->d_perm.p, perm.data(), perm.size() * 4)); KV_CUDA(up(ix->d_blk.p, blk.data(), blk.size() * 4));
+  KV_CUDA(up(ix->d_binfo.p, binfo.data(), binfo.size() * sizeof(BlockInfo))); KV_CUDA(up(ix->d_Uf.p, uf.data(), uf.size() * sizeof(__half)));
+  KV_CUDA(up(ix->d_fslot.p, fslot.data(), fslot.size() * 2)); KV_CUDA(up(ix->d_fslot2.p, fslot2.data(), fslot2.size() * 2));
+  KV_CUDA(up(ix->d_ubt.p, ubt.data(), ubt.size() * 4)); KV_CUDA(up(ix->d_rbloom.p, rbloom.data(), rbloom.size() * 4));
+  KV_CUDA(up(ix->d_rt_off.p, rt_off.data(), rt_off.size() * 4)); KV_CUDA(up(ix->d_rt_size.p, rt_size.data(), rt_size.size() * 4));
+  KV_CUDA(up(ix->d_rt_keys.p, rt_keys.data(), rt_keys.size() * 4)); KV_CUDA(up(ix->d_rt_masks.p, rt_masks.data(), rt_masks.size() * 8));
+  KV_CUDA(up(ix->d_ovf_keys.p, ovf_keys.data(), ovf_keys.size() * 8)); KV_CUDA(up(ix->d_ovf_vals.p, ovf_vals.data(), ovf_vals.size() * 4));
+  if (H.n_rows) {
+    invperm_kernel<<<(unsigned)((H.n_rows + 255) / 256), 256, 0, s>>>(ix->d_perm.p, H.n_rows, ix->d_invperm.p);
+    KV_CUDA(cudaGetLastError());
+  }
+  KV_CUDA(cudaStreamSynchronize(s));
+  {
+    int rc = make_map_f16_nf(&ix->map_u, ix->d_Uf.p, H.n_chunks_pad, B_BN);
+    if (rc != KV_OK) return rc;
+  }
+  ix->h_fslot = fslot; ix->h_fslot2 = fslot2;
+  ix->n_chunks = H.n_chunks; ix->n_chunks_pad = H.n_chunks_pad; ix->blk_words = H.blk_words; ix->n_entries = H.n_entries;
+  ix->n_rare_entries = H.n_rare_entries; ix->n_ovf = (int)H.n_ovf;
+  ix->rare_table_bytes = H.n_rt_slots * 12 + (int64_t)rbloom.size() * 4;
+  ix->layout_valid = H.n_rows > 0;
+  ix->layout_rows = H.n_rows;
+  ix->layout_univ = univ;
+  ix->finalized = false;
+  return KV_OK;
+}

@@ -370,6 +370,23 @@ class GfkbIndex:
                 "records_written": c[12], "kernel_launches": c[13], "rare_entries": c[14],
                 "pool_pages_used": c[15], "pool_pages": c[16]}
 
+    def save_layout(self, path) -> None:
+        """Persist the built scan layout (row order, column blocks, bound structures) of a finalized index."""
+        _capi.check(_capi.load().kv_index_layout_save(self._h, str(path).encode()))
+
+    def load_layout(self, path) -> bool:
+        """After appending the same rows and BEFORE finalize(): restore a persisted layout; False if the file is missing
+        or was built for other rows (finalize then builds as usual)."""
+        import os
+
+        if not os.path.exists(str(path)):
+            return False
+        rc = _capi.load().kv_index_layout_load(self._h, str(path).encode())
+        if rc in (_capi.KV_ERR_STATE, _capi.KV_ERR_INVALID):
+            return False
+        _capi.check(rc)
+        return True
+
     def close(self) -> None:
         if self._h is not None:
             _capi.load().kv_index_destroy(self._h)

@@ -154,7 +154,14 @@ class GfkbStore:
                         _sidecar.save(self.sidecar_path, self.vocab, fb, texts)
                 finally:
                     fb.close()
+            # persisted scan layout next to the sidecar: a cold start then skips the host sort + block build as well
+            lay_path = Path(str(self.sidecar_path) + ".layout") if self.sidecar_path is not None else None
+            restored = lay_path is not None and self._main.load_layout(lay_path)
             self._main.finalize()
+            if restored and self._main.last_finalize_kind == 2:
+                self.stats["layout_restored"] = self.stats.get("layout_restored", 0) + 1
+            elif lay_path is not None:
+                self._main.save_layout(lay_path)
             self.stats["full_rebuilds"] += 1
         self._n_main = self._n_indexed = n
         self._dirty = False

@@ -288,3 +288,36 @@ def test_dense_k32_exclusion_and_device_queries(lib):
         assert 1000 + i not in r2[i].tolist()
     np.testing.assert_array_equal(r2.cpu().numpy()[:, :8] - 1000, rs[:q, :8])
 
+
+
+def test_persisted_layout_gives_identical_results(lib, tmp_path):
+    """an index whose scan layout was restored from the layout file (no host sort / block build:
+    kv_index_last_finalize_kind == 2) returns bit-identical top-k and float64 scores; a file built for other rows is
+    refused; GfkbStore restores it on a cold start next to its sidecar."""
+    from kakveda_b200 import GfkbIndex, synth
+
+    n, q, k = 40_000, 500, 16
+    corpus, queries = synth.corpus(n), synth.queries(q, n)
+    a = GfkbIndex()
+    a.add_texts(corpus)
+    a.finalize()
+    assert a.last_finalize_kind == 1
+    s1, r1 = a.topk(queries, k)
+    f1 = a.score(queries[3])
+    path = tmp_path / "gfkb.layout"
+    a.save_layout(path)
+    b = GfkbIndex()
+    b.add_texts(corpus)
+    assert b.load_layout(path)
+    b.finalize()
+    assert b.last_finalize_kind == 2          # statistics only: nothing was sorted or rebuilt
+    s2, r2 = b.topk(queries, k)
+    np.testing.assert_array_equal(r1, r2)
+    np.testing.assert_array_equal(s1, s2)
+    np.testing.assert_array_equal(f1, b.score(queries[3]))
+    c = GfkbIndex()
+    c.add_texts(corpus[:-1] + ["intent_tags: | prompt_hint:some other row | tools: | env_keys:os"])
+    assert not c.load_layout(path)            # other rows: refused, the usual finalize follows
+    c.finalize()
+    assert c.last_finalize_kind == 1
+    assert not GfkbIndex().load_layout(tmp_path / "missing.layout")
