@@ -321,3 +321,30 @@ def test_persisted_layout_gives_identical_results(lib, tmp_path):
     c.finalize()
     assert c.last_finalize_kind == 1
     assert not GfkbIndex().load_layout(tmp_path / "missing.layout")
+
+
+def test_warn_batch_equals_reference_warn_handler(lib, golden):
+    """services/warning_policy/app.py:19-72 run UNMODIFIED against the reference GFKB (tests/golden/make_golden_warn.py):
+    action, confidence, pattern id, references and the message text of every response are reproduced by
+    GfkbStore.warn_batch under the three recorded policy configurations."""
+    from kakveda_b200 import GfkbStore
+
+    g = golden("service_warn.json")
+    st = GfkbStore()
+    st._reset([dict(r) for r in g["failures"]])
+    for pol in g["policies"]:
+        got = st.warn_batch(g["requests"], threshold=pol["threshold"], default_action=pol["default_action"], patterns=[g["pattern"]])
+        assert len(got) == len(pol["responses"])
+        for a, b in zip(got, pol["responses"]):
+            assert a["action"] == b["action"] and a["pattern_id"] == b["pattern_id"]
+            np.testing.assert_allclose(a["confidence"], b["confidence"], rtol=RTOL64, atol=1e-15)
+            assert len(a["references"]) == len(b["references"])
+            for ra, rb in zip(a["references"], b["references"]):
+                assert (ra["failure_id"], ra["version"], ra["failure_type"], ra["suggested_mitigation"]) == \
+                       (rb["failure_id"], rb["version"], rb["failure_type"], rb["suggested_mitigation"])
+                np.testing.assert_allclose(ra["score"], rb["score"], rtol=RTOL64, atol=1e-15)
+            if b["references"]:
+                # the text embeds the score with two decimals; everything else must match literally
+                assert a["message"] == b["message"]
+            else:
+                assert a["message"] == b["message"] == "No high-similarity match found in GFKB."
