@@ -258,9 +258,13 @@ class ShardedGfkb:
         # single index would scan of its rows
         self.index.topk_resident_seed(k, s.data_ptr(), r.data_ptr())
         ev[0].record()
-        seeds = gather_packed(buf, self.group)
-        ms, _ = merge_packed_on_device(self.device, seeds, q, k)
-        kth = ms[:, k - 1].contiguous()
+        # only the seed SCORES travel (6.4 MB per rank at 100k queries): the global k-th seed score of a query is the k-th
+        # largest of the W x k gathered scores (the shards hold disjoint rows)
+        import torch.distributed as dist
+
+        gs = torch.empty((self.world, q, k), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(gs.view(-1), s.contiguous().view(-1), group=self.group)
+        kth = torch.topk(gs.permute(1, 0, 2).reshape(q, self.world * k), k, dim=1).values[:, k - 1].contiguous()
         ev[1].record()
         torch.cuda.current_stream().synchronize()
         self.index.raise_thresholds(kth.data_ptr(), q)
