@@ -368,6 +368,10 @@ def run_ours(a):
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     h2d = shard.index.layout()["last_upload_bytes"]
     d2h = a.queries * a.k * 12
+    split = getattr(shard, "last_prepare_split_ms", None)
+    if world > 1 and split:      # sliced preparation: the rank's slice goes up, the gathered slices come back, the batch goes up
+        h2d += split["slice_bytes"]
+        d2h += split["slice_bytes"] * world
     assert int(er.sum()) == checksum, "end-to-end result differs from the resident-path result"
 
     # ---- roofline of the path, SURVEY section 8(d) accounting ----

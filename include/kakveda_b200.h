@@ -168,6 +168,17 @@ int kv_topk_device(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids,
  * when it has completed.  The batch stays valid until the next upload or finalize. */
 int kv_query_upload(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
                     const double *q_oov_tf2, int64_t n_q);
+/* The same upload for a batch that arrives as n_runs consecutive slices (a row-sharded GFKB featurises one slice per
+ * rank and exchanges them, kakveda_b200/dist.py): per run a CSR, optionally its classification flags and its text order
+ * as kv_query_prepare_slice returned them on the rank that owns the slice (all runs or none; the orders are merged
+ * instead of re-sorted).  The resulting batch is identical to kv_query_upload of the concatenated CSR. */
+int kv_query_prepare_slice(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf, int64_t n_q,
+                           int32_t *order_out, uint8_t *flags_out);
+int kv_query_upload_runs(kv_index *ix, int n_runs, const int64_t *const *q_indptr, const uint32_t *const *q_ids,
+                         const uint32_t *const *q_tf, const double *const *q_oov_tf2, const int32_t *const *order,
+                         const uint8_t *const *flags, const int64_t *n_q);
+/* Host-side split of the last upload in ms: pinned staging, classification, text order, copies + table kernels. */
+int kv_index_last_prepare_ms(const kv_index *ix, float ms[4]);
 int kv_topk_resident(kv_index *ix, int k, void *d_scores, void *d_rows);
 /* Same with host outputs (out_scores float32[n_q*k], out_rows int64[n_q*k]). */
 int kv_topk_resident_host(kv_index *ix, int k, float *out_scores, int64_t *out_rows);

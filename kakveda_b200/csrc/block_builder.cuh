@@ -37,10 +37,52 @@ inline void idf_host(int64_t n_total, uint32_t df, double &a, double &d, int jac
 }
 
 // ---- index sort: result == std::stable_sort(order = 0..n-1, less) for any strict weak ordering `less` ----
+// Two adjacent sorted runs first[0, n1) and first[n1, n1 + n2) merged on P threads: the first run is cut into P
+// pieces, each piece merges with the elements of the second run that fall between its end points.  `total` is a
+// total order (no two elements compare equal), so the cut points are unambiguous.
+template <class Total>
+void parallel_merge(int *first, int64_t n1, int64_t n2, int *tmp, Total total, int P) {
+  if (n1 == 0 || n2 == 0) return;
+  P = (int)std::max<int64_t>(1, std::min<int64_t>(P, n1 / 2048));
+  std::vector<int64_t> s1((size_t)P + 1), s2((size_t)P + 1);
+  for (int p = 0; p <= P; p++) {
+    s1[(size_t)p] = n1 * p / P;
+    s2[(size_t)p] = p == 0 ? 0 : (p == P ? n2 : std::lower_bound(first + n1, first + n1 + n2, first[s1[(size_t)p]], total) - (first + n1));
+  }
+  parallel_for(P, P, [&](int, int64_t a, int64_t b) {
+    for (int64_t p = a; p < b; p++) {
+      std::merge(first + s1[(size_t)p], first + s1[(size_t)p + 1], first + n1 + s2[(size_t)p], first + n1 + s2[(size_t)p + 1],
+                 tmp + s1[(size_t)p] + s2[(size_t)p], total);
+    }
+  });
+  parallel_for(n1 + n2, P, [&](int, int64_t a, int64_t b) { std::copy(tmp + a, tmp + b, first + a); });  // after ALL merges
+}
+
+// order holds consecutive runs [cut[i], cut[i+1]) that are each sorted by (less, index): merged pairwise, every level on
+// all T threads.
+template <class Less>
+void merge_sorted_runs(std::vector<int> &order, const std::vector<int64_t> &cut, Less less, int T) {
+  auto total = [&](int a, int b) { return less(a, b) || (!less(b, a) && a < b); };  // ties by index == stability
+  const int runs = (int)cut.size() - 1;
+  std::vector<int> tmp(order.size());
+  for (int width = 1; width < runs; width *= 2) {
+    const int merges = (runs + 2 * width - 1) / (2 * width);
+    const int per = std::max(1, T / merges);
+    parallel_for(merges, std::min(merges, std::max(T, 1)), [&](int, int64_t a, int64_t b) {
+      for (int64_t m = a; m < b; m++) {
+        const int lo = (int)(m * 2 * width), mid = std::min(runs, lo + width), hi = std::min(runs, lo + 2 * width);
+        if (mid < hi)
+          parallel_merge(order.data() + cut[(size_t)lo], cut[(size_t)mid] - cut[(size_t)lo], cut[(size_t)hi] - cut[(size_t)mid],
+                         tmp.data() + cut[(size_t)lo], total, per);
+      }
+    });
+  }
+}
+
 template <class Less>
 void stable_sort_indices(std::vector<int> &order, Less less, int T) {
   const int64_t n = (int64_t)order.size();
-  auto total = [&](int a, int b) { return less(a, b) || (!less(b, a) && a < b); };  // ties by index == stability
+  auto total = [&](int a, int b) { return less(a, b) || (!less(b, a) && a < b); };
   int parts = 1;
   if (n >= 8192) while (parts * 2 <= T && parts < 64) parts *= 2;
   std::vector<int64_t> cut((size_t)parts + 1);
@@ -48,14 +90,7 @@ void stable_sort_indices(std::vector<int> &order, Less less, int T) {
   parallel_for(parts, parts, [&](int, int64_t a, int64_t b) {
     for (int64_t i = a; i < b; i++) std::sort(order.begin() + cut[(size_t)i], order.begin() + cut[(size_t)i + 1], total);
   });
-  for (int width = 1; width < parts; width *= 2) {
-    const int merges = parts / (2 * width);
-    parallel_for(merges, merges, [&](int, int64_t a, int64_t b) {
-      for (int64_t m = a; m < b; m++)
-        std::inplace_merge(order.begin() + cut[(size_t)(m * 2 * width)], order.begin() + cut[(size_t)(m * 2 * width + width)],
-                           order.begin() + cut[(size_t)(m * 2 * width + 2 * width)], total);
-    });
-  }
+  merge_sorted_runs(order, cut, less, T);
 }
 
 // ---- column blocks ----

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -148,6 +149,7 @@ struct kv_index {
 
   float *dbg_xs = nullptr;  // test hook (kv_debug_bound_numerators)
   float last_ms[4] = {0, 0, 0, 0};
+  float last_prepare_ms[4] = {0, 0, 0, 0};  // host side of the last upload: staging, classification, text order, copies + table kernels
   float last_kernel_ms[5] = {0, 0, 0, 0, 0};  // bound pass 0, seed scan, bound pass 1, scan, merge
   float last_score_ms = 0;
   int64_t last_ctas = 0, last_tiles = 0, last_splits = 0, last_launches = 0;
@@ -691,27 +693,24 @@ int kv_score(kv_index *ix, const uint32_t *q_ids, const uint32_t *q_tf, int64_t 
 }
 
 // ---- batched top-k, in two halves: prepare_batch (host work + H2D + table kernels) and run_batch (device only) ----
-static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
-                         const double *q_oov, int64_t n_q) {
-  if (!ix->finalized) return kv_fail(KV_ERR_STATE, "kv_topk: index not finalized");
-  if (n_q >= (1LL << 31) - TILE_Q) return kv_fail(KV_ERR_INVALID, "kv_topk: too many queries in one call");
-  KV_CUDA(cudaSetDevice(ix->device));
-  cudaStream_t s = ix->stream;
-  ix->batch_valid = false;
-  ix->has_excl = false;
-  ix->irr_q.clear(); ix->irr_indptr.assign(1, 0); ix->irr_ids.clear(); ix->irr_tf.clear(); ix->irr_oov.clear();
-  for (int64_t q = 0; q < n_q; q++)
-    if (q_indptr[q + 1] < q_indptr[q] || (q_indptr[q + 1] > q_indptr[q] && (!q_ids || !q_tf)))
-      return kv_fail(KV_ERR_INVALID, "kv_topk: bad query CSR");
-  const int64_t base = q_indptr[0], nnz = q_indptr[n_q] - base;
-  const int T = host_threads();
+// A query batch arrives as one CSR or as several consecutive "runs" (a row-sharded GFKB featurises one slice of the
+// batch per rank and exchanges the slices, kakveda_b200/dist.py); a run may bring its own classification flags and its
+// own text order (kv_query_prepare_slice), which are then merged instead of recomputed.
+struct QueryRun {
+  const int64_t *indptr = nullptr;
+  const uint32_t *ids = nullptr, *tf = nullptr;
+  const double *oov = nullptr;
+  const int32_t *order = nullptr;   // optional: the run's queries sorted by feature-id sequence (ties by index)
+  const uint8_t *flags = nullptr;   // optional: 0 regular, 1 null, 2 irregular
+  int64_t n_q = 0;
+};
 
-  // ---- host: classification of the queries, text order, pinned staging of the CSR ----
-  // null: no feature of the query is in the index (every score is 0).  irregular: more features than a query table
-  // holds, or term frequencies so large that the 64-bit fixed-point sums or the fp16 bound weights could overflow --
-  // such a query takes the float64 full-scan path (K1a + selection).
+// null: no feature of the query is in the index (every score is 0).  irregular: more features than a query table
+// holds, or term frequencies so large that the 64-bit fixed-point sums or the fp16 bound weights could overflow --
+// such a query takes the float64 full-scan path (K1a + selection).
+static void classify_queries(const kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
+                             int64_t n_q, uint8_t *flag, int T) {
   const double amax = ix->jaccard ? 1.0 : std::pow(std::log((double)(ix->n_total + 2)) + 1.0, 2.0);
-  std::vector<uint8_t> flag((size_t)n_q, 0);
   parallel_for(n_q, n_q >= 2048 ? T : 1, [&](int, int64_t a, int64_t b) {
     for (int64_t q = a; q < b; q++) {
       bool known = false;
@@ -728,23 +727,109 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
         s_corr += tm * tm;
         wmax = std::max(wmax, f);
       }
-      if (!known) flag[(size_t)q] = 1;
+      flag[q] = 0;
+      if (!known) flag[q] = 1;
       else if (feats > QFEATS || s_dot * amax >= 1073741824.0 || s_corr * 32.0 >= 1073741824.0 || wmax * amax > 60000.0)
-        flag[(size_t)q] = 2;
+        flag[q] = 2;
     }
   });
-  // queries with similar text share a scan group and a bound tile (their candidates are largely the same chunks)
-  std::vector<int> order((size_t)n_q);
-  for (int64_t q = 0; q < n_q; q++) order[(size_t)q] = (int)q;
-  stable_sort_indices(order, [&](int a, int b) {
-    return cmp_seq(q_ids + q_indptr[a], q_indptr[a + 1] - q_indptr[a], q_ids + q_indptr[b], q_indptr[b + 1] - q_indptr[b]) < 0;
-  }, T);  // == std::stable_sort, on all host threads
+}
+
+static bool csr_ok(const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf, int64_t n_q) {
+  for (int64_t q = 0; q < n_q; q++)
+    if (q_indptr[q + 1] < q_indptr[q] || (q_indptr[q + 1] > q_indptr[q] && (!q_ids || !q_tf))) return false;
+  return true;
+}
+
+static int prepare_batch_runs(kv_index *ix, const QueryRun *runs, int n_runs) {
+  if (!ix->finalized) return kv_fail(KV_ERR_STATE, "kv_topk: index not finalized");
+  int64_t n_q = 0, nnz = 0;
+  std::vector<int64_t> qb((size_t)n_runs + 1, 0), nb((size_t)n_runs + 1, 0);
+  bool have_order = true, have_flags = true;
+  for (int r = 0; r < n_runs; r++) {
+    const QueryRun &R = runs[r];
+    if (R.n_q < 0 || !R.indptr || !csr_ok(R.indptr, R.ids, R.tf, R.n_q)) return kv_fail(KV_ERR_INVALID, "kv_topk: bad query CSR");
+    n_q += R.n_q;
+    nnz += R.indptr[R.n_q] - R.indptr[0];
+    qb[(size_t)r + 1] = n_q;
+    nb[(size_t)r + 1] = nnz;
+    have_order = have_order && (R.order || R.n_q == 0);
+    have_flags = have_flags && (R.flags || R.n_q == 0);
+  }
+  if (n_q < 1) return kv_fail(KV_ERR_INVALID, "kv_topk: empty query batch");
+  if (n_q >= (1LL << 31) - TILE_Q) return kv_fail(KV_ERR_INVALID, "kv_topk: too many queries in one call");
+  KV_CUDA(cudaSetDevice(ix->device));
+  cudaStream_t s = ix->stream;
+  ix->batch_valid = false;
+  ix->has_excl = false;
+  ix->irr_q.clear(); ix->irr_indptr.assign(1, 0); ix->irr_ids.clear(); ix->irr_tf.clear(); ix->irr_oov.clear();
+  const int T = host_threads();
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto ms_since = [](std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  };
+
+  // ---- host: pinned staging of the CSR (the runs back to back), classification, text order ----
   KV_CUDA(ix->h_qperm.ensure(2 * n_q));
   KV_CUDA(ix->h_flags.ensure(n_q));
   KV_CUDA(ix->h_q_indptr.ensure(n_q + 1));
   KV_CUDA(ix->h_q_ids.ensure(std::max<int64_t>(nnz, 1)));
   KV_CUDA(ix->h_q_tf.ensure(std::max<int64_t>(nnz, 1)));
   KV_CUDA(ix->h_q_oov.ensure(n_q));
+  for (int r = 0; r < n_runs; r++) {
+    const QueryRun &R = runs[r];
+    const int64_t base = R.indptr[0], rn = R.indptr[R.n_q] - base, q0 = qb[(size_t)r], p0 = nb[(size_t)r];
+    parallel_for(R.n_q, R.n_q >= 65536 ? T : 1, [&](int, int64_t a, int64_t b) {
+      for (int64_t q = a; q < b; q++) {
+        ix->h_q_indptr.p[q0 + q] = R.indptr[q] - base + p0;
+        ix->h_q_oov.p[q0 + q] = R.oov ? R.oov[q] : 0.0;
+      }
+    });
+    parallel_for(rn, rn >= (1 << 20) ? T : 1, [&](int, int64_t a, int64_t b) {
+      if (b > a) {
+        memcpy(ix->h_q_ids.p + p0 + a, R.ids + base + a, (size_t)(b - a) * 4);
+        memcpy(ix->h_q_tf.p + p0 + a, R.tf + base + a, (size_t)(b - a) * 4);
+      }
+    });
+  }
+  ix->h_q_indptr.p[n_q] = nnz;
+  const int64_t *q_indptr = ix->h_q_indptr.p;
+  const uint32_t *q_ids = ix->h_q_ids.p, *q_tf = ix->h_q_tf.p;
+  const double *q_oov = ix->h_q_oov.p;
+  ix->last_prepare_ms[0] = ms_since(t_begin);
+  auto t_mark = std::chrono::steady_clock::now();
+
+  std::vector<uint8_t> flag((size_t)n_q, 0);
+  if (have_flags) {
+    for (int r = 0; r < n_runs; r++)
+      if (runs[r].n_q) memcpy(flag.data() + qb[(size_t)r], runs[r].flags, (size_t)runs[r].n_q);
+  } else {
+    classify_queries(ix, q_indptr, q_ids, q_tf, n_q, flag.data(), T);
+  }
+  ix->last_prepare_ms[1] = ms_since(t_mark);
+  t_mark = std::chrono::steady_clock::now();
+  // queries with similar text share a scan group and a bound tile (their candidates are largely the same chunks)
+  std::vector<int> order((size_t)n_q);
+  auto less_text = [&](int a, int b) {
+    return cmp_seq(q_ids + q_indptr[a], q_indptr[a + 1] - q_indptr[a], q_ids + q_indptr[b], q_indptr[b + 1] - q_indptr[b]) < 0;
+  };
+  if (have_order) {
+    // the runs arrive sorted: merge them (a run's queries precede the next run's, so a stable merge == the full sort)
+    std::vector<uint8_t> seen((size_t)n_q, 0);
+    for (int r = 0; r < n_runs; r++)
+      for (int64_t i = 0; i < runs[r].n_q; i++) {
+        const int32_t o = runs[r].order[i];
+        if (o < 0 || o >= runs[r].n_q || seen[(size_t)(qb[(size_t)r] + o)]++)
+          return kv_fail(KV_ERR_INVALID, "kv_query_upload_runs: a slice order is not a permutation");
+        order[(size_t)(qb[(size_t)r] + i)] = (int)(qb[(size_t)r] + o);
+      }
+    if (n_runs > 1) merge_sorted_runs(order, qb, less_text, T);
+  } else {
+    for (int64_t q = 0; q < n_q; q++) order[(size_t)q] = (int)q;
+    stable_sort_indices(order, less_text, T);  // == std::stable_sort, on all host threads
+  }
+  ix->last_prepare_ms[2] = ms_since(t_mark);
+  t_mark = std::chrono::steady_clock::now();
   int *qperm = ix->h_qperm.p, *null_list = qperm + n_q;
   int64_t n_null = 0;
   for (int64_t i = 0; i < n_q; i++) {
@@ -759,21 +844,9 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
       ix->irr_ids.insert(ix->irr_ids.end(), q_ids + a, q_ids + b);
       ix->irr_tf.insert(ix->irr_tf.end(), q_tf + a, q_tf + b);
       ix->irr_indptr.push_back((int64_t)ix->irr_ids.size());
-      ix->irr_oov.push_back(q_oov ? q_oov[q] : 0.0);
+      ix->irr_oov.push_back(q_oov[q]);
     }
   }
-  parallel_for(n_q + 1, n_q >= 65536 ? T : 1, [&](int, int64_t a, int64_t b) {
-    for (int64_t q = a; q < b; q++) {
-      ix->h_q_indptr.p[q] = q_indptr[q] - base;
-      if (q < n_q) ix->h_q_oov.p[q] = q_oov ? q_oov[q] : 0.0;
-    }
-  });
-  parallel_for(nnz, nnz >= (1 << 20) ? T : 1, [&](int, int64_t a, int64_t b) {
-    if (b > a) {
-      memcpy(ix->h_q_ids.p + a, q_ids + base + a, (size_t)(b - a) * 4);
-      memcpy(ix->h_q_tf.p + a, q_tf + base + a, (size_t)(b - a) * 4);
-    }
-  });
 
   const int64_t n_tiles = (n_q + TILE_Q - 1) / TILE_Q, n_q_pad = n_tiles * TILE_Q;
   KV_CUDA(ix->d_q_indptr.ensure(n_q + 1));
@@ -826,7 +899,15 @@ static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *
   ix->batch_h2d_bytes = (n_q + 1) * 8 + nnz * 8 + n_q * 8 + 2 * n_q * (int64_t)sizeof(int) + n_q;
   ix->batch_valid = true;
   cudaEventElapsedTime(&ix->last_ms[0], ix->ev[0], ix->ev[1]);
+  ix->last_prepare_ms[3] = ms_since(t_mark);
   return KV_OK;
+}
+
+static int prepare_batch(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
+                         const double *q_oov, int64_t n_q) {
+  QueryRun R;
+  R.indptr = q_indptr; R.ids = q_ids; R.tf = q_tf; R.oov = q_oov; R.n_q = n_q;
+  return prepare_batch_runs(ix, &R, 1);
 }
 
 // Device-only half: bounds + scans + merge (+ fallback scans for irregular queries) of the uploaded batch.
@@ -1139,6 +1220,47 @@ int kv_query_upload(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids
   if (!ix || n_q < 1 || !q_indptr) return kv_fail(KV_ERR_INVALID, "kv_query_upload: bad arguments");
   std::lock_guard<std::mutex> g(ix->mu);
   return prepare_batch(ix, q_indptr, q_ids, q_tf, q_oov_tf2, n_q);
+}
+
+// A slice of a query batch prepared where it was featurised: its text order and its classification flags.
+int kv_query_prepare_slice(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf, int64_t n_q,
+                           int32_t *order_out, uint8_t *flags_out) {
+  if (!ix || n_q < 0 || !q_indptr || !order_out || !flags_out) return kv_fail(KV_ERR_INVALID, "kv_query_prepare_slice: bad arguments");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (!ix->finalized) return kv_fail(KV_ERR_STATE, "kv_query_prepare_slice: index not finalized");
+  if (n_q >= (1LL << 31) - TILE_Q || !csr_ok(q_indptr, q_ids, q_tf, n_q)) return kv_fail(KV_ERR_INVALID, "kv_query_prepare_slice: bad query CSR");
+  const int T = host_threads();
+  classify_queries(ix, q_indptr, q_ids, q_tf, n_q, flags_out, T);
+  std::vector<int> order((size_t)n_q);
+  for (int64_t q = 0; q < n_q; q++) order[(size_t)q] = (int)q;
+  stable_sort_indices(order, [&](int a, int b) {
+    return cmp_seq(q_ids + q_indptr[a], q_indptr[a + 1] - q_indptr[a], q_ids + q_indptr[b], q_indptr[b + 1] - q_indptr[b]) < 0;
+  }, T);
+  for (int64_t q = 0; q < n_q; q++) order_out[q] = order[(size_t)q];
+  return KV_OK;
+}
+
+// kv_query_upload of a batch that arrives as n_runs consecutive slices (run r holds queries [sum n_q[<r], ...)).
+int kv_query_upload_runs(kv_index *ix, int n_runs, const int64_t *const *q_indptr, const uint32_t *const *q_ids,
+                         const uint32_t *const *q_tf, const double *const *q_oov_tf2, const int32_t *const *order,
+                         const uint8_t *const *flags, const int64_t *n_q) {
+  if (!ix || n_runs < 1 || !q_indptr || !q_ids || !q_tf || !n_q) return kv_fail(KV_ERR_INVALID, "kv_query_upload_runs: bad arguments");
+  std::vector<QueryRun> runs((size_t)n_runs);
+  for (int r = 0; r < n_runs; r++) {
+    QueryRun &R = runs[(size_t)r];
+    R.indptr = q_indptr[r]; R.ids = q_ids[r]; R.tf = q_tf[r]; R.n_q = n_q[r];
+    R.oov = q_oov_tf2 ? q_oov_tf2[r] : nullptr;
+    R.order = order ? order[r] : nullptr;
+    R.flags = flags ? flags[r] : nullptr;
+  }
+  std::lock_guard<std::mutex> g(ix->mu);
+  return prepare_batch_runs(ix, runs.data(), n_runs);
+}
+
+int kv_index_last_prepare_ms(const kv_index *ix, float ms[4]) {
+  if (!ix || !ms) return kv_fail(KV_ERR_INVALID, "kv_index_last_prepare_ms: bad arguments");
+  for (int i = 0; i < 4; i++) ms[i] = ix->last_prepare_ms[i];
+  return KV_OK;
 }
 
 static int set_exclusions_locked(kv_index *ix, const int64_t *exclude_rows, int64_t n_q);

@@ -18,6 +18,7 @@ CPU; the compute stays in libkakveda_b200 (CUDA only).
 from __future__ import annotations
 
 import ctypes as C
+import os
 import sys
 from typing import Optional, Tuple
 
@@ -287,12 +288,109 @@ class ShardedGfkb:
         self.upload(qfb)
         self._resident_q = qfb.n
 
+    # ---- sharded preparation of a query batch (rows mode, world > 1) -------------------------------------------------
+    @staticmethod
+    def _slice_layout(nq_cap: int, nnz_cap: int):
+        """Byte offsets of one rank's slot in the exchanged buffer: header int64[2] (queries, entries) | indptr
+        int64[nq_cap+1] | oov float64[nq_cap] | order int32[nq_cap] | flags uint8[nq_cap] | ids uint32[nnz_cap] | tf."""
+        al = lambda x: (x + 15) & ~15
+        o_ip = 16
+        o_oov = al(o_ip + 8 * (nq_cap + 1))
+        o_ord = al(o_oov + 8 * nq_cap)
+        o_fl = al(o_ord + 4 * nq_cap)
+        o_ids = al(o_fl + nq_cap)
+        o_tf = al(o_ids + 4 * nnz_cap)
+        return o_ip, o_oov, o_ord, o_fl, o_ids, o_tf, al(o_tf + 4 * nnz_cap)
+
+    def upload_text_sharded(self, data, offsets: np.ndarray, mode: int = 0) -> int:
+        """Rows mode on several GPUs: every rank featurises, classifies and text-sorts only ITS slice of the query batch
+        (1/world of the host work), the slices travel in one all-gather over NVLink (plus a 16-byte one for the sizes),
+        and every rank uploads the assembled batch with the slice orders merged instead of re-sorted.  The resident
+        batch is identical to ``upload(featurize(all queries))``.  Returns the number of queries."""
+        import time
+
+        import torch
+        import torch.distributed as dist
+
+        t0 = time.perf_counter()
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n_q = len(offsets) - 1
+        dev = f"cuda:{self.device}"
+        lo, hi = shard_bounds(n_q, self.world, self.rank)
+        qfb = self.vocab.featurize_packed(data, offsets[lo:hi + 1], mode, grow=False)
+        try:
+            t1 = time.perf_counter()
+            order, flags = self.index.prepare_slice(qfb)
+            n_loc, nnz = qfb.n, int(qfb.indptr[qfb.n] - qfb.indptr[0])
+            sizes = torch.tensor([n_loc, nnz], dtype=torch.int64).to(dev)
+            all_sizes = torch.empty((self.world, 2), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(all_sizes.view(-1), sizes, group=self.group)
+            all_sizes = all_sizes.cpu().numpy()
+            nq_cap, nnz_cap = int(all_sizes[:, 0].max()), int(all_sizes[:, 1].max())
+            o_ip, o_oov, o_ord, o_fl, o_ids, o_tf, slot = self._slice_layout(nq_cap, nnz_cap)
+            if getattr(self, "_xq_cap", 0) < slot:           # pinned staging + device buffers, grown geometrically
+                cap = max(slot, 2 * getattr(self, "_xq_cap", 0))
+                self._xq_send = torch.empty(cap, dtype=torch.uint8).pin_memory()
+                self._xq_recv = torch.empty(cap * self.world, dtype=torch.uint8).pin_memory()
+                self._xq_dsend = torch.empty(cap, dtype=torch.uint8, device=dev)
+                self._xq_drecv = torch.empty(cap * self.world, dtype=torch.uint8, device=dev)
+                self._xq_cap = cap
+            send = self._xq_send.numpy()
+            send[0:16].view(np.int64)[:] = (n_loc, nnz)
+            send[o_ip:o_ip + 8 * (n_loc + 1)].view(np.int64)[:] = qfb.indptr - qfb.indptr[0]
+            send[o_oov:o_oov + 8 * n_loc].view(np.float64)[:] = qfb.oov
+            send[o_ord:o_ord + 4 * n_loc].view(np.int32)[:] = order
+            send[o_fl:o_fl + n_loc] = flags
+            base = int(qfb.indptr[0])
+            send[o_ids:o_ids + 4 * nnz].view(np.uint32)[:] = qfb.ids[base:base + nnz]
+            send[o_tf:o_tf + 4 * nnz].view(np.uint32)[:] = qfb.tf[base:base + nnz]
+            self._xq_dsend[:slot].copy_(self._xq_send[:slot], non_blocking=True)
+            dist.all_gather_into_tensor(self._xq_drecv[:slot * self.world], self._xq_dsend[:slot], group=self.group)
+            self._xq_recv[:slot * self.world].copy_(self._xq_drecv[:slot * self.world], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            t2 = time.perf_counter()
+            recv = self._xq_recv.numpy()
+            runs = []
+            for w in range(self.world):
+                b = recv[w * slot:(w + 1) * slot]
+                nq_w, nnz_w = (int(x) for x in b[0:16].view(np.int64))
+                if (nq_w, nnz_w) != (int(all_sizes[w, 0]), int(all_sizes[w, 1])):
+                    raise RuntimeError("query-slice exchange: header does not match the announced sizes")
+                runs.append((b[o_ip:o_ip + 8 * (nq_w + 1)].view(np.int64), b[o_ids:o_ids + 4 * nnz_w].view(np.uint32),
+                             b[o_tf:o_tf + 4 * nnz_w].view(np.uint32), b[o_oov:o_oov + 8 * nq_w].view(np.float64),
+                             b[o_ord:o_ord + 4 * nq_w].view(np.int32), b[o_fl:o_fl + nq_w]))
+            got = self.index.upload_query_runs(runs)
+            if got != n_q:
+                raise RuntimeError(f"query-slice exchange: {got} queries assembled, {n_q} expected")
+            self._exchange_thresholds(n_q)
+            self._resident_q = n_q
+            t3 = time.perf_counter()
+            self.last_prepare_split_ms = {"featurize_slice": 1e3 * (t1 - t0), "slice_order_and_exchange": 1e3 * (t2 - t1),
+                                          "assemble_and_upload": 1e3 * (t3 - t2),
+                                          "slice_bytes": int(slot), "upload_host_ms": self.index.last_prepare_ms()}
+            return n_q
+        finally:
+            qfb.close()
+
     def topk_packed(self, data, offsets: np.ndarray, k: int, mode: int = 0):
         """End-to-end step from host text: featurise, upload, scan, exchange, merge, read back.  ``last_e2e_ms`` keeps
         the wall-clock split of the last call (featurise / upload incl. table kernels / device step / read-back)."""
         import time
 
         t0 = time.perf_counter()
+        if self.world > 1 and self.mode == "rows" and os.environ.get("KAKVEDA_B200_NO_SLICED_PREP") != "1":
+            import torch
+
+            self.upload_text_sharded(data, offsets, mode)
+            t2 = time.perf_counter()
+            s, r = self.topk_resident(k)
+            torch.cuda.current_stream().synchronize()
+            t3 = time.perf_counter()
+            out = s.cpu().numpy(), r.cpu().numpy()
+            t4 = time.perf_counter()
+            self.last_e2e_ms = {"prepare_sharded": 1e3 * (t2 - t0), "device_step": 1e3 * (t3 - t2), "read_back": 1e3 * (t4 - t3),
+                                "prepare_split": self.last_prepare_split_ms}
+            return out
         qfb = self.vocab.featurize_packed(data, offsets, mode, grow=False)
         try:
             t1 = time.perf_counter()
@@ -306,7 +404,8 @@ class ShardedGfkb:
             out = s.cpu().numpy(), r.cpu().numpy()
             t4 = time.perf_counter()
             self.last_e2e_ms = {"featurize": 1e3 * (t1 - t0), "upload": 1e3 * (t2 - t1), "device_step": 1e3 * (t3 - t2),
-                                "read_back": 1e3 * (t4 - t3)}
+                                "read_back": 1e3 * (t4 - t3),
+                                "upload_host_ms": self.index.last_prepare_ms()}  # staging, classification, order, copies+tables
             return out
         finally:
             qfb.close()

@@ -285,6 +285,45 @@ class GfkbIndex:
         _capi.check(_capi.load().kv_query_upload(self._h, _ptr(fb.indptr, C.c_int64), _ptr(fb.ids, C.c_uint32),
                                                  _ptr(fb.tf, C.c_uint32), _ptr(fb.oov, C.c_double), fb.n))
 
+    def prepare_slice(self, fb) -> Tuple[np.ndarray, np.ndarray]:
+        """Text order (int32 permutation) and classification flags (uint8) of a slice of a query batch; what
+        ``upload_query_runs`` merges instead of recomputing (a row-sharded GFKB prepares one slice per rank)."""
+        order = np.empty(fb.n, dtype=np.int32)
+        flags = np.empty(fb.n, dtype=np.uint8)
+        _capi.check(_capi.load().kv_query_prepare_slice(self._h, _ptr(fb.indptr, C.c_int64), _ptr(fb.ids, C.c_uint32),
+                                                        _ptr(fb.tf, C.c_uint32), fb.n, _ptr(order, C.c_int32),
+                                                        _ptr(flags, C.c_uint8)))
+        return order, flags
+
+    def upload_query_runs(self, runs) -> int:
+        """``upload_queries`` of a batch given as consecutive slices: ``runs`` is a list of
+        ``(indptr, ids, tf, oov, order, flags)`` NumPy arrays (``order``/``flags`` from ``prepare_slice``, or None for
+        all runs).  Returns the number of queries."""
+        n = len(runs)
+        arr = lambda: (C.c_void_p * n)()
+        ip, ids, tf, oov, od, fl = arr(), arr(), arr(), arr(), arr(), arr()
+        nq = np.empty(n, dtype=np.int64)
+        with_prep = all(r[4] is not None and r[5] is not None for r in runs)
+        keep = []
+        for i, r in enumerate(runs):
+            cols = [np.ascontiguousarray(r[0], dtype=np.int64), np.ascontiguousarray(r[1], dtype=np.uint32),
+                    np.ascontiguousarray(r[2], dtype=np.uint32), np.ascontiguousarray(r[3], dtype=np.float64)]
+            if with_prep:
+                cols += [np.ascontiguousarray(r[4], dtype=np.int32), np.ascontiguousarray(r[5], dtype=np.uint8)]
+            keep.append(cols)
+            nq[i] = len(cols[0]) - 1
+            for dst, c in zip((ip, ids, tf, oov, od, fl), cols):
+                dst[i] = c.ctypes.data
+        _capi.check(_capi.load().kv_query_upload_runs(self._h, n, ip, ids, tf, oov, od if with_prep else None,
+                                                      fl if with_prep else None, _ptr(nq, C.c_int64)))
+        return int(nq.sum())
+
+    def last_prepare_ms(self) -> Tuple[float, float, float, float]:
+        """Host-side split of the last upload: pinned staging, classification, text order, copies + table kernels."""
+        ms = (C.c_float * 4)()
+        _capi.check(_capi.load().kv_index_last_prepare_ms(self._h, ms))
+        return tuple(ms)
+
     def set_exclusions(self, rows: Optional[np.ndarray]) -> None:
         """Query q of the resident batch must not match GLOBAL row ``rows[q]`` (-1 = none); ``None`` clears."""
         if rows is None:

@@ -38,7 +38,8 @@ def _worker(rank, world, port, n, q, k, tmp, mode):
         np.save(Path(tmp, f"s{rank}{mode}.npy"), s)
         np.save(Path(tmp, f"r{rank}{mode}.npy"), r)
         lay = sh.index.layout()
-        Path(tmp, f"info{rank}{mode}.txt").write_text(f"{getattr(sh, 'n_threshold_peers', 0)} {lay['pairs_scored']}")
+        sliced = int("prepare_sharded" in sh.last_e2e_ms)   # rows mode: every rank prepared only its slice of the batch
+        Path(tmp, f"info{rank}{mode}.txt").write_text(f"{getattr(sh, 'n_threshold_peers', 0)} {lay['pairs_scored']} {sliced}")
     finally:
         dist.destroy_process_group()
 
@@ -71,6 +72,7 @@ def test_two_rank_sharded_topk(built_lib, tmp_path, mode):
         # the shards exchanged their pruning-threshold arrays over CUDA IPC (NVLink peer memory): one peer each
         peers = [int((tmp_path / f"info{rk}{mode}.txt").read_text().split()[0]) for rk in (0, 1)]
         assert peers == [1, 1], peers
+        assert [int((tmp_path / f"info{rk}{mode}.txt").read_text().split()[2]) for rk in (0, 1)] == [1, 1]
 
 
 def _dense_worker(rank, world, port, n, d, q, tmp):

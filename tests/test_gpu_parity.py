@@ -292,6 +292,53 @@ def test_pruned_scan_equals_exhaustive_scan(lib):
             assert a == b or full[a] == pytest.approx(full[b], rel=RTOL32)
 
 
+def test_query_batch_uploaded_as_slices_equals_whole_batch(lib):
+    """kv_query_upload_runs (what a row-sharded GFKB's ranks exchange: slices featurised, classified and text-sorted
+    separately, orders merged) leaves the same resident batch as kv_query_upload of the whole CSR: identical results
+    and identical pruning work."""
+    from kakveda_b200 import GfkbIndex, synth
+    from kakveda_b200.similarity import pack_texts
+
+    n, k = 120_000, 16
+    buf, off = synth.signatures_packed(synth.CORPUS_SEED, 0, n)
+    ix = GfkbIndex()
+    fb = ix.vocab.featurize_packed(buf, off, 0, grow=True)
+    ix.add_features(fb)
+    fb.close()
+    ix.finalize()
+    queries = synth.queries(5000, n) + ["", "zz qq unseen", "intent_tags prompt_hint tools env_keys", " ".join(f"w{i}" for i in range(200))]
+    nq = len(queries)
+    s1, r1 = ix.topk(queries, k)
+    lay1 = ix.layout()
+    data, offsets, mode = pack_texts(queries)
+    for cuts in ([0, nq], [0, 1700, 1700, 4100, nq], [0, 7, nq - 3, nq]):       # one run; an empty run; tiny runs
+        for with_prep in (True, False):
+            runs, keep = [], []
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                qfb = ix.vocab.featurize_packed(data, offsets[a:b + 1], mode, grow=False)
+                keep.append(qfb)
+                order, flags = ix.prepare_slice(qfb) if with_prep else (None, None)
+                base, end = int(qfb.indptr[0]), int(qfb.indptr[qfb.n])
+                runs.append((qfb.indptr, qfb.ids[base:end] if end > base else np.zeros(0, np.uint32),
+                             qfb.tf[base:end] if end > base else np.zeros(0, np.uint32), qfb.oov, order, flags))
+                runs[-1] = (runs[-1][0] - base,) + runs[-1][1:]
+            assert ix.upload_query_runs(runs) == nq
+            s2, r2 = ix.topk_resident_host(nq, k)
+            lay2 = ix.layout()
+            for f in keep:
+                f.close()
+            np.testing.assert_array_equal(r1, r2)
+            np.testing.assert_array_equal(s1, s2)
+            assert lay2["pairs_passed_bound"] == lay1["pairs_passed_bound"], (cuts, with_prep)
+    # a slice order that is not a permutation is rejected
+    qfb = ix.vocab.featurize_packed(data, offsets[0:11], mode, grow=False)
+    order, flags = ix.prepare_slice(qfb)
+    bad = order.copy(); bad[0] = 10
+    with pytest.raises((ValueError, RuntimeError)):
+        ix.upload_query_runs([(qfb.indptr, qfb.ids, qfb.tf, qfb.oov, bad, flags), (qfb.indptr, qfb.ids, qfb.tf, qfb.oov, order, flags)])
+    qfb.close()
+
+
 def test_concurrent_score_calls(lib):
     from kakveda_b200 import SimilarityEngine, synth
 
