@@ -169,11 +169,16 @@ int kv_topk_device(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids,
 int kv_query_upload(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
                     const double *q_oov_tf2, int64_t n_q);
 /* The same upload for a batch that arrives as n_runs consecutive slices (a row-sharded GFKB featurises one slice per
- * rank and exchanges them, kakveda_b200/dist.py): per run a CSR, optionally its classification flags and its text order
- * as kv_query_prepare_slice returned them on the rank that owns the slice (all runs or none; the orders are merged
- * instead of re-sorted).  The resulting batch is identical to kv_query_upload of the concatenated CSR. */
-int kv_query_prepare_slice(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf, int64_t n_q,
-                           int32_t *order_out, uint8_t *flags_out);
+ * rank and exchanges them, kakveda_b200/dist.py).  kv_query_prepare_slice, on the rank that owns a slice, re-stores the
+ * slice's CSR in text order (s_indptr[n_q+1] zero-based, s_ids/s_tf[nnz], s_oov_tf2[n_q]; row p = the p-th smallest
+ * query, equal queries in their original order), with order_out[p] = original index of row p inside the slice and
+ * flags_out[p] its classification.  kv_query_upload_runs takes per run a CSR and -- for all runs or for none -- these
+ * orders and flags (then the rows must be stored sorted as above; the runs are merged instead of re-sorted; an order that
+ * is not a permutation or rows out of order are rejected with KV_ERR_INVALID).  The resident batch and every result are
+ * identical to kv_query_upload of the concatenated, unsorted CSR. */
+int kv_query_prepare_slice(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
+                           const double *q_oov_tf2, int64_t n_q, int64_t *s_indptr, uint32_t *s_ids, uint32_t *s_tf,
+                           double *s_oov_tf2, int32_t *order_out, uint8_t *flags_out);
 int kv_query_upload_runs(kv_index *ix, int n_runs, const int64_t *const *q_indptr, const uint32_t *const *q_ids,
                          const uint32_t *const *q_tf, const double *const *q_oov_tf2, const int32_t *const *order,
                          const uint8_t *const *flags, const int64_t *n_q);

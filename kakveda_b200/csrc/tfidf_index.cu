@@ -101,7 +101,7 @@ struct kv_index {
   PinnedBuf<int64_t> h_q_indptr;
   PinnedBuf<uint32_t> h_q_ids, h_q_tf;
   PinnedBuf<double> h_q_oov;
-  PinnedBuf<int> h_qperm;     // 2 * n_q: sorted slot -> original query, then null-query list
+  PinnedBuf<int> h_qperm;     // 3 * n_q: sorted slot -> original query, null-query list, sorted slot -> row of the staged CSR
   PinnedBuf<uint8_t> h_flags;
   DevBuf<int64_t> d_q_indptr;
   DevBuf<uint32_t> d_q_ids, d_q_tf;
@@ -700,8 +700,10 @@ struct QueryRun {
   const int64_t *indptr = nullptr;
   const uint32_t *ids = nullptr, *tf = nullptr;
   const double *oov = nullptr;
-  const int32_t *order = nullptr;   // optional: the run's queries sorted by feature-id sequence (ties by index)
-  const uint8_t *flags = nullptr;   // optional: 0 regular, 1 null, 2 irregular
+  // optional (kv_query_prepare_slice): the run's rows are stored SORTED by feature-id sequence (ties by original
+  // index) and order[p] = original index, inside the run, of the query in row p -- merging then walks memory in order
+  const int32_t *order = nullptr;
+  const uint8_t *flags = nullptr;   // optional, by row: 0 regular, 1 null, 2 irregular
   int64_t n_q = 0;
 };
 
@@ -770,28 +772,33 @@ static int prepare_batch_runs(kv_index *ix, const QueryRun *runs, int n_runs) {
   };
 
   // ---- host: pinned staging of the CSR (the runs back to back), classification, text order ----
-  KV_CUDA(ix->h_qperm.ensure(2 * n_q));
+  KV_CUDA(ix->h_qperm.ensure(3 * n_q));
   KV_CUDA(ix->h_flags.ensure(n_q));
   KV_CUDA(ix->h_q_indptr.ensure(n_q + 1));
   KV_CUDA(ix->h_q_ids.ensure(std::max<int64_t>(nnz, 1)));
   KV_CUDA(ix->h_q_tf.ensure(std::max<int64_t>(nnz, 1)));
   KV_CUDA(ix->h_q_oov.ensure(n_q));
-  for (int r = 0; r < n_runs; r++) {
+  auto stage_run = [&](int r, int Tr) {
     const QueryRun &R = runs[r];
     const int64_t base = R.indptr[0], rn = R.indptr[R.n_q] - base, q0 = qb[(size_t)r], p0 = nb[(size_t)r];
-    parallel_for(R.n_q, R.n_q >= 65536 ? T : 1, [&](int, int64_t a, int64_t b) {
+    parallel_for(R.n_q, R.n_q >= 65536 ? Tr : 1, [&](int, int64_t a, int64_t b) {
       for (int64_t q = a; q < b; q++) {
         ix->h_q_indptr.p[q0 + q] = R.indptr[q] - base + p0;
         ix->h_q_oov.p[q0 + q] = R.oov ? R.oov[q] : 0.0;
       }
     });
-    parallel_for(rn, rn >= (1 << 20) ? T : 1, [&](int, int64_t a, int64_t b) {
+    parallel_for(rn, rn >= (1 << 18) ? Tr : 1, [&](int, int64_t a, int64_t b) {
       if (b > a) {
         memcpy(ix->h_q_ids.p + p0 + a, R.ids + base + a, (size_t)(b - a) * 4);
         memcpy(ix->h_q_tf.p + p0 + a, R.tf + base + a, (size_t)(b - a) * 4);
       }
     });
-  }
+  };
+  if (n_runs == 1) stage_run(0, T);
+  else
+    parallel_for(n_runs, std::min(n_runs, T), [&](int, int64_t a, int64_t b) {
+      for (int64_t r = a; r < b; r++) stage_run((int)r, std::max(1, T / n_runs));
+    });
   ix->h_q_indptr.p[n_q] = nnz;
   const int64_t *q_indptr = ix->h_q_indptr.p;
   const uint32_t *q_ids = ix->h_q_ids.p, *q_tf = ix->h_q_tf.p;
@@ -813,38 +820,52 @@ static int prepare_batch_runs(kv_index *ix, const QueryRun *runs, int n_runs) {
   auto less_text = [&](int a, int b) {
     return cmp_seq(q_ids + q_indptr[a], q_indptr[a + 1] - q_indptr[a], q_ids + q_indptr[b], q_indptr[b + 1] - q_indptr[b]) < 0;
   };
+  std::vector<int> orig;  // row -> original query (sorted slices only; identity otherwise)
+  for (int64_t q = 0; q < n_q; q++) order[(size_t)q] = (int)q;
   if (have_order) {
-    // the runs arrive sorted: merge them (a run's queries precede the next run's, so a stable merge == the full sort)
+    // the runs arrive sorted (row p of a run is its p-th smallest query): merge them.  A run's queries precede the next
+    // run's and equal queries keep their original order inside a run, so the stable merge == the full stable sort.
+    orig.resize((size_t)n_q);
     std::vector<uint8_t> seen((size_t)n_q, 0);
     for (int r = 0; r < n_runs; r++)
       for (int64_t i = 0; i < runs[r].n_q; i++) {
         const int32_t o = runs[r].order[i];
         if (o < 0 || o >= runs[r].n_q || seen[(size_t)(qb[(size_t)r] + o)]++)
           return kv_fail(KV_ERR_INVALID, "kv_query_upload_runs: a slice order is not a permutation");
-        order[(size_t)(qb[(size_t)r] + i)] = (int)(qb[(size_t)r] + o);
+        orig[(size_t)(qb[(size_t)r] + i)] = (int)(qb[(size_t)r] + o);
       }
+    std::atomic<int> unsorted{0};
+    parallel_for(n_q - 1, n_q >= 8192 ? T : 1, [&](int, int64_t a, int64_t b) {
+      for (int64_t i = a; i < b; i++) {
+        const int x = (int)i, y = x + 1;
+        if (std::upper_bound(qb.begin(), qb.end(), (int64_t)x) != std::upper_bound(qb.begin(), qb.end(), (int64_t)y)) continue;  // run boundary
+        const int c = cmp_seq(q_ids + q_indptr[x], q_indptr[x + 1] - q_indptr[x], q_ids + q_indptr[y], q_indptr[y + 1] - q_indptr[y]);
+        if (c > 0 || (c == 0 && orig[(size_t)y] < orig[(size_t)x])) unsorted.store(1);
+      }
+    });
+    if (unsorted.load()) return kv_fail(KV_ERR_INVALID, "kv_query_upload_runs: a slice is not stored in text order");
     if (n_runs > 1) merge_sorted_runs(order, qb, less_text, T);
   } else {
-    for (int64_t q = 0; q < n_q; q++) order[(size_t)q] = (int)q;
     stable_sort_indices(order, less_text, T);  // == std::stable_sort, on all host threads
   }
   ix->last_prepare_ms[2] = ms_since(t_mark);
   t_mark = std::chrono::steady_clock::now();
-  int *qperm = ix->h_qperm.p, *null_list = qperm + n_q;
+  int *qperm = ix->h_qperm.p, *null_list = qperm + n_q, *qsrc = qperm + 2 * n_q;
   int64_t n_null = 0;
   for (int64_t i = 0; i < n_q; i++) {
-    const int64_t q = order[(size_t)i];
+    const int64_t row = order[(size_t)i], q = have_order ? orig[(size_t)row] : row;
     qperm[i] = (int)q;
-    ix->h_flags.p[i] = flag[(size_t)q];
-    if (flag[(size_t)q] == 1) {
+    qsrc[i] = (int)row;
+    ix->h_flags.p[i] = flag[(size_t)row];
+    if (flag[(size_t)row] == 1) {
       null_list[n_null++] = (int)q;
-    } else if (flag[(size_t)q] == 2) {
-      const int64_t a = q_indptr[q], b = q_indptr[q + 1];
+    } else if (flag[(size_t)row] == 2) {
+      const int64_t a = q_indptr[row], b = q_indptr[row + 1];
       ix->irr_q.push_back(q);
       ix->irr_ids.insert(ix->irr_ids.end(), q_ids + a, q_ids + b);
       ix->irr_tf.insert(ix->irr_tf.end(), q_tf + a, q_tf + b);
       ix->irr_indptr.push_back((int64_t)ix->irr_ids.size());
-      ix->irr_oov.push_back(q_oov[q]);
+      ix->irr_oov.push_back(q_oov[row]);
     }
   }
 
@@ -853,7 +874,7 @@ static int prepare_batch_runs(kv_index *ix, const QueryRun *runs, int n_runs) {
   KV_CUDA(ix->d_q_ids.ensure(std::max<int64_t>(nnz, 1)));
   KV_CUDA(ix->d_q_tf.ensure(std::max<int64_t>(nnz, 1)));
   KV_CUDA(ix->d_q_oov.ensure(n_q));
-  KV_CUDA(ix->d_qperm.ensure(2 * n_q));
+  KV_CUDA(ix->d_qperm.ensure(3 * n_q));
   KV_CUDA(ix->d_flags.ensure(n_q));
   KV_CUDA(ix->d_qconst.ensure(7 * n_q));
   KV_CUDA(ix->d_qtab.ensure(n_q * (int64_t)QTAB_BYTES));
@@ -867,7 +888,7 @@ static int prepare_batch_runs(kv_index *ix, const QueryRun *runs, int n_runs) {
     KV_CUDA(cudaMemcpyAsync(ix->d_q_tf.p, ix->h_q_tf.p, (size_t)nnz * 4, cudaMemcpyHostToDevice, s));
   }
   KV_CUDA(cudaMemcpyAsync(ix->d_q_oov.p, ix->h_q_oov.p, (size_t)n_q * 8, cudaMemcpyHostToDevice, s));
-  KV_CUDA(cudaMemcpyAsync(ix->d_qperm.p, ix->h_qperm.p, (size_t)2 * n_q * sizeof(int), cudaMemcpyHostToDevice, s));
+  KV_CUDA(cudaMemcpyAsync(ix->d_qperm.p, ix->h_qperm.p, (size_t)3 * n_q * sizeof(int), cudaMemcpyHostToDevice, s));
   KV_CUDA(cudaMemcpyAsync(ix->d_flags.p, ix->h_flags.p, (size_t)n_q, cudaMemcpyHostToDevice, s));
   KV_CUDA(cudaEventRecord(ix->ev[1], s));
   // ---- device: per-query constants and tables, per-tile rare-feature tables ----
@@ -877,7 +898,7 @@ static int prepare_batch_runs(kv_index *ix, const QueryRun *runs, int n_runs) {
   KV_CUDA(cudaMemsetAsync(ix->d_q3list.p, 0xFF, (size_t)n_q_pad * Q3CAP * sizeof(uint2), s));
   PrepParams P;
   P.q_indptr = ix->d_q_indptr.p; P.q_ids = ix->d_q_ids.p; P.q_tf = ix->d_q_tf.p; P.q_oov = ix->d_q_oov.p;
-  P.qperm = ix->d_qperm.p; P.flags = ix->d_flags.p;
+  P.qsrc = ix->d_qperm.p + 2 * n_q; P.flags = ix->d_flags.p;
   P.n_q = n_q; P.V = ix->V; P.n_total = ix->n_total;
   P.a64 = ix->d_a64.p; P.d64 = ix->d_d64.p; P.univ = ix->d_univ.p; P.utf = ix->d_utf.p; P.tfmax = ix->d_tfmax.p;
   P.q2cap = Q2CAP;
@@ -896,7 +917,7 @@ static int prepare_batch_runs(kv_index *ix, const QueryRun *runs, int n_runs) {
   ix->batch_q = n_q;
   ix->batch_tiles = n_tiles;
   ix->batch_null = n_null;
-  ix->batch_h2d_bytes = (n_q + 1) * 8 + nnz * 8 + n_q * 8 + 2 * n_q * (int64_t)sizeof(int) + n_q;
+  ix->batch_h2d_bytes = (n_q + 1) * 8 + nnz * 8 + n_q * 8 + 3 * n_q * (int64_t)sizeof(int) + n_q;
   ix->batch_valid = true;
   cudaEventElapsedTime(&ix->last_ms[0], ix->ev[0], ix->ev[1]);
   ix->last_prepare_ms[3] = ms_since(t_mark);
@@ -1222,21 +1243,42 @@ int kv_query_upload(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids
   return prepare_batch(ix, q_indptr, q_ids, q_tf, q_oov_tf2, n_q);
 }
 
-// A slice of a query batch prepared where it was featurised: its text order and its classification flags.
-int kv_query_prepare_slice(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf, int64_t n_q,
-                           int32_t *order_out, uint8_t *flags_out) {
-  if (!ix || n_q < 0 || !q_indptr || !order_out || !flags_out) return kv_fail(KV_ERR_INVALID, "kv_query_prepare_slice: bad arguments");
+// A slice of a query batch prepared where it was featurised: the slice's CSR re-stored in text order (s_* outputs, row
+// p = the p-th smallest query, equal queries in their original order), order_out[p] = original index of row p, and the
+// classification flags by row.
+int kv_query_prepare_slice(kv_index *ix, const int64_t *q_indptr, const uint32_t *q_ids, const uint32_t *q_tf,
+                           const double *q_oov_tf2, int64_t n_q, int64_t *s_indptr, uint32_t *s_ids, uint32_t *s_tf,
+                           double *s_oov_tf2, int32_t *order_out, uint8_t *flags_out) {
+  if (!ix || n_q < 0 || !q_indptr || !s_indptr || !order_out || !flags_out || !s_oov_tf2)
+    return kv_fail(KV_ERR_INVALID, "kv_query_prepare_slice: bad arguments");
   std::lock_guard<std::mutex> g(ix->mu);
   if (!ix->finalized) return kv_fail(KV_ERR_STATE, "kv_query_prepare_slice: index not finalized");
   if (n_q >= (1LL << 31) - TILE_Q || !csr_ok(q_indptr, q_ids, q_tf, n_q)) return kv_fail(KV_ERR_INVALID, "kv_query_prepare_slice: bad query CSR");
+  const int64_t nnz = q_indptr[n_q] - q_indptr[0];
+  if (nnz > 0 && (!s_ids || !s_tf)) return kv_fail(KV_ERR_INVALID, "kv_query_prepare_slice: bad arguments");
   const int T = host_threads();
-  classify_queries(ix, q_indptr, q_ids, q_tf, n_q, flags_out, T);
   std::vector<int> order((size_t)n_q);
   for (int64_t q = 0; q < n_q; q++) order[(size_t)q] = (int)q;
   stable_sort_indices(order, [&](int a, int b) {
     return cmp_seq(q_ids + q_indptr[a], q_indptr[a + 1] - q_indptr[a], q_ids + q_indptr[b], q_indptr[b + 1] - q_indptr[b]) < 0;
   }, T);
-  for (int64_t q = 0; q < n_q; q++) order_out[q] = order[(size_t)q];
+  s_indptr[0] = 0;
+  for (int64_t p = 0; p < n_q; p++) {
+    const int64_t q = order[(size_t)p];
+    s_indptr[p + 1] = s_indptr[p] + (q_indptr[q + 1] - q_indptr[q]);
+    order_out[p] = (int32_t)q;
+    s_oov_tf2[p] = q_oov_tf2 ? q_oov_tf2[q] : 0.0;
+  }
+  parallel_for(n_q, n_q >= 4096 ? T : 1, [&](int, int64_t a, int64_t b) {
+    for (int64_t p = a; p < b; p++) {
+      const int64_t q = order[(size_t)p], len = q_indptr[q + 1] - q_indptr[q];
+      if (len) {
+        memcpy(s_ids + s_indptr[p], q_ids + q_indptr[q], (size_t)len * 4);
+        memcpy(s_tf + s_indptr[p], q_tf + q_indptr[q], (size_t)len * 4);
+      }
+    }
+  });
+  classify_queries(ix, s_indptr, s_ids, s_tf, n_q, flags_out, T);
   return KV_OK;
 }
 

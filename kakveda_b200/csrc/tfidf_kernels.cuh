@@ -308,10 +308,10 @@ struct QFeat {
 };
 
 struct PrepParams {
-  const int64_t *q_indptr;  // [n_q + 1] by ORIGINAL query (device)
+  const int64_t *q_indptr;  // [n_q + 1] by row of the uploaded CSR (device)
   const uint32_t *q_ids, *q_tf;
   const double *q_oov;      // [n_q] or NULL
-  const int *qperm;         // sorted slot -> original query
+  const int *qsrc;          // sorted slot -> row of the uploaded CSR
   const uint8_t *flags;     // by sorted slot: 0 regular, 1 null (every score is 0), 2 irregular (float64 full-scan path)
   int64_t n_q, V, n_total;
   const double *a64, *d64;
@@ -334,7 +334,7 @@ __global__ void prep_queries_kernel(PrepParams P) {
   uint32_t *keys = (uint32_t *)(P.qtab + (size_t)i * QTAB_BYTES);
   QFeat *feats = (QFeat *)(keys + QKEYS);
   for (int j = 0; j < QKEYS; j++) keys[j] = KEY_EMPTY;
-  const int q = P.qperm[i];
+  const int q = P.qsrc[i];
   const double idf0 = P.jaccard ? 1.0 : (P.corpus_fit ? 0.0 : log((double)(P.n_total + 2) / 2.0) + 1.0);
   double nq = (P.q_oov ? P.q_oov[q] : 0.0) * idf0 * idf0;
   double dotU = 0.0, corrU = 0.0, corrS = 0.0;

@@ -320,7 +320,6 @@ class ShardedGfkb:
         qfb = self.vocab.featurize_packed(data, offsets[lo:hi + 1], mode, grow=False)
         try:
             t1 = time.perf_counter()
-            order, flags = self.index.prepare_slice(qfb)
             n_loc, nnz = qfb.n, int(qfb.indptr[qfb.n] - qfb.indptr[0])
             sizes = torch.tensor([n_loc, nnz], dtype=torch.int64).to(dev)
             all_sizes = torch.empty((self.world, 2), dtype=torch.int64, device=dev)
@@ -337,13 +336,11 @@ class ShardedGfkb:
                 self._xq_cap = cap
             send = self._xq_send.numpy()
             send[0:16].view(np.int64)[:] = (n_loc, nnz)
-            send[o_ip:o_ip + 8 * (n_loc + 1)].view(np.int64)[:] = qfb.indptr - qfb.indptr[0]
-            send[o_oov:o_oov + 8 * n_loc].view(np.float64)[:] = qfb.oov
-            send[o_ord:o_ord + 4 * n_loc].view(np.int32)[:] = order
-            send[o_fl:o_fl + n_loc] = flags
-            base = int(qfb.indptr[0])
-            send[o_ids:o_ids + 4 * nnz].view(np.uint32)[:] = qfb.ids[base:base + nnz]
-            send[o_tf:o_tf + 4 * nnz].view(np.uint32)[:] = qfb.tf[base:base + nnz]
+            # the slice goes out re-stored in text order, written straight into the pinned send buffer
+            self.index.prepare_slice(qfb, out=(send[o_ip:o_ip + 8 * (n_loc + 1)].view(np.int64),
+                                               send[o_ids:o_ids + 4 * nnz].view(np.uint32), send[o_tf:o_tf + 4 * nnz].view(np.uint32),
+                                               send[o_oov:o_oov + 8 * n_loc].view(np.float64),
+                                               send[o_ord:o_ord + 4 * n_loc].view(np.int32), send[o_fl:o_fl + n_loc]))
             self._xq_dsend[:slot].copy_(self._xq_send[:slot], non_blocking=True)
             dist.all_gather_into_tensor(self._xq_drecv[:slot * self.world], self._xq_dsend[:slot], group=self.group)
             self._xq_recv[:slot * self.world].copy_(self._xq_drecv[:slot * self.world], non_blocking=True)
@@ -372,6 +369,25 @@ class ShardedGfkb:
         finally:
             qfb.close()
 
+    def _read_back(self, s, r):
+        """Device results -> NumPy through two alternating pinned host buffers (a pageable ``.cpu()`` copy of the 19 MB
+        result costs 5 ms, a pinned one < 1 ms).  The returned arrays are views of those buffers: they stay valid until
+        the second-next call; copy them to keep them longer."""
+        import torch
+
+        slot = getattr(self, "_rb_slot", 0) ^ 1
+        self._rb_slot = slot
+        bufs = getattr(self, "_rb_bufs", None)
+        if bufs is None:
+            bufs = self._rb_bufs = [None, None]
+        if bufs[slot] is None or bufs[slot][0].shape != s.shape:
+            bufs[slot] = (torch.empty(s.shape, dtype=s.dtype).pin_memory(), torch.empty(r.shape, dtype=r.dtype).pin_memory())
+        hs, hr = bufs[slot]
+        hs.copy_(s, non_blocking=True)
+        hr.copy_(r, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return hs.numpy(), hr.numpy()
+
     def topk_packed(self, data, offsets: np.ndarray, k: int, mode: int = 0):
         """End-to-end step from host text: featurise, upload, scan, exchange, merge, read back.  ``last_e2e_ms`` keeps
         the wall-clock split of the last call (featurise / upload incl. table kernels / device step / read-back)."""
@@ -386,7 +402,7 @@ class ShardedGfkb:
             s, r = self.topk_resident(k)
             torch.cuda.current_stream().synchronize()
             t3 = time.perf_counter()
-            out = s.cpu().numpy(), r.cpu().numpy()
+            out = self._read_back(s, r)
             t4 = time.perf_counter()
             self.last_e2e_ms = {"prepare_sharded": 1e3 * (t2 - t0), "device_step": 1e3 * (t3 - t2), "read_back": 1e3 * (t4 - t3),
                                 "prepare_split": self.last_prepare_split_ms}
@@ -401,7 +417,7 @@ class ShardedGfkb:
 
             torch.cuda.current_stream().synchronize()
             t3 = time.perf_counter()
-            out = s.cpu().numpy(), r.cpu().numpy()
+            out = self._read_back(s, r)
             t4 = time.perf_counter()
             self.last_e2e_ms = {"featurize": 1e3 * (t1 - t0), "upload": 1e3 * (t2 - t1), "device_step": 1e3 * (t3 - t2),
                                 "read_back": 1e3 * (t4 - t3),

@@ -285,20 +285,28 @@ class GfkbIndex:
         _capi.check(_capi.load().kv_query_upload(self._h, _ptr(fb.indptr, C.c_int64), _ptr(fb.ids, C.c_uint32),
                                                  _ptr(fb.tf, C.c_uint32), _ptr(fb.oov, C.c_double), fb.n))
 
-    def prepare_slice(self, fb) -> Tuple[np.ndarray, np.ndarray]:
-        """Text order (int32 permutation) and classification flags (uint8) of a slice of a query batch; what
-        ``upload_query_runs`` merges instead of recomputing (a row-sharded GFKB prepares one slice per rank)."""
-        order = np.empty(fb.n, dtype=np.int32)
-        flags = np.empty(fb.n, dtype=np.uint8)
+    def prepare_slice(self, fb, out=None):
+        """A slice of a query batch re-stored in text order, as a run for ``upload_query_runs``: returns
+        ``(indptr, ids, tf, oov, order, flags)`` where row p is the slice's p-th smallest query, ``order[p]`` its original
+        index inside the slice and ``flags[p]`` its classification (a row-sharded GFKB prepares one slice per rank).
+        ``out``: optional preallocated arrays of the same six kinds to write into (e.g. views of a pinned buffer)."""
+        n = fb.n
+        base, end = int(fb.indptr[0]), int(fb.indptr[n])
+        nnz = end - base
+        if out is None:
+            out = (np.empty(n + 1, np.int64), np.empty(nnz, np.uint32), np.empty(nnz, np.uint32), np.empty(n, np.float64),
+                   np.empty(n, np.int32), np.empty(n, np.uint8))
+        ip, ids, tf, oov, order, flags = out
         _capi.check(_capi.load().kv_query_prepare_slice(self._h, _ptr(fb.indptr, C.c_int64), _ptr(fb.ids, C.c_uint32),
-                                                        _ptr(fb.tf, C.c_uint32), fb.n, _ptr(order, C.c_int32),
-                                                        _ptr(flags, C.c_uint8)))
-        return order, flags
+                                                        _ptr(fb.tf, C.c_uint32), _ptr(fb.oov, C.c_double), n,
+                                                        _ptr(ip, C.c_int64), _ptr(ids, C.c_uint32), _ptr(tf, C.c_uint32),
+                                                        _ptr(oov, C.c_double), _ptr(order, C.c_int32), _ptr(flags, C.c_uint8)))
+        return out
 
     def upload_query_runs(self, runs) -> int:
         """``upload_queries`` of a batch given as consecutive slices: ``runs`` is a list of
-        ``(indptr, ids, tf, oov, order, flags)`` NumPy arrays (``order``/``flags`` from ``prepare_slice``, or None for
-        all runs).  Returns the number of queries."""
+        ``(indptr, ids, tf, oov, order, flags)`` NumPy arrays: either what ``prepare_slice`` returned for every
+        slice, or plain CSR slices with ``order`` and ``flags`` None for all runs.  Returns the number of queries."""
         n = len(runs)
         arr = lambda: (C.c_void_p * n)()
         ip, ids, tf, oov, od, fl = arr(), arr(), arr(), arr(), arr(), arr()

@@ -317,11 +317,10 @@ def test_query_batch_uploaded_as_slices_equals_whole_batch(lib):
             for a, b in zip(cuts[:-1], cuts[1:]):
                 qfb = ix.vocab.featurize_packed(data, offsets[a:b + 1], mode, grow=False)
                 keep.append(qfb)
-                order, flags = ix.prepare_slice(qfb) if with_prep else (None, None)
-                base, end = int(qfb.indptr[0]), int(qfb.indptr[qfb.n])
-                runs.append((qfb.indptr, qfb.ids[base:end] if end > base else np.zeros(0, np.uint32),
-                             qfb.tf[base:end] if end > base else np.zeros(0, np.uint32), qfb.oov, order, flags))
-                runs[-1] = (runs[-1][0] - base,) + runs[-1][1:]
+                if with_prep:
+                    runs.append(ix.prepare_slice(qfb))          # rows re-stored in text order + order + flags
+                else:
+                    runs.append((qfb.indptr, qfb.ids, qfb.tf, qfb.oov, None, None))
             assert ix.upload_query_runs(runs) == nq
             s2, r2 = ix.topk_resident_host(nq, k)
             lay2 = ix.layout()
@@ -330,12 +329,15 @@ def test_query_batch_uploaded_as_slices_equals_whole_batch(lib):
             np.testing.assert_array_equal(r1, r2)
             np.testing.assert_array_equal(s1, s2)
             assert lay2["pairs_passed_bound"] == lay1["pairs_passed_bound"], (cuts, with_prep)
-    # a slice order that is not a permutation is rejected
+    # a slice order that is not a permutation, or rows that are not stored in text order, are rejected
     qfb = ix.vocab.featurize_packed(data, offsets[0:11], mode, grow=False)
-    order, flags = ix.prepare_slice(qfb)
-    bad = order.copy(); bad[0] = 10
+    run = ix.prepare_slice(qfb)
+    bad = run[4].copy(); bad[0] = bad[1]
     with pytest.raises((ValueError, RuntimeError)):
-        ix.upload_query_runs([(qfb.indptr, qfb.ids, qfb.tf, qfb.oov, bad, flags), (qfb.indptr, qfb.ids, qfb.tf, qfb.oov, order, flags)])
+        ix.upload_query_runs([run[:4] + (bad, run[5]), run])
+    ident = np.arange(qfb.n, dtype=np.int32)
+    with pytest.raises((ValueError, RuntimeError)):
+        ix.upload_query_runs([(qfb.indptr, qfb.ids, qfb.tf, qfb.oov, ident, run[5]), run])   # unsorted rows claimed sorted
     qfb.close()
 
 
