@@ -378,10 +378,9 @@ class ShardedGfkb:
         slot = getattr(self, "_rb_slot", 0) ^ 1
         self._rb_slot = slot
         bufs = getattr(self, "_rb_bufs", None)
-        if bufs is None:
-            bufs = self._rb_bufs = [None, None]
-        if bufs[slot] is None or bufs[slot][0].shape != s.shape:
-            bufs[slot] = (torch.empty(s.shape, dtype=s.dtype).pin_memory(), torch.empty(r.shape, dtype=r.dtype).pin_memory())
+        if bufs is None or bufs[0][0].shape != s.shape:   # both buffers at once: pinning memory is slow (cudaHostAlloc)
+            bufs = self._rb_bufs = [(torch.empty(s.shape, dtype=s.dtype).pin_memory(), torch.empty(r.shape, dtype=r.dtype).pin_memory())
+                                    for _ in range(2)]
         hs, hr = bufs[slot]
         hs.copy_(s, non_blocking=True)
         hr.copy_(r, non_blocking=True)
