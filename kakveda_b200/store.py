@@ -40,6 +40,37 @@ MAX_LIMIT = 32   # the fused top-k of the scan holds at most 32 rows per query a
 MAX_TF = 65535   # largest term frequency a row may hold (kv_index_append rejects more)
 MAX_FEATURES = (1 << 26) - 2  # vocabulary capacity of the scan layout (kv_index_finalize rejects more)
 PATTERN_NAME = "Citation hallucination without sources"  # services/pattern_detector/app.py:48
+AMBIGUITY_RTOL = 4e-6  # float32 scores closer than this (relative) may order differently in float64
+EXACT_SORT_MAX = 200_000  # up to this many rows the exact path orders with Python's own stable sort
+
+
+def stable_top(scores: np.ndarray, limit: int) -> List[int]:
+    """``sorted(range(n), key=lambda i: scores[i], reverse=True)[:limit]`` -- the reference's ordering
+    (services/gfkb/app.py:88-89: stable, ties keep row order) -- in O(n) for large n."""
+    n = len(scores)
+    if n <= EXACT_SORT_MAX:
+        vals = scores.tolist()
+        return sorted(range(n), key=lambda i: vals[i], reverse=True)[:limit]
+    if limit <= 0:
+        return []
+    v = np.partition(scores, n - limit)[n - limit]            # the limit-th largest score
+    above = np.flatnonzero(scores > v)                         # fewer than `limit` rows, ascending
+    ties = np.flatnonzero(scores == v)[: limit - len(above)]   # the lowest rows of the tie group fill the rest
+    idx = np.concatenate([above, ties])
+    return idx[np.lexsort((idx, -scores[idx]))].tolist()       # score descending, then row ascending
+
+
+def ambiguous_candidates(s32: np.ndarray, rows: np.ndarray, limit: int) -> np.ndarray:
+    """Per query: could a row that did NOT make a segment's float32 candidate list belong to the float64 top-``limit``?
+    Only if the list is full and its last score is within float32 rounding of its ``limit``-th score.  Exact zeros are
+    exact in both precisions (integer dot products), and equal float32 scores of identical rows are broken by row id
+    exactly like the reference's stable sort -- but two DISTINCT texts whose scores collide in float32 cannot be told
+    apart from the candidates alone, so such queries take the exact path."""
+    k = s32.shape[1]
+    full = rows[:, k - 1] >= 0
+    ref = s32[:, min(limit, k) - 1].astype(np.float64)
+    last = s32[:, k - 1].astype(np.float64)
+    return full & (last > 0.0) & (last >= ref - AMBIGUITY_RTOL * np.abs(ref))
 
 
 def check_indexable(text: str, vocab_size: int = 0) -> Optional[str]:
@@ -127,8 +158,10 @@ class GfkbStore:
         n = len(self.records)
         if n:
             texts = [self._index_text(i) for i in range(n)]
-            cached = _sidecar.load(self.sidecar_path, texts) if self.sidecar_path is not None else None
-            if cached is not None and len(self.vocab) == 0:
+            # the sidecar only serves a cold start (empty vocabulary); a compaction does not re-read and re-digest it
+            cold = self.sidecar_path is not None and len(self.vocab) == 0
+            cached = _sidecar.load(self.sidecar_path, texts) if cold else None
+            if cached is not None:
                 # cold start from the sidecar: the vocabulary and the first n0 rows come back as arrays
                 self.vocab.close()
                 self.vocab, head, n0 = cached
@@ -243,20 +276,31 @@ class GfkbStore:
             return {"ok": True, "created": created, "failure": rec}
 
     # -- match (services/gfkb/app.py:79-102) -------------------------------------------------------------------
-    def _candidates(self, fb: FeatureBatch, k: int) -> Tuple[np.ndarray, np.ndarray]:
-        """Per query: candidate rows from both segments with their float64 scores, ordered (score desc, row asc)."""
+    def _candidates(self, fb: FeatureBatch, k: int, limit: int = MATCH_LIMIT) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """Per query: candidate rows from both segments with their float64 scores, ordered (score desc, row asc), and
+        whether the candidate stage may have missed a top-``limit`` row (``ambiguous_candidates``)."""
         rows_all, f64_all = [], []
+        amb = np.zeros(fb.n, dtype=bool)
         for ix in (self._main, self._tail):
             if ix is None or ix.n_rows == 0:
                 continue
-            _, rows = ix.topk_features(fb, min(k, 32))
+            s32, rows = ix.topk_features(fb, min(k, MAX_LIMIT))
+            amb |= ambiguous_candidates(s32, rows, limit)
             rows_all.append(rows)
             f64_all.append(ix.rescore(fb, rows))
         rows = np.concatenate(rows_all, axis=1)
         f64 = np.concatenate(f64_all, axis=1)
         big = np.where(rows < 0, np.iinfo(np.int64).max, rows)
         order = np.lexsort((big, -f64), axis=1)  # last key is primary: score descending, then row ascending
-        return np.take_along_axis(rows, order, axis=1), np.take_along_axis(f64, order, axis=1)
+        return np.take_along_axis(rows, order, axis=1), np.take_along_axis(f64, order, axis=1), amb
+
+    def _exact_top(self, signature_text: str, limit: int) -> Tuple[List[int], List[float]]:
+        """Rows and float64 scores of the reference's ``sorted(..., reverse=True)[:limit]`` on the full score vector
+        (K1a on both segments): no candidate stage at all."""
+        parts = [ix.score(signature_text) for ix in (self._main, self._tail) if ix is not None and ix.n_rows]
+        scores = np.concatenate(parts)
+        order = stable_top(scores, limit)
+        return order, [float(scores[i]) for i in order]
 
     def match_batch(self, signature_texts: Sequence[str], failure_types: Optional[Sequence[Optional[str]]] = None,
                     limit: int = MATCH_LIMIT) -> List[List[dict]]:
@@ -268,14 +312,19 @@ class GfkbStore:
             self._sync()
             fb = self.vocab.featurize(list(signature_texts), grow=False)
             try:
-                rows, f64 = self._candidates(fb, max(CANDIDATES, limit))
+                rows, f64, amb = self._candidates(fb, max(CANDIDATES, limit), limit)
             finally:
                 fb.close()
             out = []
             for i in range(len(signature_texts)):
                 ft = failure_types[i] if failure_types is not None else None
                 matches = []
-                for r, s in zip(rows[i, :limit].tolist(), f64[i, :limit].tolist()):
+                if amb[i]:  # float32 candidates cannot decide this query's top rows: full float64 scan
+                    top_r, top_s = self._exact_top(signature_texts[i], limit)
+                    self.stats["exact_fallbacks"] = self.stats.get("exact_fallbacks", 0) + 1
+                else:
+                    top_r, top_s = rows[i, :limit].tolist(), f64[i, :limit].tolist()
+                for r, s in zip(top_r, top_s):
                     if r < 0:
                         continue
                     rec = self.records[r]
@@ -294,15 +343,13 @@ class GfkbStore:
             if not self.records:
                 return []
             self._sync()
-            parts = [ix.score(signature_text) for ix in (self._main, self._tail) if ix is not None and ix.n_rows]
-            scores = np.concatenate(parts).tolist()
-            order = sorted(range(len(scores)), key=lambda i: scores[i], reverse=True)[:limit]
+            order, top = self._exact_top(signature_text, limit)
             out = []
-            for i in order:
+            for i, sc in zip(order, top):
                 rec = self.records[i]
                 if failure_type and rec["failure_type"] != failure_type:
                     continue
-                out.append(_to_match(rec, scores[i]))
+                out.append(_to_match(rec, sc))
             return out
 
     # -- warn (services/warning_policy/app.py:19-72) ------------------------------------------------------------

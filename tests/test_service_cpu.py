@@ -162,14 +162,14 @@ def test_store_match_and_warn_host_logic_with_canned_candidates(golden, built_li
                 pass
         return _B()
 
-    def fake_candidates(fb, k):
+    def fake_candidates(fb, k, limit=5):
         rows, f64 = [], []
         for t in current["texts"]:
             s = by_query[t]
             order = sorted(range(len(s)), key=lambda i: s[i], reverse=True)[:k]   # stable: ties -> lower row
             rows.append(order)
             f64.append([s[i] for i in order])
-        return np.array(rows, dtype=np.int64), np.array(f64)
+        return np.array(rows, dtype=np.int64), np.array(f64), np.zeros(len(rows), dtype=bool)
 
     monkeypatch.setattr(st.vocab, "featurize", fake_featurize)
     monkeypatch.setattr(st, "_candidates", fake_candidates)
@@ -190,6 +190,89 @@ def test_store_match_and_warn_host_logic_with_canned_candidates(golden, built_li
     w = st.warn_batch([{"app_id": "a", "prompt": q}], threshold=2.0, default_action="silent")[0]
     assert w == {"action": "silent", "confidence": best["score"], "pattern_id": None, "references": [],
                  "message": "No high-similarity match found in GFKB."}
+
+
+def test_stable_top_equals_python_stable_sort(monkeypatch):
+    """store.stable_top == sorted(range(n), key=..., reverse=True)[:limit] (services/gfkb/app.py:88-89), on both of its
+    branches, with heavy ties."""
+    from kakveda_b200 import store
+
+    rng = np.random.default_rng(5)
+    for n, levels in ((1, 1), (7, 2), (300, 3), (5000, 40), (5000, 5000)):
+        scores = rng.integers(0, levels, size=n).astype(np.float64) / max(levels, 1)
+        vals = scores.tolist()
+        for limit in (1, 5, 16, 32, n, n + 3):
+            want = sorted(range(n), key=lambda i: vals[i], reverse=True)[:limit]
+            assert store.stable_top(scores, limit) == want
+            monkeypatch.setattr(store, "EXACT_SORT_MAX", 0)          # force the O(n) selection branch
+            if limit <= n:
+                assert store.stable_top(scores, limit) == want, (n, levels, limit)
+            monkeypatch.undo()
+
+
+def test_ambiguous_candidates_rule():
+    from kakveda_b200.store import ambiguous_candidates
+
+    k = 16
+    rows = np.tile(np.arange(k, dtype=np.int64), (6, 1))
+    s = np.tile(np.linspace(0.9, 0.1, k, dtype=np.float32), (6, 1))
+    s[1, :] = 0.5                      # 16 equal scores: rows beyond the list may tie into the top 5
+    s[2, 5:] = s[2, 4] * (1 - 1e-6)    # last score within float32 rounding of the 5th
+    s[3, :] = 0.0                      # exact zeros are exact in float64 too
+    rows[4, 10:] = -1; s[4, 10:] = -np.inf   # list not full: every row of the segment is a candidate
+    s[5, 5:] = s[5, 4] * (1 - 1e-4)    # clearly below the 5th
+    assert ambiguous_candidates(s, rows, 5).tolist() == [False, True, True, False, False, False]
+
+
+def test_store_match_takes_exact_path_when_float32_candidates_collide(built_lib, monkeypatch):
+    """two distinct texts, each stored more than 16 times, whose float64 scores collide in float32.
+    The float32 candidate list then holds only the group with the lower row ids; the reference's stable float64 top-5
+    (services/gfkb/app.py:88-89) is the OTHER group.  The store must notice and take the exact path."""
+    from kakveda_b200 import GfkbStore
+
+    n = 60
+    f64 = np.full(n, 0.25)
+    f64[0:20] = 0.8                    # group A, rows 0..19
+    f64[20:40] = 0.8 + 1e-9            # group B, rows 20..39: higher in float64, equal in float32
+    assert np.float32(f64[0]) == np.float32(f64[20])
+    want = sorted(range(n), key=lambda i: f64[i], reverse=True)[:5]
+    assert want == [20, 21, 22, 23, 24]
+
+    class FakeIndex:
+        n_rows = n
+
+        def topk_features(self, fb, k):
+            s32 = f64.astype(np.float32)
+            order = np.lexsort((np.arange(n), -s32))[:k]          # float32 score desc, row asc: what K1b returns
+            return np.tile(s32[order], (fb.n, 1)), np.tile(order.astype(np.int64), (fb.n, 1))
+
+        def rescore(self, fb, rows):
+            return f64[rows]
+
+        def score(self, text):
+            return f64.copy()
+
+        def close(self):
+            pass
+
+    st = GfkbStore()
+    st.records = [{"failure_id": f"F-{i:04d}", "version": 1, "failure_type": "T", "suggested_mitigation": None,
+                   "signature_text": "x"} for i in range(n)]
+    monkeypatch.setattr(st, "_sync", lambda: None)
+
+    class _B:
+        n = 2
+
+        def close(self):
+            pass
+    monkeypatch.setattr(st.vocab, "featurize", lambda texts, grow=False, n_threads=0: _B())
+    st._main = FakeIndex()
+    got = st.match_batch(["q0", "q1"])
+    assert [[m["failure_id"] for m in ms] for ms in got] == [[f"F-{i:04d}" for i in want]] * 2
+    assert [m["score"] for m in got[0]] == [f64[i] for i in want]
+    assert st.stats["exact_fallbacks"] == 2
+    assert [m["failure_id"] for m in st.match_exact("q0")] == [f"F-{i:04d}" for i in want]
+    st._main = None
 
 
 def test_store_rejects_unindexable_rows_before_persisting(tmp_path):
