@@ -747,7 +747,7 @@ static int prepare_batch_runs(kv_index *ix, const QueryRun *runs, int n_runs) {
   if (!ix->finalized) return kv_fail(KV_ERR_STATE, "kv_topk: index not finalized");
   int64_t n_q = 0, nnz = 0;
   std::vector<int64_t> qb((size_t)n_runs + 1, 0), nb((size_t)n_runs + 1, 0);
-  bool have_order = true, have_flags = true;
+  bool have_order = true, have_flags = true, any_order = false;
   for (int r = 0; r < n_runs; r++) {
     const QueryRun &R = runs[r];
     if (R.n_q < 0 || !R.indptr || !csr_ok(R.indptr, R.ids, R.tf, R.n_q)) return kv_fail(KV_ERR_INVALID, "kv_topk: bad query CSR");
@@ -757,7 +757,10 @@ static int prepare_batch_runs(kv_index *ix, const QueryRun *runs, int n_runs) {
     nb[(size_t)r + 1] = nnz;
     have_order = have_order && (R.order || R.n_q == 0);
     have_flags = have_flags && (R.flags || R.n_q == 0);
+    any_order = any_order || (R.order && R.n_q > 0);
   }
+  // a run with an order stores its rows sorted: without the orders of ALL runs the rows cannot be mapped back
+  if (any_order && !have_order) return kv_fail(KV_ERR_INVALID, "kv_query_upload_runs: slice orders must be given for all runs or for none");
   if (n_q < 1) return kv_fail(KV_ERR_INVALID, "kv_topk: empty query batch");
   if (n_q >= (1LL << 31) - TILE_Q) return kv_fail(KV_ERR_INVALID, "kv_topk: too many queries in one call");
   KV_CUDA(cudaSetDevice(ix->device));

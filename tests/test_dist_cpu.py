@@ -139,3 +139,22 @@ def test_text_range_sharding_host_side(built_lib):
     assert gather_rows(fb, np.zeros(0, dtype=np.int64)).n == 0
     with pytest.raises(ValueError):
         gather_rows(fb, np.array([fb.n], dtype=np.int64))
+
+
+def test_query_slice_exchange_layout_is_aligned_and_disjoint():
+    """Byte layout of one rank's slot in the query-slice all-gather (ShardedGfkb.upload_text_sharded): sections in
+    order, 16-byte aligned, large enough for the capacities, nothing overlapping."""
+    from kakveda_b200.dist import ShardedGfkb
+
+    for nq, nnz in ((0, 0), (1, 0), (7, 33), (12500, 560001), (100000, 4500003)):
+        o_ip, o_oov, o_ord, o_fl, o_ids, o_tf, slot = ShardedGfkb._slice_layout(nq, nnz)
+        sections = [(16, 0), (o_ip, 8 * (nq + 1)), (o_oov, 8 * nq), (o_ord, 4 * nq), (o_fl, nq), (o_ids, 4 * nnz), (o_tf, 4 * nnz)]
+        end = 0
+        for i, (off, size) in enumerate(sections):
+            if i:
+                assert off % 16 == 0 and off >= end, (nq, nnz, i)
+                end = off + size
+            else:
+                end = off
+        assert slot >= end and slot % 16 == 0
+
