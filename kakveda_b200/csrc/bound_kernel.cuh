@@ -6,24 +6,26 @@
 //     B_r + corr(q, r) >= Bmin_c + corrS_q                                  (corrS_q: every d(t) of q at its largest tf)
 // so  score(q, r) <= ub(q, c) = dot_bound / sqrt(|q|^2 (Bmin_c + corrS_q))  for every row r of c  (exact block-max
 // pruning: a chunk whose bound is below a query's k-th best score cannot hold a top-k row for it).
-//   * the sum over the NF = 256 FREQUENT features is a [128 queries x 256] x [256 x 128 chunks] fp16 GEMM (weights
-//     rounded UP to fp16, tf exact): tcgen05.mma cta_group::1 kind::f16, M = N = 128, fp32 accumulators in TMEM
+//   * the sum over the NF = 256 FREQUENT features is a [128 queries x 256] x [256 x 64 chunks] fp16 GEMM (weights
+//     rounded UP to fp16, tf exact): tcgen05.mma cta_group::1 kind::f16, M = 128, N = 64, fp32 accumulators in TMEM
 //     (double buffered), the query operand resident in shared memory for the CTA's life, the chunk operand streamed
 //     by TMA (128B swizzle, mbarrier expect_tx) -- this only computes BOUNDS; scores stay exact integer sums (K1b-S);
-//   * the next NF2 = 2048 features by chunk frequency ("second class": mid-frequency words and bigrams, each shared by
-//     many queries of a tile) are kept per 128-chunk block as TRANSPOSED presence bitmaps Ubt[feature][128 chunk bits]
-//     (32 KB, one bulk-async copy per block): a query thread reads ONE word per feature of its own list (<= 16) and has
-//     that feature's presence in its 32 chunk columns -- lane-parallel, no atomics;
+//   * the next NF2 = 1024 features by chunk frequency ("second class": mid-frequency words and bigrams, each shared by
+//     many queries of a tile) are kept per 64-chunk block as two TRANSPOSED presence bitmaps Ubt[feature][tf >= 1,
+//     tf >= 2][64 chunk bits] (16 KB, one bulk-async copy per block, double buffered): a query thread reads ONE word per
+//     feature of its own list (<= Q2CAP) and has that feature's presence in its 16 chunk columns -- no atomics;
 //   * the remaining RARE features are joined the other way round: every 64-chunk block carries (built at finalize) a
 //     presence bitmap and an open-addressing table of its rare features (feature -> mask of the block's chunks holding
 //     it, largest tf); each query looks ITS OWN <= 32 rare features up -- one shared-memory bit test per (query,
 //     feature, block), and only on a hit a probe of the block's table in L2 -- and adds weight x tf into
 //     R[chunk][query] (shared memory).  1.8k bit tests per tile and block instead of 5.4k entry probes;
-//   * epilogue (16 warps, thread = query, tcgen05.ld of 32 chunk columns): bound vs the query's threshold.
-//     pass 0 keeps, per thread, the 4 best chunks by bound (seeds: K1b-S scores them first, which gives every query a
-//     close lower bound theta0 of its k-th best score); pass 1 appends {chunk, mask of the group's surviving queries}
-//     to the scan group's candidate list (paged pool) for every chunk with ub >= theta0.
-// One CTA = one 128-query tile x one range of 128-chunk blocks; 18 warps: 16 workers (join + epilogue), TMA, MMA.
+//   * epilogue (16 warps, four threads per query, tcgen05.ld of 16 chunk columns each): bound vs the query's threshold.
+//     pass 0 keeps, per thread, the 4 best chunks by bound (16 seeds per query: K1b-S scores them first, which gives
+//     every query a close lower bound theta0 of its k-th best score) and stores every bound as an 8-bit code rounded up
+//     (the selection kernel below builds the candidate lists from the codes); pass 1 (only when the codes do not fit in
+//     memory) recomputes the bounds and appends {chunk, mask of the group's surviving queries} to the scan group's
+//     candidate list (paged pool) for every chunk with ub >= theta0.
+// One CTA = one 128-query tile x one range of 64-chunk blocks; 18 warps: 16 workers (join + epilogue), TMA, MMA.
 #pragma once
 #include "tfidf_kernels.cuh"
 

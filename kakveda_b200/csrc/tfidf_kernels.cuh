@@ -40,7 +40,7 @@ namespace kvk {
 
 constexpr int CHUNK_ROWS = 32;
 constexpr int NF = 256;   // features evaluated densely (tensor cores) by the bound kernel
-constexpr int NF2 = 1024; // the next most frequent features: per 128-chunk block two transposed bitmaps [NF2][tf >= 1, tf >= 2][128 bits]
+constexpr int NF2 = 1024; // the next most frequent features: per 64-chunk block two transposed bitmaps [NF2][tf >= 1, tf >= 2][64 bits]
 constexpr int Q2CAP = 24; // features of that class a query keeps in its own list (further ones are treated as rare)
 constexpr uint32_t FID_BITS = 26;
 constexpr uint32_t FID_MASK = (1u << FID_BITS) - 1;
