@@ -97,6 +97,14 @@ __device__ __forceinline__ void mbar_wait_idle(uint64_t *bar, uint32_t parity) {
   }
 }
 
+// MUFU.RSQ without the denormal pre-/post-scaling rsqrtf() carries (the argument is |q|^2 x a row norm: far from denormal;
+// for normal arguments the result is the same bit pattern)
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void umma_commit_1(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
@@ -154,9 +162,16 @@ struct __align__(1024) BoundSmem {
 
 static inline size_t bound_smem_bytes(int max_pages) { return sizeof(BoundSmem) + (size_t)4 * max_pages * sizeof(int) + 1024; }
 
+// FAST = the configuration of the headline path fixed at compile time (pass 0 with bound codes, TF-IDF cosine, no test
+// hook): the epilogue then holds no uniform branches, parameter reloads or dead variants.  FAST = false is the same code
+// with those four switches read from the parameters.
+template <bool FAST>
 __global__ void __launch_bounds__(B_THREADS, 1)
 tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_u, BoundParams P) {
   extern __shared__ unsigned char smem_raw[];
+  const int pass = FAST ? 0 : P.pass;
+  const bool jacc = FAST ? false : (P.jaccard != 0);
+  const bool has_codes = FAST ? true : (P.ubq != nullptr);
   // 1024-byte alignment by an OFFSET into the shared array (not by rounding a generic pointer): the compiler keeps
   // the shared address space, so every access below is LDS/STS/ATOMS instead of a generic load / store / atomic
   BoundSmem &S = *reinterpret_cast<BoundSmem *>(smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u));
@@ -306,9 +321,9 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       if (threadIdx.x < B_BN) S.minB[as][threadIdx.x] = P.chunk_minB[c0 + threadIdx.x];
       // this block's threshold of the query (pass 1: theta0 from the seed scan, possibly raised by peers meanwhile)
       float tq = 0.f;
-      if (P.pass == 1 && q_ok) {
+      if (pass == 1 && q_ok) {
         const float th = __int_as_float(__ldcg(&P.gthr[slot]));
-        if (th > 0.f) tq = P.jaccard ? th / PRUNE_SLACK : th * th * nq / (PRUNE_SLACK * PRUNE_SLACK);
+        if (th > 0.f) tq = jacc ? th / PRUNE_SLACK : th * th * nq / (PRUNE_SLACK * PRUNE_SLACK);
       }
       asm volatile("bar.sync 1, 512;" ::: "memory");
       // ---- epilogue, thread = query, B_COLS chunk columns: rare part (R) + second-class part (bitmaps) + frequent
@@ -362,25 +377,26 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       const float *mb = &S.minB[as][cs * B_COLS];
       const int64_t cbase = c0 + cs * B_COLS;
       uint32_t mymask = 0;
-      const bool dbg = P.dbg_xs != nullptr;
+      const bool dbg = FAST ? false : (P.dbg_xs != nullptr);
+      const int nv = (int)min((int64_t)B_COLS, P.n_chunks - cbase);  // chunk columns of this thread that exist
       uint32_t codes[B_COLS / 4];
 #pragma unroll
       for (int j = 0; j < B_COLS / 4; j++) codes[j] = 0;
 #pragma unroll
       for (int j = 0; j < B_COLS; j++) {
         const float xs = base + __uint_as_float(v[j]) + x[j];
-        const bool c_ok = cbase + j < P.n_chunks;
+        const bool c_ok = j < nv;
         if (dbg && q_in && c_ok) P.dbg_xs[(size_t)slot * P.dbg_stride + cbase + j] = xs;
-        const float den = P.jaccard ? (nq + mb[j] - xs) : (mb[j] + corrS);
-        if (P.pass == 1) {
-          const float lhs = P.jaccard ? xs : xs * xs;
+        const float den = jacc ? (nq + mb[j] - xs) : (mb[j] + corrS);
+        if (pass == 1) {
+          const float lhs = jacc ? xs : xs * xs;
           const bool sv = q_ok && c_ok && (tq <= 0.f || den <= 0.f || lhs >= tq * den);
           const uint32_t m = __ballot_sync(FULL, sv);
           if (lane == j) mymask = m;
         } else if (q_ok && c_ok) {
           // the bound itself (slack included): seeds are ranked by it, and it is stored as a code that only errs upwards
-          float metric = den > 0.f ? (P.jaccard ? __fdividef(xs, den) : xs * rsqrtf(nq * den)) * (PRUNE_SLACK * 1.00001f) : INFINITY;
-          if (P.ubq) codes[j >> 2] |= (uint32_t)fminf(255.f, ceilf(metric * UBQ_SCALE)) << ((j & 3) * 8);
+          float metric = den > 0.f ? (jacc ? __fdividef(xs, den) : xs * rsqrt_approx(nq * den)) * (PRUNE_SLACK * 1.00001f) : INFINITY;
+          if (has_codes) codes[j >> 2] |= (uint32_t)fminf(255.f, ceilf(metric * UBQ_SCALE)) << ((j & 3) * 8);
           if (metric > sm[B_SEEDS - 1]) {
             int cc = (int)(cbase + j);
 #pragma unroll
@@ -392,9 +408,9 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
           }
         }
       }
-      if (P.pass == 0 && P.ubq && q_in)
+      if (pass == 0 && has_codes && q_in)
         *reinterpret_cast<uint4 *>(P.ubq + (size_t)slot * P.ubq_stride + cbase) = make_uint4(codes[0], codes[1], codes[2], codes[3]);
-      if (P.pass == 1) {
+      if (pass == 1) {
         // lanes holding a non-empty mask append {chunk, mask} to the group's list (warp-aggregated; four warps share
         // a list; the warp whose range crosses into a new page allocates it)
         const uint32_t am = __ballot_sync(FULL, mymask != 0);
@@ -428,7 +444,7 @@ tfidf_bound_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       }
       asm volatile("bar.sync 1, 512;" ::: "memory");  // R is clean again and every reader of this block's side data is done
     }
-    if (P.pass == 0) {
+    if (pass == 0) {
       if (q_in) {
         int *o = P.seeds + ((size_t)slot * P.n_bsplits + bsplit) * B_SEEDS_PER_QUERY + cs * B_SEEDS;
 #pragma unroll

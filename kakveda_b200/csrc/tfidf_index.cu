@@ -1015,7 +1015,8 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r, in
   static bool attr_set[64] = {false};
   if (!attr_set[ix->device & 63]) {
     KV_CUDA(cudaFuncSetAttribute(tfidf_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(32)));
-    KV_CUDA(cudaFuncSetAttribute(tfidf_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    KV_CUDA(cudaFuncSetAttribute(tfidf_bound_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    KV_CUDA(cudaFuncSetAttribute(tfidf_bound_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set[ix->device & 63] = true;
   }
   if (prune && bound_smem_bytes(max_pages) > 232448)
@@ -1070,7 +1071,11 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r, in
         // pass 0: seeds
         KV_CUDA(cudaEventRecord(ix->evk[0], s));
         BP.pass = 0;
-        tfidf_bound_kernel<<<bgrid, B_THREADS, b_smem, s>>>(ix->map_w, ix->map_u, BP);
+        // the headline configuration (bound codes kept, TF-IDF cosine, no test hook) runs the specialised instantiation
+        if (BP.ubq && !BP.jaccard && !BP.dbg_xs && !getenv("KAKVEDA_B200_GENERIC_BOUND"))
+          tfidf_bound_kernel<true><<<bgrid, B_THREADS, b_smem, s>>>(ix->map_w, ix->map_u, BP);
+        else
+          tfidf_bound_kernel<false><<<bgrid, B_THREADS, b_smem, s>>>(ix->map_w, ix->map_u, BP);
         KV_CUDA(cudaGetLastError());
         seeds_to_lists_kernel<<<(unsigned)((n_groups * GROUP_Q * n_seed + 255) / 256), 256, 0, s>>>(ix->d_seeds.p, n_q, n_seed,
                                                                                                    ix->d_direct.p, ix->d_list_count.p);
@@ -1106,7 +1111,7 @@ static int run_batch(kv_index *ix, int k, float *d_out_s, long long *d_out_r, in
         tfidf_select_kernel<<<dim3((unsigned)n_groups, (unsigned)n_bsplits), SEL_WARPS * 32, (size_t)max_pages * sizeof(int), s>>>(LP);
       } else {
         BP.pass = 1;
-        tfidf_bound_kernel<<<bgrid, B_THREADS, b_smem, s>>>(ix->map_w, ix->map_u, BP);
+        tfidf_bound_kernel<false><<<bgrid, B_THREADS, b_smem, s>>>(ix->map_w, ix->map_u, BP);
       }
       KV_CUDA(cudaGetLastError());
       KV_CUDA(cudaEventRecord(ix->evk[3], s));
