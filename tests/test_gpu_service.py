@@ -50,7 +50,9 @@ def test_store_replays_reference_upserts_and_matches(lib, golden, tmp_path):
     assert st0.stats["stat_refreshes"] == 0
     for a, b in zip(seen, seen0):
         assert [(x[0], x[1]) for x in a] == [(x[0], x[1]) for x in b]
-        np.testing.assert_allclose([x[2] for x in a], [x[2] for x in b], rtol=1e-13)
+        # a score may come from K6 (candidate path) in one store and from K1a (exact path) in the other: both float64, they
+        # agree to 1e-13 (test_rescore_is_float64_and_ties_exactly); one decade of slack on top
+        np.testing.assert_allclose([x[2] for x in a], [x[2] for x in b], rtol=1e-12)
     # a store opened on the written file serves the same matches (cold start: one full build)
     from kakveda_b200 import GfkbStore
     st2 = GfkbStore(path=st.path)
